@@ -1,0 +1,284 @@
+// Batched fixed-base Pippenger MSM for the Groth16 prover.
+//
+// The bases of a proving key never change, so every base is expanded once into its 16 window
+// multiples 2^(16 j) P (affine).  A 254-bit scalar then contributes 16 signed 16-bit digits that all
+// land in ONE set of 2^15 buckets:  sum_k s_k P_k = sum_b (b+1) * B_b,
+// B_b = sum of +-2^(16 j) P_k over the (k, j) whose |digit| is b+1.  Per batch item:
+//   1. digits + counting sort of (k, j) by bucket      (k_digits<false>, k_scan, k_digits<true>)
+//   2. one thread per bucket sums its list in XYZZ     (k_accumulate) - the IMAD-bound bulk
+//   3. weighted bucket reduction, running sums over chunks of 32, then a warp (k_reduce1/2)
+// A/B1/B2/C share the witness as scalars, so they share one sort; bases at infinity ((0,0)) are
+// skipped by the mixed add.  Integer pipe (IMAD.WIDE carry chains) only - no tensor-core work here.
+#include "msm.cuh"
+
+namespace zkb {
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+static constexpr int RED_CHUNK = 32;
+static constexpr int RED_PARTS = MSM_BUCKETS / RED_CHUNK;   // 1024
+
+template <class T>
+__device__ __forceinline__ T ldg_pod(const T *p) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte multiples");
+  T r;
+  const uint4 *s = reinterpret_cast<const uint4 *>(p);
+  uint4 *d = reinterpret_cast<uint4 *>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+  return r;
+}
+template <class T>
+__device__ __forceinline__ void stg_pod(T *p, const T &v) {
+  const uint4 *s = reinterpret_cast<const uint4 *>(&v);
+  uint4 *d = reinterpret_cast<uint4 *>(p);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// table build
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__global__ void k_table(Affine<F> *tab, const Affine<F> *bases, uint32_t n) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  Affine<F> p = ldg_pod(bases + k);
+  XYZZ<F> acc = XYZZ<F>::from_affine(p);
+  for (int j = 0; j < MSM_WINDOWS; j++) {
+    Affine<F> a;
+    xyzz_to_affine_ni(&acc, &a);
+    stg_pod(tab + (size_t)j * n + k, a);
+    if (j + 1 < MSM_WINDOWS)
+      for (int i = 0; i < MSM_C; i++) xyzz_dbl_ni(&acc);
+  }
+}
+
+template <class F>
+cudaError_t msm_build_table(MsmTable<F> &t, const Affine<F> *bases, uint32_t n, cudaStream_t st) {
+  t.n = n;
+  CK(cudaMalloc(&t.tab, (size_t)n * MSM_WINDOWS * sizeof(Affine<F>)));
+  k_table<F><<<(n + 63) / 64, 64, 0, st>>>(t.tab, bases, n);
+  return cudaGetLastError();
+}
+template cudaError_t msm_build_table<Fq>(MsmTable<Fq> &, const Affine<Fq> *, uint32_t, cudaStream_t);
+template cudaError_t msm_build_table<Fq2>(MsmTable<Fq2> &, const Affine<Fq2> *, uint32_t, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// digits + counting sort
+// ---------------------------------------------------------------------------------------------
+template <bool SCATTER>
+__global__ void k_digits(const Fr *scalars, size_t scalar_stride, uint32_t n, uint32_t *counts_or_cursor,
+                         uint32_t *entries) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t b = blockIdx.y;
+  if (k >= n) return;
+  const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + (size_t)b * scalar_stride + k);
+  uint4 lo = sp[0], hi = sp[1];
+  uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  uint32_t *cc = counts_or_cursor + (size_t)b * MSM_BUCKETS;
+  uint32_t *ent = entries + (size_t)b * n * MSM_WINDOWS;
+  uint32_t carry = 0;
+#pragma unroll
+  for (int j = 0; j < MSM_WINDOWS; j++) {
+    uint32_t v = ((w[j >> 1] >> (16 * (j & 1))) & 0xffffu) + carry;
+    uint32_t neg = v > (uint32_t)MSM_BUCKETS;        // v in [0, 65536]
+    uint32_t mag = neg ? 65536u - v : v;             // |digit| in [0, 32768]
+    carry = neg;
+    if (mag) {
+      if (SCATTER) {
+        uint32_t pos = atomicAdd(cc + (mag - 1), 1u);
+        ent[pos] = ((uint32_t)j * n + k) | (neg << 31);
+      } else {
+        atomicAdd(cc + (mag - 1), 1u);
+      }
+    }
+  }
+}
+
+// offsets[b][0..BUCKETS] = exclusive scan of counts[b]; cursor[b] = offsets[b][0..BUCKETS)
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor) {
+  __shared__ uint32_t warp_tot[32];
+  uint32_t b = blockIdx.x, t = threadIdx.x;
+  const uint32_t *c = counts + (size_t)b * MSM_BUCKETS + t * 32;
+  uint32_t loc[32], sum = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) { loc[i] = sum; sum += c[i]; }
+  // block exclusive scan of `sum`
+  uint32_t x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if ((t & 31) >= d) x += y;
+  }
+  if ((t & 31) == 31) warp_tot[t >> 5] = x;
+  __syncthreads();
+  if (t < 32) {
+    uint32_t v = warp_tot[t], z = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, z, d);
+      if (t >= d) z += y;
+    }
+    warp_tot[t] = z - v;
+  }
+  __syncthreads();
+  uint32_t base = warp_tot[t >> 5] + x - sum;
+  uint32_t *o = offsets + (size_t)b * (MSM_BUCKETS + 1) + t * 32;
+  uint32_t *cu = cursor + (size_t)b * MSM_BUCKETS + t * 32;
+#pragma unroll
+  for (int i = 0; i < 32; i++) { o[i] = base + loc[i]; cu[i] = base + loc[i]; }
+  if (t == 1023) offsets[(size_t)b * (MSM_BUCKETS + 1) + MSM_BUCKETS] = base + sum;
+}
+
+cudaError_t MsmSort::alloc(uint32_t n_, uint32_t batch_) {
+  n = n_;
+  batch = batch_;
+  CK(cudaMalloc(&counts, (size_t)batch * MSM_BUCKETS * 4));
+  CK(cudaMalloc(&offsets, (size_t)batch * (MSM_BUCKETS + 1) * 4));
+  CK(cudaMalloc(&cursor, (size_t)batch * MSM_BUCKETS * 4));
+  CK(cudaMalloc(&entries, (size_t)batch * n * MSM_WINDOWS * 4));
+  return cudaSuccess;
+}
+void MsmSort::free_all() {
+  cudaFree(counts); cudaFree(offsets); cudaFree(cursor); cudaFree(entries);
+  counts = offsets = cursor = entries = nullptr;
+}
+cudaError_t MsmSort::run(const Fr *scalars, size_t scalar_stride, uint32_t nbatch, cudaStream_t st) {
+  if (nbatch > batch) return cudaErrorInvalidValue;
+  CK(cudaMemsetAsync(counts, 0, (size_t)nbatch * MSM_BUCKETS * 4, st));
+  dim3 grid((n + 255) / 256, nbatch);
+  k_digits<false><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, counts, nullptr);
+  k_scan<<<nbatch, 1024, 0, st>>>(counts, offsets, cursor);
+  k_digits<true><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cursor, entries);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// bucket accumulation: thread = (bucket, table, batch item)
+// ---------------------------------------------------------------------------------------------
+template <class F>
+struct TablePtrs { const Affine<F> *tab[4]; };
+
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_accumulate(TablePtrs<F> tabs, int ntab, uint32_t n,
+                                                        const uint32_t *__restrict__ offsets,
+                                                        const uint32_t *__restrict__ entries, XYZZ<F> *buckets) {
+  uint32_t bucket = blockIdx.x * THREADS + threadIdx.x;
+  uint32_t t = blockIdx.y, b = blockIdx.z;
+  const Affine<F> *tab = tabs.tab[t];
+  const uint32_t *off = offsets + (size_t)b * (MSM_BUCKETS + 1);
+  const uint32_t *ent = entries + (size_t)b * n * MSM_WINDOWS;
+  uint32_t beg = off[bucket], end = off[bucket + 1];
+  XYZZ<F> acc = XYZZ<F>::infinity();
+  for (uint32_t e = beg; e < end; e++) {
+    uint32_t x = ent[e];
+    Affine<F> p = ldg_pod(tab + (x & 0x7fffffffu));
+    if (x >> 31) p.y = p.y.neg();
+    acc.add_affine(p);
+  }
+  stg_pod(buckets + ((size_t)(b * ntab + t) * MSM_BUCKETS + bucket), acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bucket reduction  sum_i (i+1) B_i
+// ---------------------------------------------------------------------------------------------
+// level 1: thread = chunk of 32 buckets:  R = sum (u+1) B[32t+u],  S = sum B[32t+u]
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_reduce1(const XYZZ<F> *buckets, XYZZ<F> *part_r, XYZZ<F> *part_s) {
+  uint32_t t = blockIdx.x * THREADS + threadIdx.x;   // chunk
+  uint32_t slot = blockIdx.y;
+  const XYZZ<F> *B = buckets + (size_t)slot * MSM_BUCKETS + (size_t)t * RED_CHUNK;
+  XYZZ<F> run = XYZZ<F>::infinity(), acc = XYZZ<F>::infinity();
+  for (int u = RED_CHUNK - 1; u >= 0; u--) {
+    XYZZ<F> x = ldg_pod(B + u);
+    xyzz_add_ni(&run, &x);
+    xyzz_add_ni(&acc, &run);
+  }
+  stg_pod(part_r + (size_t)slot * RED_PARTS + t, acc);
+  stg_pod(part_s + (size_t)slot * RED_PARTS + t, run);
+}
+
+// level 2: one warp per slot.  total = sum_t R_t + 32 * sum_t t * S_t
+template <class F>
+__global__ void __launch_bounds__(32) k_reduce2(const XYZZ<F> *part_r, const XYZZ<F> *part_s, XYZZ<F> *out) {
+  __shared__ XYZZ<F> sh_r[32], sh_sig[32], sh_rho[32];
+  uint32_t slot = blockIdx.x, l = threadIdx.x;
+  const XYZZ<F> *R = part_r + (size_t)slot * RED_PARTS + l * 32;
+  const XYZZ<F> *S = part_s + (size_t)slot * RED_PARTS + l * 32;
+  XYZZ<F> r = XYZZ<F>::infinity(), x;
+  for (int u = 0; u < 32; u++) {
+    x = ldg_pod(R + u);
+    xyzz_add_ni(&r, &x);
+  }
+  XYZZ<F> run = XYZZ<F>::infinity(), rho = XYZZ<F>::infinity();
+  for (int u = 31; u >= 1; u--) {
+    x = ldg_pod(S + u);
+    xyzz_add_ni(&run, &x);
+    xyzz_add_ni(&rho, &run);      // rho = sum_u u * S_u
+  }
+  x = ldg_pod(S);
+  xyzz_add_ni(&run, &x);          // sigma = sum_u S_u
+  sh_r[l] = r;
+  sh_sig[l] = run;
+  sh_rho[l] = rho;
+  __syncwarp();
+  if (l == 0) {
+    XYZZ<F> rt = XYZZ<F>::infinity(), pt = XYZZ<F>::infinity();
+    for (int i = 0; i < 32; i++) { xyzz_add_ni(&rt, &sh_r[i]); xyzz_add_ni(&pt, &sh_rho[i]); }
+    XYZZ<F> run2 = XYZZ<F>::infinity(), lt = XYZZ<F>::infinity();
+    for (int i = 31; i >= 1; i--) {
+      xyzz_add_ni(&run2, &sh_sig[i]);
+      xyzz_add_ni(&lt, &run2);    // lt = sum_l l * sigma_l
+    }
+    for (int i = 0; i < 5; i++) xyzz_dbl_ni(&lt);  // * 32
+    xyzz_add_ni(&lt, &pt);                         // sum_t t * S_t
+    for (int i = 0; i < 5; i++) xyzz_dbl_ni(&lt);  // * 32 (chunk size)
+    xyzz_add_ni(&lt, &rt);
+    stg_pod(out + slot, lt);
+  }
+}
+
+template <class F>
+cudaError_t MsmWork<F>::alloc(uint32_t slots_) {
+  slots = slots_;
+  CK(cudaMalloc(&buckets, (size_t)slots * MSM_BUCKETS * sizeof(XYZZ<F>)));
+  CK(cudaMalloc(&part_r, (size_t)slots * RED_PARTS * sizeof(XYZZ<F>)));
+  CK(cudaMalloc(&part_s, (size_t)slots * RED_PARTS * sizeof(XYZZ<F>)));
+  return cudaSuccess;
+}
+template <class F>
+void MsmWork<F>::free_all() {
+  cudaFree(buckets); cudaFree(part_r); cudaFree(part_s);
+  buckets = part_r = part_s = nullptr;
+}
+template struct MsmWork<Fq>;
+template struct MsmWork<Fq2>;
+
+template <class F> struct AccCfg;
+template <> struct AccCfg<Fq> { static constexpr int THREADS = 128; static constexpr int RED_THREADS = 64; };
+template <> struct AccCfg<Fq2> { static constexpr int THREADS = 64; static constexpr int RED_THREADS = 32; };
+
+template <class F>
+cudaError_t msm_run(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
+                    XYZZ<F> *out, cudaStream_t st) {
+  if (ntab < 1 || ntab > 4 || nbatch * (uint32_t)ntab > work.slots) return cudaErrorInvalidValue;
+  TablePtrs<F> tp;
+  for (int i = 0; i < 4; i++) tp.tab[i] = i < ntab ? tables[i].tab : nullptr;
+  for (int i = 0; i < ntab; i++)
+    if (tables[i].n != sort.n) return cudaErrorInvalidValue;
+  constexpr int TH = AccCfg<F>::THREADS, RT = AccCfg<F>::RED_THREADS;
+  dim3 grid(MSM_BUCKETS / TH, ntab, nbatch);
+  k_accumulate<F, TH><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.offsets, sort.entries, work.buckets);
+  uint32_t slots = nbatch * ntab;
+  dim3 g1(RED_PARTS / RT, slots);
+  k_reduce1<F, RT><<<g1, RT, 0, st>>>(work.buckets, work.part_r, work.part_s);
+  k_reduce2<F><<<slots, 32, 0, st>>>(work.part_r, work.part_s, out);
+  return cudaGetLastError();
+}
+template cudaError_t msm_run<Fq>(const MsmSort &, const MsmTable<Fq> *, int, uint32_t, MsmWork<Fq> &, XYZZ<Fq> *,
+                                 cudaStream_t);
+template cudaError_t msm_run<Fq2>(const MsmSort &, const MsmTable<Fq2> *, int, uint32_t, MsmWork<Fq2> &, XYZZ<Fq2> *,
+                                  cudaStream_t);
+
+}  // namespace zkb

@@ -1,0 +1,277 @@
+// Fr NTT kernels for the QAP quotient: radix-2 stages grouped into passes of up to
+// 9 stages; each pass stages a 2048-element tile (64 KiB, limb-planar) in shared memory, runs its
+// butterflies there and makes exactly one coalesced HBM read and one HBM write of the vector.
+//
+//   inverse transform = decimation-in-frequency passes (natural in -> bit-reversed out)
+//   forward transform = decimation-in-time passes     (bit-reversed in -> natural out)
+// so the prover's iNTT -> coset shift -> NTT chain needs no permutation pass: the shift table is
+// indexed by the bit-reversed position and the H-MSM consumes the natural-order result.
+//
+// Roots are snarkjs' / ptau's: omega_{2^28} = 5^((r-1)/2^28), omega_{2^k} by repeated squaring.
+#include "ntt.cuh"
+#include <cstdio>
+
+namespace zkb {
+
+static constexpr int TILE_LOG = 11;
+static constexpr int TILE = 1 << TILE_LOG;      // elements per CTA tile
+static constexpr int NTT_THREADS = 256;
+
+// omega_{2^28} in Montgomery form
+__device__ __constant__ uint32_t OMEGA28[8] = {0x80d13d9cu, 0x636e7355u, 0x2445ffd6u, 0xa22bf374u,
+                                              0x1eb203d8u, 0x56452ac0u, 0x2963f9e7u, 0x1860ef94u};
+
+// pw[k] = base^(2^k), k < 32 ; out[e] = base^e for e < count (square-and-multiply over pw)
+__global__ void k_powers(Fr *out, const Fr *pw, size_t count, Fr lead) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  Fr acc = lead;
+  size_t x = e;
+  for (int k = 0; x; k++, x >>= 1)
+    if (x & 1) acc = acc * pw[k];
+  out[e] = acc;
+}
+
+// pw[k] = g^(2^k) where g = omega_{2^logn} (inverse ? g^-1 : g)
+__global__ void k_root_powers(Fr *pw, int logn, int inverse, Fr *ninv_out) {
+  if (threadIdx.x || blockIdx.x) return;
+  Fr g;
+  for (int i = 0; i < 8; i++) g.v[i] = OMEGA28[i];
+  for (int i = 28; i > logn; i--) g = g.sqr();
+  if (inverse) g = g.inv();
+  for (int k = 0; k < 32; k++) {
+    pw[k] = g;
+    g = g.sqr();
+  }
+  if (ninv_out) {
+    // 2^-logn
+    Fr two = Fr::one() + Fr::one(), t = Fr::one();
+    for (int i = 0; i < logn; i++) t = t * two;
+    *ninv_out = t.inv();
+  }
+}
+
+// scale[p] = ninv * inc^(bitrev_logn(p))   (coset shift applied to a bit-reversed coefficient vector)
+__global__ void k_coset_scale(Fr *out, const Fr *pw_inc, const Fr *ninv, int logn) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >> logn) return;
+  uint32_t e = __brev((uint32_t)p) >> (32 - logn);
+  Fr acc = *ninv;
+  for (int k = 0; e; k++, e >>= 1)
+    if (e & 1) acc = acc * pw_inc[k];
+  out[p] = acc;
+}
+
+__device__ __forceinline__ Fr lds_fr(const uint32_t *sm, int idx) {
+  Fr r;
+#pragma unroll
+  for (int l = 0; l < 8; l++) r.v[l] = sm[l * TILE + idx];
+  return r;
+}
+__device__ __forceinline__ void sts_fr(uint32_t *sm, int idx, const Fr &x) {
+#pragma unroll
+  for (int l = 0; l < 8; l++) sm[l * TILE + idx] = x.v[l];
+}
+__device__ __forceinline__ Fr ldg_fr(const Fr *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = q[0], b = q[1];
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void stg_fr(Fr *p, const Fr &x) {
+  uint4 *q = reinterpret_cast<uint4 *>(p);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+
+// One pass over stage bits [lo, hi) of a 2^logn transform on `nvec` vectors laid `vec_stride`
+// elements apart.  DIF=true: stages hi-1 .. lo with (u,v) -> (u+v, (u-v)w).  DIF=false (DIT):
+// stages lo .. hi-1 with (u,v) -> (u+vw, u-vw).  tw[e] = omega_N^e (or its inverse), e < N/2.
+// `scale` (optional) multiplies the element stored at position p by scale[p].
+template <bool DIF>
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr *data, size_t vec_stride, int logn, int lo, int hi,
+                                                           const Fr *__restrict__ tw, const Fr *__restrict__ scale) {
+  extern __shared__ uint32_t sm[];
+  const int rows_log = hi - lo, rows = 1 << rows_log;
+  const int G = TILE >> rows_log;                    // groups per tile (columns or chunks)
+  const bool col = lo > 0;
+  Fr *vec = data + (size_t)blockIdx.y * vec_stride;
+  const int tile = blockIdx.x;
+  // tile -> (hi_idx, low_grp)
+  size_t base;
+  int low0 = 0;                                       // low bits (below lo) of group 0's index
+  if (col) {
+    int low_groups = (1 << lo) / G;
+    int hi_idx = tile / low_groups, low_grp = tile % low_groups;
+    low0 = low_grp * G;
+    base = ((size_t)hi_idx << hi) + low0;
+  } else {
+    base = (size_t)tile * TILE;
+  }
+  // ---- load -----------------------------------------------------------------------------
+  for (int i = threadIdx.x; i < TILE; i += NTT_THREADS) {
+    int k, g;
+    size_t addr;
+    int sidx;
+    if (col) { g = i % G; k = i / G; addr = base + ((size_t)k << lo) + g; sidx = k * G + g; }
+    else { k = i % rows; g = i / rows; addr = base + (size_t)g * rows + k; sidx = g * rows + k; }
+    sts_fr(sm, sidx, ldg_fr(vec + addr));
+  }
+  __syncthreads();
+  const int stride = col ? G : 1;
+  // ---- butterflies ----------------------------------------------------------------------
+  for (int st = 0; st < rows_log; st++) {
+    const int sb = DIF ? (rows_log - 1 - st) : st;    // bit (within the tile rows) of this stage
+    const int s = lo + sb;                            // global stage: half distance 2^s
+    const int d = 1 << sb;
+    for (int b = threadIdx.x; b < TILE / 2; b += NTT_THREADS) {
+      int kk, g;
+      if (col) { g = b % G; kk = b / G; } else { kk = b % (rows / 2); g = b / (rows / 2); }
+      int k = ((kk >> sb) << (sb + 1)) | (kk & (d - 1));
+      int i0 = col ? (k * G + g) : (g * rows + k);
+      int i1 = i0 + d * stride;
+      size_t j = ((size_t)(k & (d - 1)) << lo) + (col ? (low0 + g) : 0);
+      size_t e = j << (logn - 1 - s);
+      Fr w = ldg_fr(tw + e);
+      Fr u = lds_fr(sm, i0), v = lds_fr(sm, i1);
+      if (DIF) {
+        sts_fr(sm, i0, u + v);
+        sts_fr(sm, i1, (u - v) * w);
+      } else {
+        Fr t = v * w;
+        sts_fr(sm, i0, u + t);
+        sts_fr(sm, i1, u - t);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- store ----------------------------------------------------------------------------
+  for (int i = threadIdx.x; i < TILE; i += NTT_THREADS) {
+    int k, g;
+    size_t addr;
+    int sidx;
+    if (col) { g = i % G; k = i / G; addr = base + ((size_t)k << lo) + g; sidx = k * G + g; }
+    else { k = i % rows; g = i / rows; addr = base + (size_t)g * rows + k; sidx = g * rows + k; }
+    Fr x = lds_fr(sm, sidx);
+    if (scale) x = x * ldg_fr(scale + addr);
+    stg_fr(vec + addr, x);
+  }
+}
+
+// out[bitrev(i)] = in[i]
+__global__ void k_bitrev(Fr *out, const Fr *in, int logn, size_t vec_stride) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >> logn) return;
+  size_t j = __brev((uint32_t)i) >> (32 - logn);
+  stg_fr(out + blockIdx.y * vec_stride + j, ldg_fr(in + blockIdx.y * vec_stride + i));
+}
+
+__global__ void k_to_mont(Fr *x, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stg_fr(x + i, ldg_fr(x + i).to_mont());
+}
+__global__ void k_from_mont(Fr *x, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stg_fr(x + i, ldg_fr(x + i).from_mont());
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t NttPlan::init(int logn_, cudaStream_t st) {
+  logn = logn_;
+  if (logn < TILE_LOG + 1 || logn > 27) return cudaErrorInvalidValue;
+  size_t n = (size_t)1 << logn;
+  CK(cudaMalloc(&tw_fwd, (n / 2) * sizeof(Fr)));
+  CK(cudaMalloc(&tw_inv, (n / 2) * sizeof(Fr)));
+  CK(cudaMalloc(&coset_scale, n * sizeof(Fr)));
+  Fr *pw, *ninv;
+  CK(cudaMalloc(&pw, 32 * sizeof(Fr)));
+  CK(cudaMalloc(&ninv, sizeof(Fr)));
+  Fr one = Fr::one();
+  int th = 256;
+  k_root_powers<<<1, 1, 0, st>>>(pw, logn, 0, ninv);
+  k_powers<<<(unsigned)((n / 2 + th - 1) / th), th, 0, st>>>(tw_fwd, pw, n / 2, one);
+  k_root_powers<<<1, 1, 0, st>>>(pw, logn, 1, nullptr);
+  k_powers<<<(unsigned)((n / 2 + th - 1) / th), th, 0, st>>>(tw_inv, pw, n / 2, one);
+  // inc = omega_{2^(logn+1)}  (snarkjs: Fr.w[power+1])
+  k_root_powers<<<1, 1, 0, st>>>(pw, logn + 1, 0, nullptr);
+  k_coset_scale<<<(unsigned)((n + th - 1) / th), th, 0, st>>>(coset_scale, pw, ninv, logn);
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(pw));
+  CK(cudaFree(ninv));
+  CK(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 32));
+  CK(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 32));
+  return cudaGetLastError();
+}
+
+void NttPlan::destroy() {
+  if (tw_fwd) cudaFree(tw_fwd);
+  if (tw_inv) cudaFree(tw_inv);
+  if (coset_scale) cudaFree(coset_scale);
+  tw_fwd = tw_inv = coset_scale = nullptr;
+}
+
+// stage ranges, top-down: column passes of 9 stages while more than 11 remain (hi >= 11 keeps a tile
+// inside one high index), then one contiguous pass over the remaining low stages [0, <=11).
+static int split_passes(int logn, int lo[4], int hi[4]) {
+  int np = 0, top = logn;
+  while (top > TILE_LOG) {
+    lo[np] = top - 9;
+    hi[np] = top;
+    top -= 9;
+    np++;
+  }
+  lo[np] = 0;
+  hi[np] = top;
+  return np + 1;
+}
+
+// DIF passes: natural in -> bit-reversed out.  inverse selects the twiddle table; with_coset_scale
+// multiplies by n^-1 * inc^bitrev(p) in the last pass.
+cudaError_t NttPlan::dif(Fr *data, int nvec, size_t vec_stride, bool inverse, bool with_coset_scale,
+                         cudaStream_t st) const {
+  int lo[4], hi[4];
+  int np = split_passes(logn, lo, hi);
+  size_t n = (size_t)1 << logn;
+  dim3 grid((unsigned)(n / TILE), nvec);
+  for (int p = 0; p < np; p++) {
+    const Fr *sc = (with_coset_scale && p == np - 1) ? coset_scale : nullptr;
+    k_ntt_pass<true><<<grid, NTT_THREADS, TILE * 32, st>>>(data, vec_stride, logn, lo[p], hi[p],
+                                                           inverse ? tw_inv : tw_fwd, sc);
+  }
+  return cudaGetLastError();
+}
+
+// DIT passes: bit-reversed in -> natural out
+cudaError_t NttPlan::dit(Fr *data, int nvec, size_t vec_stride, bool inverse, cudaStream_t st) const {
+  int lo[4], hi[4];
+  int np = split_passes(logn, lo, hi);
+  size_t n = (size_t)1 << logn;
+  dim3 grid((unsigned)(n / TILE), nvec);
+  for (int p = np - 1; p >= 0; p--)
+    k_ntt_pass<false><<<grid, NTT_THREADS, TILE * 32, st>>>(data, vec_stride, logn, lo[p], hi[p],
+                                                            inverse ? tw_inv : tw_fwd, nullptr);
+  return cudaGetLastError();
+}
+
+cudaError_t ntt_bitrev(Fr *out, const Fr *in, int logn, int nvec, size_t vec_stride, cudaStream_t st) {
+  size_t n = (size_t)1 << logn;
+  dim3 grid((unsigned)((n + 255) / 256), nvec);
+  k_bitrev<<<grid, 256, 0, st>>>(out, in, logn, vec_stride);
+  return cudaGetLastError();
+}
+cudaError_t fr_to_mont(Fr *x, size_t n, cudaStream_t st) {
+  k_to_mont<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n);
+  return cudaGetLastError();
+}
+cudaError_t fr_from_mont(Fr *x, size_t n, cudaStream_t st) {
+  k_from_mont<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n);
+  return cudaGetLastError();
+}
+
+}  // namespace zkb

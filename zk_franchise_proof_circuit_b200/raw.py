@@ -1,0 +1,67 @@
+"""Raw kernel entry points (BASELINE.json config 5: BN254 G1/G2 MSM and Fr NTT on caller data)."""
+import ctypes
+import numpy as np
+from . import _native
+
+
+def field_op(field: str, op: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Element-wise op on Montgomery residues; a, b: uint32[n, 8]."""
+    ops = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "sqr": 4, "to_mont": 5, "from_mont": 6, "neg": 7}
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    b = np.ascontiguousarray(b, dtype=np.uint32)
+    out = np.zeros_like(a)
+    _native.check(_native.lib().zkb_raw_field_op(0 if field == "fq" else 1, ops[op], a.ctypes.data, b.ctypes.data,
+                                                 out.ctypes.data, a.shape[0]))
+    return out
+
+
+def bench_modmul(field="fq", iters=4096, blocks_per_sm=8):
+    r, ms = ctypes.c_double(), ctypes.c_double()
+    _native.check(_native.lib().zkb_bench_modmul(0 if field == "fq" else 1, iters, blocks_per_sm,
+                                                 ctypes.byref(r), ctypes.byref(ms)))
+    return r.value, ms.value
+
+
+def ntt(values: np.ndarray, inverse=False, timing=False):
+    """values: uint8[nvec, 2^k, 32] or [2^k, 32] canonical LE; natural order in and out."""
+    v = np.ascontiguousarray(values, dtype=np.uint8).copy()
+    shp = v.shape
+    nvec = 1 if v.ndim == 2 else shp[0]
+    n = shp[-2]
+    logn = n.bit_length() - 1
+    assert 1 << logn == n
+    ms = ctypes.c_float()
+    _native.check(_native.lib().zkb_raw_ntt(v.ctypes.data, logn, nvec, 1 if inverse else 0, ctypes.byref(ms)))
+    return (v, ms.value) if timing else v
+
+
+def coset_ntt(values: np.ndarray):
+    """NTT(coset_shift(iNTT(values))) - the prover's odd-coset evaluation (snarkjs groth16 prove)."""
+    v = np.ascontiguousarray(values, dtype=np.uint8).copy()
+    nvec = 1 if v.ndim == 2 else v.shape[0]
+    n = v.shape[-2]
+    logn = n.bit_length() - 1
+    _native.check(_native.lib().zkb_raw_coset_ntt(v.ctypes.data, logn, nvec))
+    return v
+
+
+def _msm(fn, psize, bases, scalars, timing):
+    b = np.ascontiguousarray(bases, dtype=np.uint8)
+    s = np.ascontiguousarray(scalars, dtype=np.uint8)
+    n = b.shape[0]
+    nbatch = 1 if s.ndim == 2 else s.shape[0]
+    assert s.shape[-2] == n
+    out = np.zeros((nbatch, psize), dtype=np.uint8)
+    kms, tms = ctypes.c_float(), ctypes.c_float()
+    _native.check(fn(b.ctypes.data, n, s.ctypes.data, nbatch, out.ctypes.data,
+                     ctypes.byref(kms) if timing else None, ctypes.byref(tms) if timing else None))
+    return (out, kms.value, tms.value) if timing else out
+
+
+def msm_g1(bases, scalars, timing=False):
+    """bases: uint8[n, 64] canonical affine (zeros = infinity); scalars: uint8[(nbatch,) n, 32]."""
+    return _msm(_native.lib().zkb_raw_msm_g1, 64, bases, scalars, timing)
+
+
+def msm_g2(bases, scalars, timing=False):
+    return _msm(_native.lib().zkb_raw_msm_g2, 128, bases, scalars, timing)
