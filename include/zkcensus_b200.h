@@ -1,0 +1,133 @@
+/* libzkcensus_b200 - C ABI of the B200-native census Groth16 prover.
+ *
+ * Drop-in boundary for the proving path of vocdoni/zk-franchise-proof-circuit: the native library a
+ * cgo / N-API / ctypes binding loads in place of go-rapidsnark's static libs (Go) or snarkjs' wasm
+ * engine (JS).  Plain C: pointers and sizes only, caller-owned buffers, no C++ or torch types.
+ * Citations are paths in the reference repository.
+ *
+ * Ownership: every input pointer is borrowed for the duration of the call; whatever must persist
+ * (key tables, witness constants) is copied to the device inside zkb_load_circuit.  Outputs go to
+ * caller-allocated buffers with in/out sizes, as in rapidsnark's prover.h.
+ * Threading: calls may arrive on arbitrary OS threads (cgo); each call binds its device itself and
+ * calls on one circuit handle are serialised internally.
+ * There is NO CPU fallback: without an sm_100 GPU every compute entry point returns ZKB_ERROR.
+ */
+#ifndef ZKCENSUS_B200_H
+#define ZKCENSUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes (0/1/2 coincide with rapidsnark's PROVER_OK / PROVER_ERROR / PROVER_ERROR_SHORT_BUFFER;
+ * 4 is the circom wasm's exceptionHandler(4) "constraint assert failed"). */
+#define ZKB_OK 0
+#define ZKB_ERROR 1
+#define ZKB_SHORT_BUFFER 2
+#define ZKB_INVALID_WITNESS_LENGTH 3
+#define ZKB_ASSERT_FAILED 4
+#define ZKB_UNSUPPORTED_CIRCUIT 5
+
+typedef struct zkb_ctx zkb_ctx;         /* one GPU + its stream */
+typedef struct zkb_circuit zkb_circuit; /* a proving key (+ witness calculator) resident on that GPU */
+
+/* NUL-terminated description of the last error on the calling thread. */
+const char *zkb_last_error(void);
+int zkb_device_count(void);
+
+/* One context per GPU; multi-GPU = one process (or one context) per device, proofs sharded by the caller. */
+int zkb_ctx_create(int device, zkb_ctx **out);
+void zkb_ctx_destroy(zkb_ctx *ctx);
+void *zkb_ctx_stream(zkb_ctx *ctx); /* cudaStream_t the pipeline runs on (for external CUDA-event timing) */
+
+/* Parses the snarkjs .zkey and the circom .wasm exactly as the reference reads them from
+ * artifacts/<name>/<env>/<nLevels>/{proving_key.zkey,circuit.wasm} (zk_census_test.go:81-84) and makes the
+ * key device-resident (fixed-base MSM tables, CSR coefficients, NTT twiddles, Poseidon constants,
+ * witness template).  wasm may be NULL: then only zkb_prove_wtns / groth16_prover are available.
+ * Returns ZKB_UNSUPPORTED_CIRCUIT when the wasm is not a census.circom witness calculator. */
+int zkb_load_circuit(zkb_ctx *ctx, const void *zkey, size_t zkey_len, const void *wasm, size_t wasm_len,
+                     zkb_circuit **out);
+void zkb_circuit_destroy(zkb_circuit *c);
+/* info[8] = nVars, nPublic, domainSize, nInputs, nLevels+1, nSignals, chunk, resident capacity */
+int zkb_circuit_info(zkb_circuit *c, uint32_t *info);
+
+/* Test hook: pin the Groth16 blinding scalars r, s (canonical little-endian, < r) so that pi_a/pi_b/pi_c
+ * can be compared bit-for-bit with snarkjs groth16.prove on the same inputs.  NULL, NULL = random again. */
+int zkb_set_blinding(zkb_circuit *c, const uint8_t *r32, const uint8_t *s32);
+
+/* --- reference-shaped entry points ---------------------------------------------------------------- */
+
+/* prover.Prove(zkey, wasm, inputs) (zk_census_test.go:89) / groth16.fullProve (ts_inputs/src/example.ts:358):
+ * inputs.json in, proof.json + public.json out (compact JSON, the bytes (*Proof).Bytes() returns,
+ * zk_census_test.go:93-100).  *proof_size / *public_size: capacity in, bytes written (or needed) out.
+ * A failed circuit assert returns ZKB_ASSERT_FAILED (the wasm's exception code 4). */
+int zkb_fullprove(zkb_circuit *c, const char *inputs_json, size_t inputs_len, char *proof_buf, size_t *proof_size,
+                  char *public_buf, size_t *public_size, char *err, size_t errmax);
+
+/* n independent proofs in one call.  Outputs are NUL-terminated strings at proofs + i*proof_stride and
+ * publics + i*public_stride (1024 bytes each suffice); status[i] per proof, the batch continues past failures. */
+int zkb_fullprove_batch(zkb_circuit *c, int n, const char *const *inputs_json, const size_t *inputs_len, char *proofs,
+                        size_t proof_stride, char *publics, size_t public_stride, int *status);
+
+/* The witness step alone: .wtns bytes for one inputs.json (what go-rapidsnark/witness CalculateWTNSBin and
+ * circom_runtime calculateWTNSBin return when they run circuit.wasm). */
+int zkb_witness(zkb_circuit *c, const char *inputs_json, size_t inputs_len, void *wtns_out, size_t *wtns_len);
+
+/* The Groth16 step alone from a caller-supplied .wtns (go-rapidsnark prover.Groth16ProverRaw). */
+int zkb_prove_wtns(zkb_circuit *c, const void *wtns, size_t wtns_size, char *proof_buf, size_t *proof_size,
+                   char *public_buf, size_t *public_size);
+
+/* rapidsnark prover.h, same symbol and signature, so go-rapidsnark's cgo wrapper links unchanged
+ * (go.mod:30 github.com/iden3/go-rapidsnark/prover v0.0.9).  Returns 0 / 1 / 2. */
+int groth16_prover(const void *zkey_buffer, unsigned long zkey_size, const void *wtns_buffer, unsigned long wtns_size,
+                   char *proof_buffer, unsigned long *proof_size, char *public_buffer, unsigned long *public_size,
+                   char *error_msg, unsigned long error_msg_maxsize);
+
+/* Batched Poseidon with the circuit's constants (arity 2..4): the hash function of the census and SIK trees
+ * (arbo.HashFunctionPoseidon, internal/helpers.go:45-49; circomlibjs in ts_inputs/src/inputs.ts:16,33).
+ * in: n x arity canonical 32-byte values, out: n x 32 bytes. */
+int zkb_poseidon_hash(zkb_circuit *c, int arity, int n, const void *in, void *out);
+
+/* --- resident-input batch path (inputs already in HBM; what bench.py times as `value`) -------------- */
+
+/* inputs: n x nInputs canonical 32-byte little-endian values in the circuit's main-signal order
+ * (electionId[2], nullifier, voteHash[2], sikRoot, censusRoot, voteWeight, availableWeight, address, password,
+ * signature, censusSiblings[nLevels+1], sikSiblings[nLevels+1]; circuit/census.circom:51-67 with the public
+ * list of circuit/circuit-compiler.sh:85-88 first). */
+int zkb_batch_set_inputs(zkb_circuit *c, int n, const void *inputs);
+/* witness + Groth16 for the n resident inputs, results stay on the device.  stage_ms: NULL or 8 floats
+ * (witness, buildABC, NTT+join, MSM sort, MSM accumulate G1, MSM accumulate G2, MSM reduce, finalize) measured
+ * with CUDA events on the pipeline stream. */
+int zkb_batch_prove_resident(zkb_circuit *c, int n, float *stage_ms);
+/* proofs256: n x 256 B (A.x A.y B.x.c0 B.x.c1 B.y.c0 B.y.c1 C.x C.y canonical LE); publics: n x nPublic x 32 B */
+int zkb_batch_get_results(zkb_circuit *c, int n, void *proofs256, void *publics, int *status);
+int zkb_batch_get_witness(zkb_circuit *c, int first, int n, void *wtns);
+/* measurement aids: kernels launched so far by the proving pipeline; executed MSM work of the last chunk
+ * (out[6]: G1 mixed adds, G2 mixed adds, witness digit entries, H digit entries, proofs in chunk, chunk capacity) */
+uint64_t zkb_launch_count(void);
+int zkb_work_counters(zkb_circuit *c, uint64_t *out);
+/* debugging aid for parity tests: the five MSM partial sums (pi_a' pi_b1' pi_b' pi_c' pi_h, 384 B affine canonical)
+ * and the H scalars (domainSize x 32 B) of the first proof of the last processed chunk */
+int zkb_debug_partials(zkb_circuit *c, void *out384, void *h_out);
+
+/* --- raw kernels on caller data (BASELINE.json config 5) --------------------------------------------- */
+
+/* field: 0 = Fq, 1 = Fr; op: 0 mul 1 add 2 sub 3 inv 4 sqr 5 to_mont 6 from_mont 7 neg; 8 x u32 Montgomery residues */
+int zkb_raw_field_op(int field, int op, const void *a, const void *b, void *out, size_t n);
+int zkb_bench_modmul(int field, int iters, int blocks_per_sm, double *modmul_per_s, double *ms);
+/* nvec vectors of 2^logn canonical Fr values, natural order in and out */
+int zkb_raw_ntt(void *data, int logn, int nvec, int inverse, float *kernel_ms);
+int zkb_raw_coset_ntt(void *data, int logn, int nvec);
+/* bases: n canonical affine points (64 B G1 / 128 B G2, zeros = infinity); scalars: nbatch x n x 32 B */
+int zkb_raw_msm_g1(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
+                   float *table_ms);
+int zkb_raw_msm_g2(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
+                   float *table_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKCENSUS_B200_H */

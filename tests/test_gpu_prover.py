@@ -1,0 +1,208 @@
+"""GPU parity tests of the census proving path through the C ABI / the reference-shaped host API.
+
+Bar: the witness is bit-exact against the reference's circuit.wasm (oracle/_ref) and, with r,s pinned,
+pi_a / pi_b / pi_c are bit-exact against the CPU oracle's restatement of snarkjs groth16.prove; every proof
+verifies under the vkey of the dev setup."""
+import json
+import numpy as np
+import pytest
+
+import helpers as H
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def circuit(art_dir):
+    from zk_franchise_proof_circuit_b200 import prover
+    zkey = open(art_dir + "/proving_key.zkey", "rb").read()
+    wasm = open(art_dir + "/circuit.wasm", "rb").read()
+    c = prover.load(zkey, wasm)
+    assert (c.n_vars, c.n_public, c.domain, c.n_inputs, c.n_levels1) == (82754, 8, 131072, 334, 161)
+    return c
+
+
+def _ref_witness(inputs):
+    import ref_witness as RW
+    if not RW.available():
+        pytest.skip("oracle/_ref not built")
+    return RW.witness(inputs)
+
+
+def test_witness_fixture_bit_exact(circuit):
+    inp = H.fixture_inputs()
+    wtns = circuit.witness(json.dumps(inp))
+    w = H.wtns_payload(wtns, circuit.n_vars)
+    assert H.sha(w.tobytes()) == H.WITNESS_SHA256                      # golden KAT (reference wasm)
+    kat = json.load(open(H.GOLDEN + "/witness_kat.json"))
+    for i, v in kat["wires"].items():
+        assert O.from_le(w[int(i)]) == int(v)
+    code, ref = _ref_witness(inp)
+    assert code == 0 and np.array_equal(ref, w)
+    # public signals == signals.json
+    pub = json.load(open(H.GOLDEN + "/signals.json"))
+    assert [str(O.from_le(w[i])) for i in range(1, 9)] == pub
+
+
+def test_witness_synthetic_voters_bit_exact(circuit):
+    from zk_franchise_proof_circuit_b200 import prover
+    vs = H.voters(64)
+    packed = np.stack([prover.pack_inputs(v) for v in vs])
+    circuit.set_inputs(packed)
+    circuit.prove_resident()
+    _, _, status = circuit.get_results()
+    assert (status == 0).all()
+    for i in (0, 1, 31, 63):
+        code, ref = _ref_witness(vs[i])
+        assert code == 0
+        assert np.array_equal(circuit.get_witness(i, 1)[0], ref), f"voter {i}"
+
+
+def test_assert_failures_match_wasm(circuit):
+    inp = H.fixture_inputs()
+    for patch in ({"voteWeight": "11"}, {"nullifier": "5"}, {"censusRoot": "7"}):
+        bad = dict(inp)
+        bad.update(patch)
+        proofs, pubs, status = circuit.fullprove_batch([json.dumps(bad), json.dumps(inp)])
+        assert status == [4, 0], patch                                  # exceptionHandler(4); batch continues
+        assert proofs[0] == b"" and proofs[1] != b""
+    from zk_franchise_proof_circuit_b200.prover import NativeError
+    with pytest.raises(NativeError) as ei:
+        circuit.fullprove(json.dumps(dict(inp, voteWeight="11")))
+    assert ei.value.code == 4
+    missing = dict(inp)
+    del missing["address"]
+    with pytest.raises(NativeError):
+        circuit.fullprove(json.dumps(missing))
+
+
+def test_proof_fixture_bit_exact_with_pinned_blinding(circuit):
+    inp = H.fixture_inputs()
+    circuit.set_blinding(H.R_FIXED, H.S_FIXED)
+    try:
+        pj, sj = circuit.fullprove(json.dumps(inp))
+    finally:
+        circuit.set_blinding(None, None)
+    proof, pub = json.loads(pj), json.loads(sj)
+    assert set(proof) == {"pi_a", "pi_b", "pi_c"}
+    assert pub == json.load(open(H.GOLDEN + "/signals.json"))
+    code, w = _ref_witness(inp)
+    exp, exp_part = H.zkey_ref().prove(w, H.R_FIXED, H.S_FIXED, partials=True)
+    # stage-by-stage first, so that a mismatch names the stage: H scalars, then the five MSM partial sums
+    part, h = circuit.debug_partials(with_h=True)
+    assert np.array_equal(h, H.zkey_ref().h_scalars(w)), "H scalars (buildABC / NTT / join)"
+    for name, lo, hi in (("pi_a'", 0, 64), ("pi_b1'", 64, 128), ("pi_b'", 128, 256), ("pi_c'", 256, 320), ("pi_h", 320, 384)):
+        assert part[lo:hi] == exp_part[lo:hi], f"MSM partial {name}"
+    got = O.proof_bin(proof)
+    for name, lo, hi in (("pi_a", 0, 64), ("pi_b", 64, 192), ("pi_c", 192, 256)):
+        assert got[lo:hi] == exp[lo:hi], f"proof element {name}"         # A, B, C limb for limb
+    assert O.verify(H.dev_vkey(), pub, proof)
+
+
+def test_batch_proofs_verify_and_match_oracle(circuit):
+    vs = H.voters(64)
+    docs = [json.dumps(v) for v in vs]
+    circuit.set_blinding(H.R_FIXED, H.S_FIXED)
+    try:
+        proofs, pubs, status = circuit.fullprove_batch(docs)
+    finally:
+        circuit.set_blinding(None, None)
+    assert status == [0] * 64
+    vk = H.dev_vkey()
+    pb = b"".join(O.proof_bin(json.loads(p)) for p in proofs)
+    qb = b"".join(O.pub_bin(json.loads(q)) for q in pubs)
+    ok = O.verify_many(vk, qb, pb, 64)
+    assert ok.all()
+    for i in (0, 17, 40, 63):                                            # bit-exact vs the CPU oracle
+        code, w = _ref_witness(vs[i])
+        assert pb[i * 256:(i + 1) * 256] == H.zkey_ref().prove(w, H.R_FIXED, H.S_FIXED), f"voter {i}"
+
+
+def test_random_blinding_differs_but_verifies(circuit):
+    inp = json.dumps(H.fixture_inputs())
+    p1, s1 = circuit.fullprove(inp)
+    p2, s2 = circuit.fullprove(inp)
+    assert p1 != p2 and s1 == s2
+    vk = H.dev_vkey()
+    assert O.verify(vk, json.loads(s1), json.loads(p1)) and O.verify(vk, json.loads(s2), json.loads(p2))
+
+
+def test_go_and_snarkjs_shaped_api(art_dir):
+    from zk_franchise_proof_circuit_b200 import prover
+    zkey = open(art_dir + "/proving_key.zkey", "rb").read()
+    wasm = open(art_dir + "/circuit.wasm", "rb").read()
+    inputs = open(H.GOLDEN + "/inputs_example.json", "rb").read()
+    proof = prover.prove(zkey, wasm, inputs)                             # zk_census_test.go:89
+    pdata, psig = proof.bytes()                                          # :93
+    again = prover.parse_proof(pdata, psig)                              # :118
+    assert O.verify(H.dev_vkey(), again.pub_signals, again.data)         # :122 (oracle verifier)
+    assert b" " not in pdata and pdata.startswith(b'{"pi_a":["')
+    res = prover.groth16.full_prove(json.loads(inputs), art_dir + "/circuit.wasm", art_dir + "/proving_key.zkey")
+    assert res["proof"]["protocol"] == "groth16" and res["proof"]["curve"] == "bn128"
+    assert res["publicSignals"] == json.load(open(H.GOLDEN + "/signals.json"))
+    assert O.verify(H.dev_vkey(), res["publicSignals"], res["proof"])
+
+
+def test_rapidsnark_abi_groth16_prover(circuit, art_dir):
+    """groth16_prover(zkey, wtns, ...) - the symbol go-rapidsnark binds - with a .wtns produced by zkb_witness."""
+    import ctypes
+    from zk_franchise_proof_circuit_b200 import prover
+    L = prover._lib()
+    zkey = open(art_dir + "/proving_key.zkey", "rb").read()
+    wtns = circuit.witness(json.dumps(H.fixture_inputs()))
+    pbuf, qbuf, ebuf = ctypes.create_string_buffer(16), ctypes.create_string_buffer(2048), ctypes.create_string_buffer(256)
+    pn, qn = ctypes.c_ulong(16), ctypes.c_ulong(2048)
+    zb = (ctypes.c_char * len(zkey)).from_buffer_copy(zkey)
+    wb = (ctypes.c_char * len(wtns)).from_buffer_copy(wtns)
+    rc = L.groth16_prover(zb, len(zkey), wb, len(wtns), pbuf, ctypes.byref(pn), qbuf, ctypes.byref(qn), ebuf, 256)
+    assert rc == 2 and pn.value > 16                                     # PROVER_ERROR_SHORT_BUFFER, size reported
+    pbuf = ctypes.create_string_buffer(pn.value + 64)                    # random blinding: digits may differ
+    pn, qn = ctypes.c_ulong(len(pbuf)), ctypes.c_ulong(2048)             # sizes are in/out, as in rapidsnark
+    rc = L.groth16_prover(zb, len(zkey), wb, len(wtns), pbuf, ctypes.byref(pn), qbuf, ctypes.byref(qn), ebuf, 256)
+    assert rc == 0, ebuf.value
+    proof, pub = json.loads(pbuf.raw[:pn.value]), json.loads(qbuf.raw[:qn.value])
+    assert O.verify(H.dev_vkey(), pub, proof)
+    pn, qn = ctypes.c_ulong(len(pbuf)), ctypes.c_ulong(2048)
+    rc = L.groth16_prover(zb, len(zkey), wb, len(wtns) - 32, pbuf, ctypes.byref(pn), qbuf, ctypes.byref(qn), ebuf, 256)
+    assert rc == 1
+
+
+def test_unsupported_inputs_are_errors_not_fallbacks(art_dir):
+    from zk_franchise_proof_circuit_b200 import prover
+    zkey = open(art_dir + "/proving_key.zkey", "rb").read()
+    with pytest.raises(prover.NativeError):
+        prover.Circuit(prover._context(), zkey[:1000], None)
+    with pytest.raises(prover.NativeError) as ei:
+        prover.Circuit(prover._context(), zkey, b"\0asm\x01\0\0\0")
+    assert ei.value.code == prover.UNSUPPORTED_CIRCUIT
+
+
+def test_gpu_census_generator_matches_oracle(circuit):
+    """census_tree.gen_census (GPU Poseidon, one launch per tree level) == oracle/census_gen.py, field for field."""
+    from zk_franchise_proof_circuit_b200 import census_tree
+    import census_gen as G
+    P = G.Poseidon(H.poseidon_tables())
+    rows = [(1, 2), (0, 0), (2**200, 5)]
+    assert circuit.poseidon(rows) == [P(list(r)) for r in rows]
+    assert circuit.poseidon([(1, 2, 3), (0, 0, 1)]) == [P([1, 2, 3]), P([0, 0, 1])]
+    assert circuit.poseidon([(1, 2, 3, 4)]) == [P([1, 2, 3, 4])]
+    got = census_tree.gen_census(circuit, 64, seed=0xC0FFEE)
+    assert got == H.voters(64)
+
+
+def test_stage_timing_and_work_counters(circuit):
+    from zk_franchise_proof_circuit_b200 import prover
+    vs = H.voters(64)
+    packed = np.stack([prover.pack_inputs(v) for v in vs[:32]])
+    circuit.set_inputs(packed)
+    n0 = prover.launch_count()
+    st = circuit.prove_resident(32, stages=True)
+    assert prover.launch_count() > n0
+    assert st.shape == (8,) and (st > 0).all()
+    wc = circuit.work_counters()
+    # dense bound: 16 windows x 82,754 scalars x 3 tables + 16 x 131,072 (H); executed is below it, above half
+    dense = 16 * (3 * 82754 + 131072)
+    assert 0.5 * dense < wc["g1_madds_per_proof"] < dense
+    assert wc["g2_madds_per_proof"] < 16 * 82754
+    print("stage ms for 32 proofs:", [round(float(x), 2) for x in st], wc)

@@ -1,0 +1,81 @@
+"""CPU tests: the Groth16 oracle against the reference's verifier fixtures and its own closed form."""
+import json
+import os
+import numpy as np
+import pytest
+
+import helpers as H
+import oracle_lib as O
+
+
+def test_reference_proof_verifies_under_reference_vkey():
+    """proof.json + signals.json verify under verification_key.json; tampering is rejected."""
+    vk = json.load(open(H.GOLDEN + "/verification_key.json"))
+    pf = json.load(open(H.GOLDEN + "/proof.json"))
+    pub = json.load(open(H.GOLDEN + "/signals.json"))
+    assert O.verify(vk, pub, pf)
+    bad = list(pub)
+    bad[7] = "6"
+    assert not O.verify(vk, bad, pf)
+    pf2 = json.loads(json.dumps(pf))
+    pf2["pi_a"][0], pf2["pi_c"][0] = pf["pi_c"][0], pf["pi_a"][0]
+    assert not O.verify(vk, pub, pf2)
+
+
+def test_vk_alphabeta_12_reproduced():
+    vk = json.load(open(H.GOLDEN + "/verification_key.json"))
+    assert O.alphabeta12(vk) == vk["vk_alphabeta_12"]
+
+
+def test_dev_zkey_shape(art_dir):
+    zk = H.zkey_ref()
+    assert (zk.n_vars, zk.n_public, zk.domain) == (82754, 8, 131072)
+    assert zk.n_coefs == 462889                                  # nnzA + nnzB + 9
+    vk = H.dev_vkey()
+    assert vk["nPublic"] == 8 and len(vk["IC"]) == 9
+    assert O.alphabeta12(vk) == vk["vk_alphabeta_12"]
+
+
+def test_oracle_prove_verifies_and_matches_closed_form(art_dir):
+    import ref_witness as RW
+    if not RW.available():
+        pytest.skip("oracle/_ref not built")
+    inp = H.fixture_inputs()
+    code, w = RW.witness(inp)
+    pf = H.zkey_ref().prove(w, H.R_FIXED, H.S_FIXED)
+    pub = [str(O.from_le(w[i])) for i in range(1, 9)]
+    assert O.verify(H.dev_vkey(), pub, O.proof_json(pf))
+    r1cs = os.path.join(H.ART, "circuit.r1cs")
+    if os.path.exists(r1cs):
+        import make_dev_artifacts as MDA
+        assert O.check_closed_form(r1cs, MDA.SETUP_SEED, w, H.R_FIXED, H.S_FIXED, pf) == 1
+    # a different blinding gives a different, still valid proof
+    pf2 = H.zkey_ref().prove(w, 99, 7)
+    assert pf2 != pf and O.verify(H.dev_vkey(), pub, O.proof_json(pf2))
+
+
+def test_oracle_ntt_and_msm_self_consistency():
+    rng = np.random.default_rng(3)
+    v = rng.integers(0, 256, size=(1 << 10, 32), dtype=np.uint8)
+    v[:, 31] &= 0x0F
+    assert np.array_equal(O.ntt(O.ntt(v), inverse=True), v)
+    # NTT of delta_1 is the geometric sequence of w: spot check linearity against a direct evaluation
+    R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    w = pow(5, (R - 1) >> 10, R)
+    d = np.zeros((1 << 10, 32), dtype=np.uint8)
+    d[1, 0] = 1
+    out = O.ntt(d)
+    assert [O.from_le(out[i]) for i in range(4)] == [pow(w, i, R) for i in range(4)]
+    # MSM linearity: msm(P, a) + msm(P, b) == msm(P, a+b) checked through k*G
+    import ctypes
+    pts = np.zeros((8, 64), dtype=np.uint8)
+    for i in range(8):
+        buf = (ctypes.c_uint8 * 64)()
+        O.lib().orc_g1_mul_gen(O._buf(O.le32(i + 2)), buf)
+        pts[i] = np.frombuffer(bytes(buf), dtype=np.uint8)
+    sc = [int(x) for x in rng.integers(1, 1 << 60, size=8)]
+    s = np.frombuffer(b"".join(O.le32(x) for x in sc), dtype=np.uint8).reshape(8, 32)
+    total = sum((i + 2) * k for i, k in enumerate(sc)) % R
+    buf = (ctypes.c_uint8 * 64)()
+    O.lib().orc_g1_mul_gen(O._buf(O.le32(total)), buf)
+    assert O.msm_g1(pts, s) == bytes(buf)

@@ -1,0 +1,532 @@
+// Census witness program: the signal-level evaluation of `circuit/census.circom:49-115`
+// (ZkFranchiseProofCircuit) and the circomlib 2.0.5 templates it instantiates, written as per-thread
+// host/device code.  It reproduces what the reference's circuit.wasm computes:
+// every circom signal is produced at circom's own signal number and stored through the wasm's
+// witness->signal table, so the output is the 82,754-wire witness in wasm order, canonical form.
+//
+// One proof is split into three independent tasks (one thread each in the batched kernel):
+//   task 0: censusVerifier = SMTVerifier(161) on (address, availableWeight)
+//   task 1: sik = Poseidon3(address,password,signature), sikVerifier = SMTVerifier(161) on (address, sik)
+//   task 2: main inputs, checkWeight = LessEqThan(252), computedNullifier = Poseidon4, checkNullifier
+// Below a leaf's insertion level every SMT level hashes Poseidon2(0,0): those 770-signal blocks (and
+// the oldKey=0 / oldValue=0 sub-circuits) are identical in every proof.  With skip_const they are not
+// recomputed: the output buffer is pre-filled from a template produced once per circuit by running
+// this same program with skip_const = false.  The decision is made on the DATA
+// (both hash inputs zero), never on an assumed tree depth, so the witness stays bit-exact.
+//
+// Assert semantics follow the wasm: a failed `===` sets status 4 (exceptionHandler(4)).
+#pragma once
+#include "fp.cuh"
+
+#if defined(__CUDACC__)
+#define ZKB_HDN __host__ __device__ __noinline__
+#else
+#define ZKB_HDN inline
+#endif
+
+namespace zkb {
+
+struct PexLayout {           // PoseidonEx(t-1, 1) block, offsets relative to its first signal
+  int t, rp;
+  uint32_t size;
+  uint32_t ark, mix, mixlast, mixs, sigf, sigp;
+  uint32_t c_off, s_off, m_off, p_off;   // offsets (in Fr elements) into the constants buffer
+};
+
+struct VerifierLayout {      // SMTVerifier(n), absolute signal numbers
+  uint32_t base;             // enabled, root, siblings[n], oldKey, oldValue, isOld0, key, value, fnc
+  uint32_t areKeyEquals, checkRoot, hash1New, hash1Old, keysOk, levels, n2bNew, n2bOld, sm, smtLevIns;
+};
+
+struct CensusLayout {
+  uint32_t n;                // levels = nLevels + 1
+  uint32_t n_signals, n_wires, n_inputs;
+  PexLayout pex[3];          // t = 3, 4, 5
+  uint32_t level_size;       // 789
+  VerifierLayout census, sik;
+  uint32_t checkNullifier, checkWeight, computedNullifier, sikHash;
+  // main input signal numbers
+  uint32_t electionId, nullifier, voteHash, sikRoot, censusRoot, voteWeight, availableWeight, address, password,
+      signature, censusSiblings, sikSiblings;
+};
+
+static inline uint32_t pex_size(int t, int rp) { return (t + 1) + 16 * t + 14 * t + (t + 1) + 2 * t * rp + 32 * t + 4 * rp; }
+
+// Fills everything except the constants offsets.  Returns false when n is unsupported.
+static inline bool census_layout_build(CensusLayout &L, uint32_t n_levels_plus1) {
+  const uint32_t n = n_levels_plus1;
+  if (n < 4 || n > 254) return false;
+  L.n = n;
+  const int rps[3] = {57, 56, 60};
+  for (int i = 0; i < 3; i++) {
+    PexLayout &p = L.pex[i];
+    int t = 3 + i;
+    p.t = t;
+    p.rp = rps[i];
+    p.ark = t + 1;
+    p.mix = p.ark + 16 * t;
+    p.mixlast = p.mix + 14 * t;
+    p.mixs = p.mixlast + (t + 1);
+    p.sigf = p.mixs + 2 * t * p.rp;
+    p.sigp = p.sigf + 32 * t;
+    p.size = p.sigp + 4 * p.rp;
+  }
+  const uint32_t poseidon2 = 3 + L.pex[0].size;            // Poseidon(2): out, inputs[2], pEx
+  const uint32_t poseidon3 = 4 + L.pex[1].size;
+  const uint32_t poseidon4 = 5 + L.pex[2].size;
+  const uint32_t hash1 = 3 + poseidon3, hash2 = 3 + poseidon2;
+  L.level_size = 13 + hash2 + 6;
+  const uint32_t n2b_strict = 255 + (254 + (383 + 136)) + 255;
+  const uint32_t levins = 3 * n + 3 * n;
+  const uint32_t verifier = (n + 8) + 6 + 6 + 2 * hash1 + 20 + n * L.level_size + 2 * n2b_strict + 15 * n + levins;
+  uint32_t s = 1;
+  L.electionId = s; s += 2;
+  L.nullifier = s; s += 1;
+  L.voteHash = s; s += 2;
+  L.sikRoot = s++; L.censusRoot = s++; L.voteWeight = s++; L.availableWeight = s++;
+  L.address = s++; L.password = s++; L.signature = s++;
+  L.censusSiblings = s; s += n;
+  L.sikSiblings = s; s += n;
+  L.n_inputs = s - 1;
+  auto place = [&](VerifierLayout &v) {
+    v.base = s;
+    uint32_t q = s + n + 8;
+    v.areKeyEquals = q; q += 6;
+    v.checkRoot = q; q += 6;
+    v.hash1New = q; q += hash1;
+    v.hash1Old = q; q += hash1;
+    v.keysOk = q; q += 20;
+    v.levels = q; q += n * L.level_size;
+    v.n2bNew = q; q += n2b_strict;
+    v.n2bOld = q; q += n2b_strict;
+    v.sm = q; q += 15 * n;
+    v.smtLevIns = q; q += levins;
+    s += verifier;
+  };
+  place(L.census);
+  L.checkNullifier = s; s += 6;
+  L.checkWeight = s; s += 3 + 3 + 254;
+  L.computedNullifier = s; s += poseidon4;
+  L.sikHash = s; s += poseidon3;
+  place(L.sik);
+  L.n_signals = s;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Env: where signals go.  consts = Poseidon tables (Montgomery form), sig2wire = inverse of the
+// wasm's witness->signal table (-1 = signal eliminated), out = this proof's witness (canonical).
+// ---------------------------------------------------------------------------------------------
+struct WitnessEnv {
+  const CensusLayout *L;
+  const Fr *consts;
+  const int32_t *sig2wire;
+  Fr *out;
+  int status;
+
+  ZKB_HD void put_norm(uint32_t sig, const Fr &v) {       // v already canonical
+    int32_t w = sig2wire[sig];
+    if (w >= 0) out[w] = v;
+  }
+  ZKB_HDN void put(uint32_t sig, const Fr &v_mont) {      // v in Montgomery form
+    int32_t w = sig2wire[sig];
+    if (w >= 0) out[w] = v_mont.from_mont();
+  }
+  ZKB_HD void put_u32(uint32_t sig, uint32_t x) {
+    int32_t w = sig2wire[sig];
+    if (w >= 0) {
+      Fr v = Fr::zero();
+      v.v[0] = x;
+      out[w] = v;
+    }
+  }
+  ZKB_HD void fail() { status = 4; }
+};
+
+ZKB_HDN Fr fr_sbox(WitnessEnv &e, uint32_t sig, const Fr &x) {   // Sigma {out,in,in2,in4}
+  Fr x2 = x.sqr(), x4 = x2.sqr(), y = x4 * x;
+  e.put(sig + 1, x);
+  e.put(sig + 2, x2);
+  e.put(sig + 3, x4);
+  e.put(sig, y);
+  return y;
+}
+
+// PoseidonEx(T-1 inputs, 1 output), initialState = 0.  `base` = first signal of the PoseidonEx block.
+// emit = false computes the hash only.
+template <int T>
+ZKB_HDN Fr poseidon_ex(WitnessEnv &e, uint32_t base, const Fr *inputs, bool emit) {
+  const PexLayout &pl = e.L->pex[T - 3];
+  const Fr *C = e.consts + pl.c_off, *S = e.consts + pl.s_off, *M = e.consts + pl.m_off, *Pm = e.consts + pl.p_off;
+  const int RP = pl.rp;
+  Fr st[T], tmp[T];
+  st[0] = Fr::zero();
+  for (int j = 1; j < T; j++) st[j] = inputs[j - 1];
+  if (emit) {
+    for (int j = 1; j < T; j++) e.put(base + j, inputs[j - 1]);
+    e.put_u32(base + T, 0);
+  }
+  auto ark = [&](int k, int coff) {       // Ark k: {out[T], in[T]}
+    uint32_t s = base + pl.ark + k * 2 * T;
+    for (int j = 0; j < T; j++) {
+      if (emit) e.put(s + T + j, st[j]);
+      st[j] = st[j] + C[coff + j];
+      if (emit) e.put(s + j, st[j]);
+    }
+  };
+  auto mix = [&](int k, const Fr *Mx) {   // Mix k: out[i] = sum_j M[j][i] in[j]
+    uint32_t s = base + pl.mix + k * 2 * T;
+    for (int i = 0; i < T; i++) {
+      Fr acc = Mx[i] * st[0];
+      for (int j = 1; j < T; j++) acc = acc + Mx[j * T + i] * st[j];
+      tmp[i] = acc;
+    }
+    for (int j = 0; j < T; j++) {
+      if (emit) { e.put(s + T + j, st[j]); e.put(s + j, tmp[j]); }
+      st[j] = tmp[j];
+    }
+  };
+  auto sigma_full = [&](int r) {
+    for (int j = 0; j < T; j++) {
+      uint32_t s = base + pl.sigf + (r * T + j) * 4;
+      if (emit) st[j] = fr_sbox(e, s, st[j]);
+      else { Fr x2 = st[j].sqr(); st[j] = x2.sqr() * st[j]; }
+    }
+  };
+  ark(0, 0);
+  for (int r = 0; r < 3; r++) {
+    sigma_full(r);
+    ark(r + 1, (r + 1) * T);
+    mix(r, M);
+  }
+  sigma_full(3);
+  ark(4, 4 * T);
+  mix(3, Pm);
+  for (int r = 0; r < RP; r++) {
+    uint32_t ss = base + pl.sigp + r * 4, ms = base + pl.mixs + r * 2 * T;
+    Fr y;
+    if (emit) y = fr_sbox(e, ss, st[0]);
+    else { Fr x2 = st[0].sqr(); y = x2.sqr() * st[0]; }
+    st[0] = y + C[5 * T + r];
+    const Fr *Sr = S + (2 * T - 1) * r;
+    Fr o0 = Sr[0] * st[0];
+    for (int i = 1; i < T; i++) o0 = o0 + Sr[i] * st[i];
+    if (emit) {
+      for (int j = 0; j < T; j++) e.put(ms + T + j, st[j]);
+      e.put(ms, o0);
+    }
+    for (int i = 1; i < T; i++) {
+      st[i] = st[i] + st[0] * Sr[T + i - 1];
+      if (emit) e.put(ms + i, st[i]);
+    }
+    st[0] = o0;
+  }
+  for (int r = 0; r < 3; r++) {
+    sigma_full(4 + r);
+    ark(5 + r, 5 * T + RP + r * T);
+    mix(4 + r, M);
+  }
+  sigma_full(7);
+  Fr o = M[0] * st[0];
+  for (int j = 1; j < T; j++) o = o + M[j * T] * st[j];
+  if (emit) {
+    uint32_t s = base + pl.mixlast;
+    for (int j = 0; j < T; j++) e.put(s + 1 + j, st[j]);
+    e.put(s, o);
+    e.put(base, o);
+  }
+  return o;
+}
+
+// Poseidon(T-1) = {out, inputs[T-1]} + pEx
+template <int T>
+ZKB_HD Fr poseidon_comp(WitnessEnv &e, uint32_t base, const Fr *inputs, bool emit) {
+  Fr o = poseidon_ex<T>(e, base + T, inputs, emit);
+  if (emit) {
+    e.put(base, o);
+    for (int j = 0; j < T - 1; j++) e.put(base + 1 + j, inputs[j]);
+  }
+  return o;
+}
+
+// canonical 256-bit helpers ---------------------------------------------------------------------
+ZKB_HD uint32_t bit_of(const Fr &x, int i) { return (x.v[i >> 5] >> (i & 31)) & 1u; }
+
+// IsZero {out,in,inv}; x in Montgomery form.  Returns out (0/1).
+ZKB_HDN uint32_t is_zero_comp(WitnessEnv &e, uint32_t sig, const Fr &x) {
+  uint32_t z = x.is_zero() ? 1u : 0u;
+  e.put_u32(sig, z);
+  e.put(sig + 1, x);
+  if (z) e.put_u32(sig + 2, 0);
+  else e.put(sig + 2, x.inv());
+  return z;
+}
+
+// Num2Bits(nbits) {out[nbits], in}: x canonical.  Returns false when x does not fit (assert).
+ZKB_HD bool num2bits_comp(WitnessEnv &e, uint32_t sig, const Fr &x, int nbits) {
+  for (int i = 0; i < nbits; i++) e.put_u32(sig + i, bit_of(x, i));
+  e.put_norm(sig + nbits, x);
+  for (int i = nbits; i < 256; i++)
+    if (bit_of(x, i)) return false;
+  return true;
+}
+
+// Num2Bits_strict {out[254], in} + aliasCheck {in[254]} + compConstant(-1) + n2b(254).  key canonical.
+ZKB_HDN void num2bits_strict_comp(WitnessEnv &e, uint32_t sig, const Fr &key) {
+  const uint32_t alias = sig + 255, cc = alias + 254, n2b = sig + 255 + 773;
+  for (int i = 0; i < 254; i++) {
+    uint32_t b = bit_of(key, i);
+    e.put_u32(sig + i, b);
+    e.put_u32(alias + i, b);
+    e.put_u32(cc + 1 + i, b);
+    e.put_u32(n2b + i, b);
+  }
+  e.put_norm(sig + 254, key);
+  e.put_norm(n2b + 254, key);
+  // CompConstant(ct = r - 1): parts[i] from bit pairs; a = 2^i, b = 2^128 - 2^i; values as plain integers
+  uint32_t sout[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 127; i++) {
+    uint32_t clsb = (FrParams::mod((2 * i) >> 5) >> ((2 * i) & 31)) & 1u;       // bits of r - 1: r is odd, so
+    uint32_t cmsb = (FrParams::mod((2 * i + 1) >> 5) >> ((2 * i + 1) & 31)) & 1u;
+    if (i == 0) clsb = 0;                                                        // (r-1) clears bit 0 only
+    uint32_t sl = bit_of(key, 2 * i), sm = bit_of(key, 2 * i + 1);
+    int kind;  // 0: zero, 1: a, 2: b
+    if (!cmsb && !clsb) kind = (sl | sm) ? 2 : 0;
+    else if (!cmsb && clsb) kind = sm ? 2 : (sl ? 0 : 1);
+    else if (cmsb && !clsb) kind = sm ? (sl ? 2 : 0) : 1;
+    else kind = (sm & sl) ? 0 : 1;
+    uint32_t part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (kind == 1) part[i >> 5] = 1u << (i & 31);
+    else if (kind == 2) {
+      // 2^128 - 2^i : bits i..127 set
+      for (int w = 0; w < 4; w++) {
+        uint32_t m = 0xffffffffu;
+        int lo = w * 32;
+        if (i >= lo + 32) m = 0;
+        else if (i > lo) m = 0xffffffffu << (i - lo);
+        part[w] = m;
+      }
+    }
+    Fr pv;
+    for (int w = 0; w < 8; w++) pv.v[w] = part[w];
+    e.put_norm(cc + 255 + i, pv);
+    uint64_t c = 0;
+    for (int w = 0; w < 8; w++) {
+      c += (uint64_t)sout[w] + part[w];
+      sout[w] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+  Fr sv;
+  for (int w = 0; w < 8; w++) sv.v[w] = sout[w];
+  e.put_norm(cc + 382, sv);
+  if (!num2bits_comp(e, cc + 383, sv, 135)) e.fail();
+  uint32_t outbit = bit_of(sv, 127);
+  e.put_u32(cc, outbit);
+  if (outbit) e.fail();           // AliasCheck: compConstant.out === 0
+}
+
+// SMTHash1 {out,key,value} + Poseidon(3); inputs Montgomery
+ZKB_HD Fr smt_hash1(WitnessEnv &e, uint32_t sig, const Fr &key, const Fr &value, bool emit) {
+  Fr in[3] = {key, value, Fr::one()};
+  Fr o = poseidon_comp<4>(e, sig + 3, in, emit);
+  if (emit) { e.put(sig, o); e.put(sig + 1, key); e.put(sig + 2, value); }
+  return o;
+}
+
+// SMTVerifier(n) with enabled = 1, fnc = 0, oldKey = oldValue = isOld0 = 0 (census.circom:79-103).
+// key_n/value_n/root_n/siblings canonical.  h00 = Poseidon2(0,0), h001 = Poseidon3(0,0,1) (Montgomery).
+ZKB_HDN void smt_verifier(WitnessEnv &e, const VerifierLayout &V, const Fr &key_n, const Fr &value_n, const Fr &root_n,
+                         const Fr *siblings_n, const Fr &h00, const Fr &h001, bool skip_const) {
+  const uint32_t n = e.L->n;
+  const uint32_t b = V.base;
+  const Fr key = key_n.to_mont(), value = value_n.to_mont(), root = root_n.to_mont();
+  e.put_u32(b, 1);
+  e.put_norm(b + 1, root_n);
+  for (uint32_t i = 0; i < n; i++) e.put_norm(b + 2 + i, siblings_n[i]);
+  e.put_u32(b + n + 2, 0);   // oldKey
+  e.put_u32(b + n + 3, 0);   // oldValue
+  e.put_u32(b + n + 4, 0);   // isOld0
+  e.put_norm(b + n + 5, key_n);
+  e.put_norm(b + n + 6, value_n);
+  e.put_u32(b + n + 7, 0);   // fnc
+  // hash1Old = SMTHash1(0, 0): constant
+  Fr old1leaf = h001;
+  if (!skip_const) old1leaf = smt_hash1(e, V.hash1Old, Fr::zero(), Fr::zero(), true);
+  Fr new1leaf = smt_hash1(e, V.hash1New, key, value, true);
+  if (!skip_const) num2bits_strict_comp(e, V.n2bOld, Fr::zero());
+  num2bits_strict_comp(e, V.n2bNew, key_n);
+  // smtLevIns {levIns[n], enabled, siblings[n], done[n-1]} + isZero[n]
+  const uint32_t li = V.smtLevIns;
+  e.put_u32(li + n, 1);
+  // bitmask of zero siblings (n <= 254)
+  uint32_t zmask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (uint32_t i = 0; i < n; i++) {
+    e.put_norm(li + n + 1 + i, siblings_n[i]);
+    Fr sm = siblings_n[i].to_mont();
+    uint32_t z = is_zero_comp(e, li + 3 * n + 3 * i, sm);
+    zmask[i >> 5] |= z << (i & 31);
+  }
+  auto isz = [&](uint32_t i) { return (zmask[i >> 5] >> (i & 31)) & 1u; };
+  if (!isz(n - 1)) e.fail();                                  // (isZero[n-1].out - 1) * enabled === 0
+  // levIns / done (all 0/1); levmask bit i = levIns[i]
+  uint32_t levmask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  {
+    uint32_t lev = 1u - isz(n - 2);
+    e.put_u32(li + n - 1, lev);
+    levmask[(n - 1) >> 5] |= lev << ((n - 1) & 31);
+    uint32_t done = lev;
+    e.put_u32(li + 2 * n + 1 + (n - 2), done);
+    for (uint32_t i = n - 2; i > 0; i--) {
+      lev = (1u - done) * (1u - isz(i - 1));
+      e.put_u32(li + i, lev);
+      levmask[i >> 5] |= lev << (i & 31);
+      done = lev + done;
+      e.put_u32(li + 2 * n + 1 + (i - 1), done);
+    }
+    lev = 1u - done;
+    e.put_u32(li, lev);
+    levmask[0] |= lev;
+  }
+  // state machines sm[i] (is0 = 0, fnc = 0)
+  uint32_t topmask[8] = {0, 0, 0, 0, 0, 0, 0, 0}, inewmask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t namask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  {
+    uint32_t p_top = 1, p_i0 = 0, p_iold = 0, p_inew = 0, p_na = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t s = V.sm + 15 * i;
+      uint32_t lev = (levmask[i >> 5] >> (i & 31)) & 1u;
+      uint32_t ptl = p_top * lev;
+      uint32_t st_top = p_top - ptl, st_inew = ptl, st_iold = 0, st_i0 = 0;
+      uint32_t st_na = p_na + p_inew + p_iold + p_i0;
+      e.put_u32(s + 0, st_top); e.put_u32(s + 1, st_i0); e.put_u32(s + 2, st_iold); e.put_u32(s + 3, st_inew);
+      e.put_u32(s + 4, st_na); e.put_u32(s + 5, 0); e.put_u32(s + 6, lev); e.put_u32(s + 7, 0);
+      e.put_u32(s + 8, p_top); e.put_u32(s + 9, p_i0); e.put_u32(s + 10, p_iold); e.put_u32(s + 11, p_inew);
+      e.put_u32(s + 12, p_na); e.put_u32(s + 13, ptl); e.put_u32(s + 14, 0);
+      topmask[i >> 5] |= st_top << (i & 31);
+      inewmask[i >> 5] |= st_inew << (i & 31);
+      namask[i >> 5] |= (st_na & 1u) << (i & 31);
+      if (i == n - 1 && st_na + st_iold + st_inew + st_i0 != 1) e.fail();
+      p_top = st_top; p_i0 = st_i0; p_iold = st_iold; p_inew = st_inew; p_na = st_na;
+    }
+  }
+  // levels n-1 .. 0
+  Fr child = Fr::zero();
+  for (int i = (int)n - 1; i >= 0; i--) {
+    const uint32_t s = V.levels + (uint32_t)i * e.L->level_size;
+    const uint32_t st_top = (topmask[i >> 5] >> (i & 31)) & 1u, st_inew = (inewmask[i >> 5] >> (i & 31)) & 1u;
+    const uint32_t st_na = (namask[i >> 5] >> (i & 31)) & 1u;
+    const uint32_t lrbit = bit_of(key_n, i);
+    const Fr sib = siblings_n[i].to_mont();
+    e.put_u32(s + 1, st_top); e.put_u32(s + 2, 0); e.put_u32(s + 3, 0); e.put_u32(s + 4, st_inew);
+    e.put_u32(s + 5, st_na);
+    e.put_norm(s + 6, siblings_n[i]);
+    e.put(s + 7, old1leaf);
+    e.put(s + 8, new1leaf);
+    e.put_u32(s + 9, lrbit);
+    e.put(s + 10, child);
+    // switcher {outL,outR,sel,L,R,aux}
+    const uint32_t sw = s + 13 + (3 + 3 + e.L->pex[0].size);
+    Fr aux = lrbit ? (sib - child) : Fr::zero();
+    Fr outL = aux + child, outR = sib - aux;
+    e.put(sw, outL); e.put(sw + 1, outR); e.put_u32(sw + 2, lrbit); e.put(sw + 3, child); e.put(sw + 4, sib);
+    e.put(sw + 5, aux);
+    // proofHash = SMTHash2 {out,L,R} + Poseidon(2)
+    Fr h;
+    const uint32_t ph = s + 13;
+    if (skip_const && outL.is_zero() && outR.is_zero()) {
+      h = h00;                      // block left as pre-filled from the template
+    } else {
+      Fr in[2] = {outL, outR};
+      h = poseidon_comp<3>(e, ph + 3, in, true);
+      e.put(ph, h); e.put(ph + 1, outL); e.put(ph + 2, outR);
+    }
+    Fr aux0 = st_top ? h : Fr::zero();
+    e.put(s + 11, aux0);
+    e.put_u32(s + 12, 0);           // aux[1] = old1leaf * st_iold, st_iold = 0
+    Fr rt = st_inew ? aux0 + new1leaf : aux0;
+    e.put(s, rt);
+    child = rt;
+  }
+  // areKeyEquals = IsEqual(oldKey = 0, key) {out,in[2]} + isz
+  {
+    uint32_t s = V.areKeyEquals;
+    e.put_u32(s + 1, 0);
+    e.put_norm(s + 2, key_n);
+    uint32_t z = is_zero_comp(e, s + 3, key);
+    e.put_u32(s, z);
+    // keysOk = MultiAND(4)(fnc=0, 1-isOld0=1, areKeyEquals.out, enabled=1)
+    uint32_t k = V.keysOk;
+    e.put_u32(k, 0);
+    e.put_u32(k + 1, 0); e.put_u32(k + 2, 1); e.put_u32(k + 3, z); e.put_u32(k + 4, 1);
+    e.put_u32(k + 5, 0); e.put_u32(k + 6, 0); e.put_u32(k + 7, z);              // and2 {out,a,b}
+    e.put_u32(k + 8, 0); e.put_u32(k + 9, 0); e.put_u32(k + 10, 1);             // ands[0] {out,in[2]}
+    e.put_u32(k + 11, 0); e.put_u32(k + 12, 0); e.put_u32(k + 13, 1);           //   and1 {out,a,b}
+    e.put_u32(k + 14, z); e.put_u32(k + 15, z); e.put_u32(k + 16, 1);           // ands[1]
+    e.put_u32(k + 17, z); e.put_u32(k + 18, z); e.put_u32(k + 19, 1);           //   and1
+  }
+  // checkRoot = ForceEqualIfEnabled(1, levels[0].root, root)
+  {
+    uint32_t s = V.checkRoot;
+    e.put_u32(s, 1);
+    e.put(s + 1, child);
+    e.put_norm(s + 2, root_n);
+    Fr d = root - child;
+    uint32_t z = is_zero_comp(e, s + 3, d);
+    if (!z) e.fail();
+  }
+}
+
+// Task 2: main inputs, checkWeight, computedNullifier, checkNullifier.  in = the 2n+12 canonical inputs in
+// main-signal order (signal 1 + k).
+ZKB_HDN void census_main_task(WitnessEnv &e, const Fr *in) {
+  const CensusLayout &L = *e.L;
+  e.put_u32(0, 1);
+  for (uint32_t k = 0; k < L.n_inputs; k++) e.put_norm(1 + k, in[k]);
+  const Fr &voteWeight = in[L.voteWeight - 1], &availableWeight = in[L.availableWeight - 1];
+  // checkWeight = LessEqThan(252) {out,in[2]} + lt = LessThan(252) {out,in[2]} + n2b = Num2Bits(253)
+  {
+    uint32_t s = L.checkWeight, lt = s + 3, n2b = lt + 3;
+    Fr one = Fr::zero();
+    one.v[0] = 1;
+    Fr in1p = availableWeight + one;                 // canonical arithmetic: + and - are form-agnostic
+    Fr two252 = Fr::zero();
+    two252.v[7] = 1u << 28;
+    Fr x = voteWeight + two252 - in1p;
+    e.put_norm(s + 1, voteWeight); e.put_norm(s + 2, availableWeight);
+    e.put_norm(lt + 1, voteWeight); e.put_norm(lt + 2, in1p);
+    if (!num2bits_comp(e, n2b, x, 253)) e.fail();
+    uint32_t o = 1u - bit_of(x, 252);
+    e.put_u32(lt, o);
+    e.put_u32(s, o);
+    if (o != 1) e.fail();                            // checkWeight.out === 1
+  }
+  Fr hin[4] = {in[L.signature - 1].to_mont(), in[L.password - 1].to_mont(), in[L.electionId - 1].to_mont(),
+               in[L.electionId].to_mont()};
+  Fr nul = poseidon_comp<5>(e, L.computedNullifier, hin, true);
+  {
+    uint32_t s = L.checkNullifier;
+    Fr given = in[L.nullifier - 1].to_mont();
+    e.put_u32(s, 1);
+    e.put(s + 1, nul);
+    e.put_norm(s + 2, in[L.nullifier - 1]);
+    uint32_t z = is_zero_comp(e, s + 3, given - nul);
+    if (!z) e.fail();
+  }
+}
+
+ZKB_HD void census_tree_task(WitnessEnv &e, int which, const Fr *in, const Fr &h00, const Fr &h001, bool skip_const) {
+  const CensusLayout &L = *e.L;
+  const Fr &address = in[L.address - 1];
+  if (which == 0) {
+    smt_verifier(e, L.census, address, in[L.availableWeight - 1], in[L.censusRoot - 1], in + (L.censusSiblings - 1),
+                 h00, h001, skip_const);
+  } else {
+    Fr hin[3] = {address.to_mont(), in[L.password - 1].to_mont(), in[L.signature - 1].to_mont()};
+    Fr sik = poseidon_comp<4>(e, L.sikHash, hin, true);
+    smt_verifier(e, L.sik, address, sik.from_mont(), in[L.sikRoot - 1], in + (L.sikSiblings - 1), h00, h001,
+                 skip_const);
+  }
+}
+
+}  // namespace zkb

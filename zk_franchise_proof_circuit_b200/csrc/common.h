@@ -10,6 +10,9 @@
 #define ZKB_ASSERT_FAILED 4
 #define ZKB_UNSUPPORTED_CIRCUIT 5
 
+extern "C" int zkb_device_count(void);
+extern "C" const char *zkb_last_error(void);
+
 namespace zkb {
 void set_error(const std::string &s);
 int cuda_fail(cudaError_t e, const char *what);

@@ -133,7 +133,7 @@ struct alignas(16) XYZZ {
 // compiled body per field instead of one per call site keeps code size and build time sane.  The
 // hot bucket-accumulation loop uses the inlined members above.
 #if defined(__CUDACC__)
-#define ZKB_NI __device__ __noinline__
+#define ZKB_NI __host__ __device__ __noinline__
 #else
 #define ZKB_NI inline
 #endif

@@ -1,0 +1,84 @@
+// Proof assembly kernels - see finalize.cuh for the formulas
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "finalize_kernels.h"
+
+namespace zkb {
+
+// 4-bit fixed-base tables for delta1 / delta2 (finalize.cuh)
+template <class F>
+__global__ void k_fixed_table(Affine<F> *tab, const Affine<F> *base) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 15) return;
+  Affine<F> b = *base, a;
+  fixed_table_entry<F>(b, i, a);
+  tab[i] = a;
+}
+
+
+// one CTA of 4 warps per proof, one warp per independent piece, so the four scalar
+// multiplications run on four schedulers instead of serialising as divergent lanes:
+//   warp 0: A = pi_a' + alpha1 + r*delta1, then s*A          warp 1: B1 = pi_b1' + beta1 + s*delta1, then r*B1
+//   warp 2: -(r*s)*delta1 and the public signals             warp 3: B = pi_b' + beta2 + s*delta2   (G2)
+//   then warp 0: C = pi_c' + pi_h + s*A + r*B1 - (r*s)*delta1
+__global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
+  __shared__ XYZZ<Fq> sh[5];          // A, s*A | B1, r*B1 | -(rs)delta1
+  __shared__ XYZZ<Fq2> shB;
+  const uint32_t p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t *out = P.out + (size_t)p * (256 + 32 * P.n_public);
+  XYZZ<Fq> *scratch = P.scratch + ((size_t)p * 2) * 15;
+  if (lane == 0) {
+    const Fr r = P.rs[2 * p], s = P.rs[2 * p + 1];
+    if (warp == 0) {
+      fin_point<Fq>(P.g1 + 3 * p, P.alpha1, P.d1tab, r.v, &sh[0]);
+      Affine<Fq> a;
+      xyzz_to_affine_ni(&sh[0], &a);
+      Fq x = a.x.from_mont(), y = a.y.from_mont();
+      memcpy(out, x.v, 32);
+      memcpy(out + 32, y.v, 32);
+      var_mul<Fq>(&sh[0], s.v, scratch, &sh[1]);
+    } else if (warp == 1) {
+      fin_point<Fq>(P.g1 + 3 * p + 1, P.beta1, P.d1tab, s.v, &sh[2]);
+      var_mul<Fq>(&sh[2], r.v, scratch + 15, &sh[3]);
+    } else if (warp == 2) {
+      fin_neg_rs_delta(P.d1tab, r, s, &sh[4]);
+      const Fr *w = P.wtns + (size_t)p * P.wtns_stride;
+      for (uint32_t i = 0; i < P.n_public; i++) memcpy(out + 256 + 32 * i, w[1 + i].v, 32);
+    } else {
+      fin_point<Fq2>(P.g2 + p, P.beta2, P.d2tab, s.v, &shB);
+      Affine<Fq2> b;
+      xyzz_to_affine_ni(&shB, &b);
+      Fq c[4] = {b.x.a.from_mont(), b.x.b.from_mont(), b.y.a.from_mont(), b.y.b.from_mont()};
+      memcpy(out + 64, c, 128);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // C = pi_c' + pi_h + s*A + r*B1 - (r*s)*delta1, accumulated in sh[1]
+    xyzz_add_ni(&sh[1], &sh[3]);
+    xyzz_add_ni(&sh[1], &sh[4]);
+    xyzz_add_ni(&sh[1], P.g1 + 3 * p + 2);
+    xyzz_add_ni(&sh[1], P.g1h + p);
+    Affine<Fq> c;
+    xyzz_to_affine_ni(&sh[1], &c);
+    Fq x = c.x.from_mont(), y = c.y.from_mont();
+    memcpy(out + 192, x.v, 32);
+    memcpy(out + 224, y.v, 32);
+  }
+}
+
+cudaError_t launch_fixed_tables(Affine<Fq> *d1tab, const Affine<Fq> *delta1, Affine<Fq2> *d2tab, const Affine<Fq2> *delta2,
+                                cudaStream_t st) {
+  k_fixed_table<Fq><<<(64 * 15 + 63) / 64, 64, 0, st>>>(d1tab, delta1);
+  k_fixed_table<Fq2><<<(64 * 15 + 63) / 64, 64, 0, st>>>(d2tab, delta2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const FinalizeParams &P, cudaStream_t st) {
+  k_finalize<<<P.n, 128, 0, st>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace zkb

@@ -11,6 +11,10 @@
 // swapping the roles of the two accumulators every row.  Integer pipe only - there is no dense
 // contraction here for tensor cores to do.
 //
+// Inline-asm rule used throughout: an asm block holds a whole carry chain (the CC flag never crosses
+// statements) and every pure output that is written before the last input is read is early-clobber
+// ("=&r"), otherwise ptxas/nvcc may give it the register of a not-yet-consumed input.
+//
 // The host versions (plain 64-bit C) exist for two reasons: host-side table preparation, and so
 // that the per-thread algorithms built on top (curve formulas, Poseidon, the census witness
 // program) can be unit-tested on a machine without a GPU.  They are not a product fallback: every
@@ -116,8 +120,8 @@ struct alignas(16) Fp {
         "subc.cc.u32 %6, %15, %23;\n\t"
         "subc.cc.u32 %7, %16, %24;\n\t"
         "subc.u32 %8, 0, 0;\n\t"
-        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]),
-          "=r"(borrow)
+        : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]),
+          "=&r"(borrow)
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
           "r"(P::mod(0)), "r"(P::mod(1)), "r"(P::mod(2)), "r"(P::mod(3)), "r"(P::mod(4)), "r"(P::mod(5)),
           "r"(P::mod(6)), "r"(P::mod(7)));
@@ -148,8 +152,8 @@ struct alignas(16) Fp {
         "addc.cc.u32 %5, %13, %21;\n\t"
         "addc.cc.u32 %6, %14, %22;\n\t"
         "addc.u32 %7, %15, %23;\n\t"
-        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
-          "=r"(r.v[7])
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]),
+          "=&r"(r.v[7])
         : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(o.v[0]),
           "r"(o.v[1]), "r"(o.v[2]), "r"(o.v[3]), "r"(o.v[4]), "r"(o.v[5]), "r"(o.v[6]), "r"(o.v[7]));
 #else
@@ -177,8 +181,8 @@ struct alignas(16) Fp {
         "subc.cc.u32 %6, %15, %23;\n\t"
         "subc.cc.u32 %7, %16, %24;\n\t"
         "subc.u32 %8, 0, 0;\n\t"
-        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
-          "=r"(r.v[7]), "=r"(borrow)
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]),
+          "=&r"(r.v[7]), "=&r"(borrow)
         : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(o.v[0]),
           "r"(o.v[1]), "r"(o.v[2]), "r"(o.v[3]), "r"(o.v[4]), "r"(o.v[5]), "r"(o.v[6]), "r"(o.v[7]));
     if (borrow) {

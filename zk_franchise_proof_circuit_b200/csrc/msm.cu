@@ -260,22 +260,81 @@ template <> struct AccCfg<Fq> { static constexpr int THREADS = 128; static const
 template <> struct AccCfg<Fq2> { static constexpr int THREADS = 64; static constexpr int RED_THREADS = 32; };
 
 template <class F>
-cudaError_t msm_run(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
-                    XYZZ<F> *out, cudaStream_t st) {
-  if (ntab < 1 || ntab > 4 || nbatch * (uint32_t)ntab > work.slots) return cudaErrorInvalidValue;
+cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
+                           uint32_t slot0, cudaStream_t st) {
+  if (ntab < 1 || ntab > 4 || slot0 + nbatch * (uint32_t)ntab > work.slots) return cudaErrorInvalidValue;
   TablePtrs<F> tp;
   for (int i = 0; i < 4; i++) tp.tab[i] = i < ntab ? tables[i].tab : nullptr;
   for (int i = 0; i < ntab; i++)
     if (tables[i].n != sort.n) return cudaErrorInvalidValue;
-  constexpr int TH = AccCfg<F>::THREADS, RT = AccCfg<F>::RED_THREADS;
+  constexpr int TH = AccCfg<F>::THREADS;
   dim3 grid(MSM_BUCKETS / TH, ntab, nbatch);
-  k_accumulate<F, TH><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.offsets, sort.entries, work.buckets);
-  uint32_t slots = nbatch * ntab;
-  dim3 g1(RED_PARTS / RT, slots);
-  k_reduce1<F, RT><<<g1, RT, 0, st>>>(work.buckets, work.part_r, work.part_s);
-  k_reduce2<F><<<slots, 32, 0, st>>>(work.part_r, work.part_s, out);
+  k_accumulate<F, TH><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.offsets, sort.entries,
+                                           work.buckets + (size_t)slot0 * MSM_BUCKETS);
   return cudaGetLastError();
 }
+
+// out[i] = sum_b (b+1) * buckets[slot0 + i][b], i < nslots
+template <class F>
+cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F> *out, cudaStream_t st) {
+  if (slot0 + nslots > work.slots) return cudaErrorInvalidValue;
+  constexpr int RT = AccCfg<F>::RED_THREADS;
+  dim3 g1(RED_PARTS / RT, nslots);
+  k_reduce1<F, RT><<<g1, RT, 0, st>>>(work.buckets + (size_t)slot0 * MSM_BUCKETS, work.part_r + (size_t)slot0 * RED_PARTS,
+                                      work.part_s + (size_t)slot0 * RED_PARTS);
+  k_reduce2<F><<<nslots, 32, 0, st>>>(work.part_r + (size_t)slot0 * RED_PARTS, work.part_s + (size_t)slot0 * RED_PARTS, out);
+  return cudaGetLastError();
+}
+
+template <class F>
+cudaError_t msm_run(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
+                    XYZZ<F> *out, cudaStream_t st) {
+  cudaError_t e = msm_accumulate<F>(sort, tables, ntab, nbatch, work, 0, st);
+  if (e != cudaSuccess) return e;
+  return msm_reduce<F>(work, 0, nbatch * (uint32_t)ntab, out, st);
+}
+
+// executed mixed adds of one accumulate launch: per bucket (non-infinity entries - 1)+, summed
+__global__ void k_count_madds(const uint8_t *inf_mask, uint32_t n, const uint32_t *offsets, const uint32_t *entries,
+                              unsigned long long *total) {
+  uint32_t bucket = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t b = blockIdx.y;
+  const uint32_t *off = offsets + (size_t)b * (MSM_BUCKETS + 1);
+  const uint32_t *ent = entries + (size_t)b * n * MSM_WINDOWS;
+  uint32_t cnt = 0;
+  for (uint32_t e = off[bucket]; e < off[bucket + 1]; e++) cnt += inf_mask[(ent[e] & 0x7fffffffu) % n] ? 0u : 1u;
+  if (cnt > 1) atomicAdd(total, (unsigned long long)(cnt - 1));
+}
+
+template <class F>
+__global__ void k_inf_mask(const Affine<F> *tab, uint32_t n, uint8_t *mask) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) mask[k] = ldg_pod(tab + k).is_inf() ? 1 : 0;
+}
+
+template <class F>
+cudaError_t msm_count_madds(const MsmSort &sort, const MsmTable<F> &table, uint32_t nbatch, unsigned long long *host_total,
+                            cudaStream_t st) {
+  uint8_t *mask = nullptr;
+  unsigned long long *dtot = nullptr;
+  CK(cudaMalloc(&mask, table.n));
+  CK(cudaMalloc(&dtot, 8));
+  CK(cudaMemsetAsync(dtot, 0, 8, st));
+  k_inf_mask<F><<<(table.n + 255) / 256, 256, 0, st>>>(table.tab, table.n, mask);
+  dim3 grid(MSM_BUCKETS / 128, nbatch);
+  k_count_madds<<<grid, 128, 0, st>>>(mask, sort.n, sort.offsets, sort.entries, dtot);
+  CK(cudaMemcpyAsync(host_total, dtot, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(mask);
+  cudaFree(dtot);
+  return cudaGetLastError();
+}
+template cudaError_t msm_count_madds<Fq>(const MsmSort &, const MsmTable<Fq> &, uint32_t, unsigned long long *, cudaStream_t);
+template cudaError_t msm_count_madds<Fq2>(const MsmSort &, const MsmTable<Fq2> &, uint32_t, unsigned long long *, cudaStream_t);
+template cudaError_t msm_accumulate<Fq>(const MsmSort &, const MsmTable<Fq> *, int, uint32_t, MsmWork<Fq> &, uint32_t, cudaStream_t);
+template cudaError_t msm_accumulate<Fq2>(const MsmSort &, const MsmTable<Fq2> *, int, uint32_t, MsmWork<Fq2> &, uint32_t, cudaStream_t);
+template cudaError_t msm_reduce<Fq>(MsmWork<Fq> &, uint32_t, uint32_t, XYZZ<Fq> *, cudaStream_t);
+template cudaError_t msm_reduce<Fq2>(MsmWork<Fq2> &, uint32_t, uint32_t, XYZZ<Fq2> *, cudaStream_t);
 template cudaError_t msm_run<Fq>(const MsmSort &, const MsmTable<Fq> *, int, uint32_t, MsmWork<Fq> &, XYZZ<Fq> *,
                                  cudaStream_t);
 template cudaError_t msm_run<Fq2>(const MsmSort &, const MsmTable<Fq2> *, int, uint32_t, MsmWork<Fq2> &, XYZZ<Fq2> *,

@@ -52,4 +52,15 @@ template <class F>
 cudaError_t msm_run(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
                     XYZZ<F> *out, cudaStream_t st);
 
+// split form: bucket sums of (batch item b, table t) go to work.buckets[slot0 + b*ntab + t]; reduce separately
+template <class F>
+cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
+                           uint32_t slot0, cudaStream_t st);
+template <class F>
+cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F> *out, cudaStream_t st);
+// exact number of mixed adds an accumulate launch over (sort, table) executes (measurement aid, not timed)
+template <class F>
+cudaError_t msm_count_madds(const MsmSort &sort, const MsmTable<F> &table, uint32_t nbatch, unsigned long long *host_total,
+                            cudaStream_t st);
+
 }  // namespace zkb

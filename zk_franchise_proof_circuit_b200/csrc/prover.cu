@@ -1,0 +1,944 @@
+// Census Groth16 prover: circuit loading, the batched GPU pipeline and the C ABI
+// (include/zkcensus_b200.h).  Replaces what runs behind `prover.Prove(zkey, wasm, inputs)`
+// (`zk_census_test.go:89`) / `groth16.fullProve` (`ts_inputs/src/example.ts:358-362`):
+//
+//   inputs.json --host parse--> 2n+12 canonical Fr values per proof --H2D-->
+//   k_witness        census witness, 3 threads per proof            
+//   k_build_abc      A_T, B_T from the CSR coefficients, C_T = A_T o B_T   (G2)
+//   NTT              iNTT -> coset shift -> NTT on 3 vectors per proof     (G3)
+//   k_join           h = a*b - c, to canonical form                        (G4)
+//   MSM              A, B1, C (G1) + B2 (G2) over the witness, H over h    (G5)
+//   k_finalize       blinding with r,s and affine conversion               (G6)
+//   --D2H--> 256 B proof + nPublic*32 B public signals --host format--> proof.json / public.json (G7)
+//
+// Everything heavy is device code; the host only parses/prints decimal strings.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+#include <mutex>
+#include <random>
+#include <memory>
+#include <atomic>
+#include <cstdlib>
+#include "common.h"
+#include "ntt.cuh"
+#include "msm.cuh"
+#include "census_witness.cuh"
+#include "finalize_kernels.h"
+#include "wasm_circuit.h"
+#include "zkey.h"
+#include "json_io.h"
+
+namespace zkb {
+
+#define CKR(x, what) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_, what); } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+// Poseidon constants as found in the wasm -> Montgomery form
+__global__ void k_consts_to_mont(Fr *c, const int *form, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr v = c[i];
+  if (form[i] == 0) v = v.to_mont();
+  else if (form[i] == 2) v = v.to_mont().neg();
+  c[i] = v;
+}
+
+__global__ void k_hash_consts(CensusLayout L, const Fr *consts, Fr *hc) {
+  if (threadIdx.x || blockIdx.x) return;
+  WitnessEnv e;
+  e.L = &L; e.consts = consts; e.sig2wire = nullptr; e.out = nullptr; e.status = 0;
+  Fr z2[2] = {Fr::zero(), Fr::zero()};
+  hc[0] = poseidon_ex<3>(e, 0, z2, false);
+  Fr z3[3] = {Fr::zero(), Fr::zero(), Fr::one()};
+  hc[1] = poseidon_ex<4>(e, 0, z3, false);
+}
+
+// thread = (proof, task).  inputs: [n][n_inputs] canonical; wtns: [n][n_wires]
+__global__ void __launch_bounds__(32) k_witness(CensusLayout L, const Fr *consts, const int32_t *sig2wire,
+                                                 const Fr *hc, const Fr *inputs, Fr *wtns, int *status, uint32_t n,
+                                                 int skip_const) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  WitnessEnv e;
+  e.L = &L;
+  e.consts = consts;
+  e.sig2wire = sig2wire;
+  e.out = wtns + (size_t)p * L.n_wires;
+  e.status = 0;
+  const Fr *in = inputs + (size_t)p * L.n_inputs;
+  int task = blockIdx.y;
+  if (task == 2) census_main_task(e, in);
+  else census_tree_task(e, task, in, hc[0], hc[1], skip_const != 0);
+  if (e.status) atomicMax(status + p, e.status);
+}
+
+// batched Poseidon hash with the circuit's constants: in [n][T-1] canonical -> out [n] canonical
+template <int T>
+__global__ void k_poseidon_batch(CensusLayout L, const Fr *consts, const Fr *in, Fr *out, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  WitnessEnv e;
+  e.L = &L; e.consts = consts; e.sig2wire = nullptr; e.out = nullptr; e.status = 0;
+  Fr x[T - 1];
+  for (int j = 0; j < T - 1; j++) x[j] = in[(size_t)i * (T - 1) + j].to_mont();
+  out[i] = poseidon_ex<T>(e, 0, x, false).from_mont();
+}
+
+__global__ void k_fill_template(uint4 *dst, const uint4 *tmpl, size_t per_proof_u4, uint32_t n) {
+  size_t total = per_proof_u4 * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = tmpl[i % per_proof_u4];
+}
+
+__device__ __forceinline__ Fr ldg_fr8(const Fr *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void stg_fr8(Fr *p, const Fr &x) {
+  uint4 *q = reinterpret_cast<uint4 *>(p);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+
+// thread = (row, proof): a = sum coefA * w, b = sum coefB * w, c = a * b  (snarkjs buildABC1)
+struct CsrDev { const uint32_t *row_ptr, *wire; const Fr *value; };
+__global__ void __launch_bounds__(128) k_build_abc(CsrDev A, CsrDev B, const Fr *wtns, size_t wtns_stride, Fr *abc,
+                                                   uint32_t domain) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= domain) return;
+  const Fr *w = wtns + (size_t)blockIdx.y * wtns_stride;
+  Fr a = Fr::zero(), b = Fr::zero();
+  for (uint32_t k = A.row_ptr[row], e = A.row_ptr[row + 1]; k < e; k++) a = a + ldg_fr8(A.value + k) * ldg_fr8(w + A.wire[k]);
+  for (uint32_t k = B.row_ptr[row], e = B.row_ptr[row + 1]; k < e; k++) b = b + ldg_fr8(B.value + k) * ldg_fr8(w + B.wire[k]);
+  Fr *out = abc + (size_t)blockIdx.y * 3 * domain;
+  stg_fr8(out + row, a);
+  stg_fr8(out + domain + row, b);
+  stg_fr8(out + 2 * (size_t)domain + row, a * b);
+}
+
+// h = a * b - c on the odd coset, back to canonical form (snarkjs joinABC)
+__global__ void __launch_bounds__(256) k_join(const Fr *abc, Fr *h, uint32_t domain) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= domain) return;
+  const Fr *in = abc + (size_t)blockIdx.y * 3 * domain;
+  Fr a = ldg_fr8(in + i), b = ldg_fr8(in + domain + i), c = ldg_fr8(in + 2 * (size_t)domain + i);
+  stg_fr8(h + (size_t)blockIdx.y * domain + i, (a * b - c).from_mont());
+}
+
+// ---------------------------------------------------------------------------------------------
+// host objects
+// ---------------------------------------------------------------------------------------------
+static std::atomic<uint64_t> g_launches{0};   // kernels of this library launched by the proving pipeline
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+};
+
+static const char *INPUT_NAMES[12] = {"electionId", "nullifier", "voteHash", "sikRoot", "censusRoot", "voteWeight",
+                                      "availableWeight", "address", "password", "signature", "censusSiblings",
+                                      "sikSiblings"};
+
+struct Circuit {
+  Ctx *ctx = nullptr;
+  uint32_t n_vars = 0, n_public = 0, domain = 0, power = 0;
+  CensusLayout L;
+  uint32_t in_pos[12], in_size[12];
+  // device constants
+  Fr *consts = nullptr, *hc = nullptr, *tmpl = nullptr;
+  int32_t *sig2wire = nullptr;
+  uint32_t *csr_buf = nullptr;
+  Fr *csr_val = nullptr;
+  CsrDev csrA, csrB;
+  NttPlan ntt;
+  MsmTable<Fq> tabA, tabB1, tabC, tabH;
+  MsmTable<Fq2> tabB2;
+  Affine<Fq> *fix1 = nullptr;      // alpha1, beta1
+  Affine<Fq2> *fix2 = nullptr;     // beta2
+  Affine<Fq> *d1tab = nullptr;
+  Affine<Fq2> *d2tab = nullptr;
+  // blinding override (tests): when set every proof uses these r, s
+  bool fixed_rs = false;
+  uint32_t fr[8], fs[8];
+  // batch workspace
+  uint32_t cap = 0;                // proofs resident at once (witness group)
+  uint32_t chunk = 0;              // proofs per NTT/MSM chunk
+  Fr *inputs = nullptr, *wtns = nullptr, *abc = nullptr, *hs = nullptr, *rs = nullptr;
+  int *status = nullptr;
+  MsmSort sortW, sortH;
+  MsmWork<Fq> work1;
+  MsmWork<Fq2> work2;
+  XYZZ<Fq> *g1out = nullptr;
+  XYZZ<Fq2> *g2out = nullptr;
+  XYZZ<Fq> *fin_scratch = nullptr;
+  uint8_t *out = nullptr;          // device results
+  uint8_t *h_out = nullptr;        // pinned
+  Fr *h_inputs = nullptr;          // pinned
+  Fr *h_rs = nullptr;              // pinned
+  int *h_status = nullptr;         // pinned
+  std::mutex mu;
+  uint32_t last_chunk_m = 0;
+  std::mt19937_64 rng;
+  // stage timing of the last device pass (ms)
+  float t_witness = 0, t_abc = 0, t_ntt = 0, t_msm = 0, t_fin = 0;
+  size_t out_stride() const { return 256 + 32 * (size_t)n_public; }
+};
+
+static void random_fr(std::mt19937_64 &g, uint32_t out[8]) {
+  static const uint32_t RMOD[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+  for (;;) {
+    for (int i = 0; i < 8; i += 2) { uint64_t x = g(); out[i] = (uint32_t)x; out[i + 1] = (uint32_t)(x >> 32); }
+    out[7] &= 0x3fffffffu;
+    for (int i = 7; i >= 0; i--) {
+      if (out[i] < RMOD[i]) return;
+      if (out[i] > RMOD[i]) break;
+    }
+  }
+}
+
+static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
+  if (c->cap >= cap && c->chunk >= chunk) return ZKB_OK;
+  // (re)allocate everything; sizes are small next to the 180 GB of HBM
+  cudaFree(c->inputs); cudaFree(c->wtns); cudaFree(c->abc); cudaFree(c->hs); cudaFree(c->rs); cudaFree(c->status);
+  cudaFree(c->g1out); cudaFree(c->g2out); cudaFree(c->out); cudaFree(c->fin_scratch);
+  if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_inputs) cudaFreeHost(c->h_inputs);
+  if (c->h_rs) cudaFreeHost(c->h_rs);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->sortW.counts) c->sortW.free_all();
+  if (c->sortH.counts) c->sortH.free_all();
+  if (c->work1.buckets) c->work1.free_all();
+  if (c->work2.buckets) c->work2.free_all();
+  c->cap = cap;
+  c->chunk = chunk;
+  CKR(cudaMalloc(&c->inputs, (size_t)cap * c->L.n_inputs * 32), "alloc inputs");
+  CKR(cudaMalloc(&c->wtns, (size_t)cap * c->n_vars * 32), "alloc witness");
+  CKR(cudaMalloc(&c->abc, (size_t)chunk * 3 * c->domain * 32), "alloc abc");
+  CKR(cudaMalloc(&c->hs, (size_t)chunk * c->domain * 32), "alloc h");
+  CKR(cudaMalloc(&c->rs, (size_t)cap * 64), "alloc rs");
+  CKR(cudaMalloc(&c->status, (size_t)cap * 4), "alloc status");
+  CKR(cudaMalloc(&c->g1out, (size_t)chunk * 4 * sizeof(XYZZ<Fq>)), "alloc g1out");
+  CKR(cudaMalloc(&c->g2out, (size_t)chunk * sizeof(XYZZ<Fq2>)), "alloc g2out");
+  CKR(cudaMalloc(&c->fin_scratch, (size_t)chunk * 30 * sizeof(XYZZ<Fq>)), "alloc finalize scratch");
+  CKR(cudaMalloc(&c->out, (size_t)cap * c->out_stride()), "alloc out");
+  CKR(cudaMallocHost(&c->h_out, (size_t)cap * c->out_stride()), "alloc pinned out");
+  CKR(cudaMallocHost(&c->h_inputs, (size_t)cap * c->L.n_inputs * 32), "alloc pinned inputs");
+  CKR(cudaMallocHost(&c->h_rs, (size_t)cap * 64), "alloc pinned rs");
+  CKR(cudaMallocHost(&c->h_status, (size_t)cap * 4), "alloc pinned status");
+  CKR(c->sortW.alloc(c->n_vars, chunk), "alloc sortW");
+  CKR(c->sortH.alloc(c->domain, chunk), "alloc sortH");
+  CKR(c->work1.alloc(chunk * 4), "alloc msm work g1");
+  CKR(c->work2.alloc(chunk), "alloc msm work g2");
+  return ZKB_OK;
+}
+
+// witness for proofs [0, n) already in c->inputs
+static int run_witness(Circuit *c, uint32_t n, cudaStream_t st) {
+  CKR(cudaMemsetAsync(c->status, 0, (size_t)n * 4, st), "memset status");
+  size_t per = (size_t)c->n_vars * 2;   // uint4 per proof
+  k_fill_template<<<1184, 256, 0, st>>>(reinterpret_cast<uint4 *>(c->wtns), reinterpret_cast<const uint4 *>(c->tmpl),
+                                        per, n);
+  dim3 grid((n + 31) / 32, 3);
+  k_witness<<<grid, 32, 0, st>>>(c->L, c->consts, c->sig2wire, c->hc, c->inputs, c->wtns, c->status, n, 1);
+  g_launches += 2;
+  return cudaGetLastError() == cudaSuccess ? ZKB_OK : cuda_fail(cudaGetLastError(), "witness launch");
+}
+
+// Groth16 for proofs [first, first + m) of the resident witnesses, m <= chunk
+static int run_prove_chunk(Circuit *c, uint32_t first, uint32_t m, cudaStream_t st, cudaEvent_t *ev) {
+  const Fr *w = c->wtns + (size_t)first * c->n_vars;
+  dim3 g1((c->domain + 127) / 128, m);
+  k_build_abc<<<g1, 128, 0, st>>>(c->csrA, c->csrB, w, c->n_vars, c->abc, c->domain);
+  g_launches += 1 + 4 + 1;   // build_abc, 2 DIF + 2 DIT passes, join
+  if (ev) cudaEventRecord(ev[1], st);
+  CKR(c->ntt.dif(c->abc, 3 * m, c->domain, true, true, st), "ntt dif");
+  CKR(c->ntt.dit(c->abc, 3 * m, c->domain, false, st), "ntt dit");
+  dim3 g2((c->domain + 255) / 256, m);
+  k_join<<<g2, 256, 0, st>>>(c->abc, c->hs, c->domain);
+  if (ev) cudaEventRecord(ev[2], st);
+  CKR(c->sortW.run(w, c->n_vars, m, st), "sort witness digits");
+  CKR(c->sortH.run(c->hs, c->domain, m, st), "sort h digits");
+  if (ev) cudaEventRecord(ev[3], st);
+  // bucket sums: G1 over the witness (A, B1, C share one sort) -> slots [0, 3m); H -> slots [3*chunk, 3*chunk + m)
+  MsmTable<Fq> tabs[3] = {c->tabA, c->tabB1, c->tabC};
+  CKR(msm_accumulate<Fq>(c->sortW, tabs, 3, m, c->work1, 0, st), "msm accumulate g1 (A,B1,C)");
+  CKR(msm_accumulate<Fq>(c->sortH, &c->tabH, 1, m, c->work1, 3 * c->chunk, st), "msm accumulate g1 (H)");
+  if (ev) cudaEventRecord(ev[4], st);
+  CKR(msm_accumulate<Fq2>(c->sortW, &c->tabB2, 1, m, c->work2, 0, st), "msm accumulate g2 (B2)");
+  if (ev) cudaEventRecord(ev[5], st);
+  CKR(msm_reduce<Fq>(c->work1, 0, 3 * m, c->g1out, st), "msm reduce g1");
+  CKR(msm_reduce<Fq>(c->work1, 3 * c->chunk, m, c->g1out + (size_t)3 * c->chunk, st), "msm reduce g1 (H)");
+  CKR(msm_reduce<Fq2>(c->work2, 0, m, c->g2out, st), "msm reduce g2");
+  if (ev) cudaEventRecord(ev[6], st);
+  g_launches += 6 + 2 + 1 + 6;
+  FinalizeParams P;
+  P.g1 = c->g1out;
+  P.g1h = c->g1out + (size_t)3 * c->chunk;
+  P.g2 = c->g2out;
+  P.rs = c->rs + (size_t)first * 2;
+  P.wtns = w;
+  P.wtns_stride = c->n_vars;
+  P.alpha1 = c->fix1;
+  P.beta1 = c->fix1 + 1;
+  P.d1tab = c->d1tab;
+  P.beta2 = c->fix2;
+  P.d2tab = c->d2tab;
+  P.scratch = c->fin_scratch;
+  P.out = c->out + (size_t)first * c->out_stride();
+  P.n_public = c->n_public;
+  P.n = m;
+  CKR(launch_finalize(P, st), "finalize");
+  g_launches += 1;
+  if (ev) cudaEventRecord(ev[7], st);
+  CKR(cudaGetLastError(), "prove chunk launch");
+  return ZKB_OK;
+}
+
+// full device pass over the n resident proofs; stage_ms (optional, 8 floats): witness, build_abc, ntt+join,
+// msm sort, msm accumulate G1, msm accumulate G2, msm reduce, finalize
+static int prove_resident(Circuit *c, uint32_t n, bool with_witness, float *stage_ms) {
+  cudaStream_t st = c->ctx->stream;
+  std::vector<cudaEvent_t> evs;
+  auto newev = [&]() { cudaEvent_t e; cudaEventCreate(&e); evs.push_back(e); return e; };
+  cudaEvent_t w0 = nullptr, w1 = nullptr;
+  if (stage_ms) { w0 = newev(); w1 = newev(); cudaEventRecord(w0, st); }
+  if (with_witness) { int rc = run_witness(c, n, st); if (rc) return rc; }
+  if (stage_ms) cudaEventRecord(w1, st);
+  std::vector<cudaEvent_t> chunk_ev;
+  for (uint32_t first = 0; first < n; first += c->chunk) {
+    uint32_t m = n - first < c->chunk ? n - first : c->chunk;
+    cudaEvent_t ev[8];
+    if (stage_ms) {
+      for (int i = 0; i < 8; i++) { ev[i] = newev(); chunk_ev.push_back(ev[i]); }
+      cudaEventRecord(ev[0], st);
+    }
+    int rc = run_prove_chunk(c, first, m, st, stage_ms ? ev : nullptr);
+    if (rc) return rc;
+    c->last_chunk_m = m;
+  }
+  CKR(cudaStreamSynchronize(st), "prove");
+  if (stage_ms) {
+    for (int i = 0; i < 8; i++) stage_ms[i] = 0;
+    cudaEventElapsedTime(&stage_ms[0], w0, w1);
+    for (size_t k = 0; k + 7 < chunk_ev.size(); k += 8)
+      for (int i = 0; i < 7; i++) { float t; cudaEventElapsedTime(&t, chunk_ev[k + i], chunk_ev[k + i + 1]); stage_ms[1 + i] += t; }
+  }
+  for (auto e : evs) cudaEventDestroy(e);
+  return ZKB_OK;
+}
+
+static void fill_blinding(Circuit *c, uint32_t n) {
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t *r = c->h_rs[2 * i].v, *s = c->h_rs[2 * i + 1].v;
+    if (c->fixed_rs) { memcpy(r, c->fr, 32); memcpy(s, c->fs, 32); }
+    else { random_fr(c->rng, r); random_fr(c->rng, s); }
+  }
+}
+
+// inputs.json -> canonical values in main-signal order (n_inputs x 8 u32)
+static int pack_inputs(const Circuit *c, const char *json, size_t len, uint32_t *dst, std::string &err) {
+  std::map<std::string, std::vector<uint32_t>> m;
+  if (!parse_inputs_json(json, len, m, err)) return ZKB_ERROR;
+  size_t total = 0;
+  for (int k = 0; k < 12; k++) {
+    auto it = m.find(INPUT_NAMES[k]);
+    if (it == m.end()) { err = std::string("inputs: signal not found: ") + INPUT_NAMES[k]; return ZKB_ERROR; }
+    if (it->second.size() != (size_t)c->in_size[k] * 8) { err = std::string("inputs: wrong number of values for ") + INPUT_NAMES[k]; return ZKB_ERROR; }
+    memcpy(dst + (size_t)(c->in_pos[k] - 1) * 8, it->second.data(), it->second.size() * 4);
+    total += c->in_size[k];
+  }
+  if (m.size() != 12) { err = "inputs: unexpected signal (not an input of the census circuit)"; return ZKB_ERROR; }
+  if (total != c->L.n_inputs) { err = "inputs: size mismatch"; return ZKB_ERROR; }
+  return ZKB_OK;
+}
+
+static uint32_t env_u32(const char *name, uint32_t dflt) {
+  const char *v = getenv(name);
+  if (!v || !*v) return dflt;
+  long x = atol(v);
+  return x > 0 ? (uint32_t)x : dflt;
+}
+
+template <class T>
+static cudaError_t upload(T **dptr, const void *src, size_t bytes) {
+  cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 16);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+}
+
+static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const uint8_t *wasm, size_t wasm_len,
+                        Circuit **out) {
+  CKR(cudaSetDevice(ctx->device), "set device");
+  std::string err;
+  ZkeyView z;
+  if (!parse_zkey(zkey, zkey_len, z, err)) { set_error(err); return ZKB_ERROR; }
+  std::unique_ptr<Circuit> c(new Circuit());
+  c->ctx = ctx;
+  c->n_vars = z.n_vars; c->n_public = z.n_public; c->domain = z.domain; c->power = z.power;
+  std::random_device rd;
+  c->rng.seed(((uint64_t)rd() << 32) ^ rd());
+  cudaStream_t st = ctx->stream;
+  memset(&c->L, 0, sizeof c->L);
+
+  if (wasm) {
+    WasmCircuit w;
+    if (!parse_circom_wasm(wasm, wasm_len, w, err)) { set_error(err); return ZKB_UNSUPPORTED_CIRCUIT; }
+    uint32_t pos = 0, size = 0;
+    if (!wasm_input_lookup(w, "censusSiblings", pos, size) || size < 4) { set_error("wasm is not the census circuit (censusSiblings missing)"); return ZKB_UNSUPPORTED_CIRCUIT; }
+    if (!census_layout_build(c->L, size)) { set_error("unsupported number of levels"); return ZKB_UNSUPPORTED_CIRCUIT; }
+    c->L.n_wires = w.n_wires;
+    const uint32_t expect_pos[12] = {c->L.electionId, c->L.nullifier, c->L.voteHash, c->L.sikRoot, c->L.censusRoot,
+                                     c->L.voteWeight, c->L.availableWeight, c->L.address, c->L.password,
+                                     c->L.signature, c->L.censusSiblings, c->L.sikSiblings};
+    const uint32_t expect_size[12] = {2, 1, 2, 1, 1, 1, 1, 1, 1, 1, size, size};
+    for (int k = 0; k < 12; k++) {
+      if (!wasm_input_lookup(w, INPUT_NAMES[k], c->in_pos[k], c->in_size[k]) || c->in_pos[k] != expect_pos[k] ||
+          c->in_size[k] != expect_size[k]) {
+        set_error(std::string("wasm is not the census circuit (input ") + INPUT_NAMES[k] + ")");
+        return ZKB_UNSUPPORTED_CIRCUIT;
+      }
+    }
+    if (w.n_inputs != c->L.n_inputs || w.witness_map.back() >= c->L.n_signals || w.witness_map[0] != 0) {
+      set_error("wasm is not the census circuit (signal layout mismatch)");
+      return ZKB_UNSUPPORTED_CIRCUIT;
+    }
+    if (w.n_wires != z.n_vars) { set_error("zkey and wasm disagree on the number of wires"); return ZKB_INVALID_WITNESS_LENGTH; }
+    if (z.n_public != 8) { set_error("census circuit has 8 public signals; zkey says otherwise"); return ZKB_UNSUPPORTED_CIRCUIT; }
+    // constants
+    std::vector<uint32_t> cbuf;
+    std::vector<int> forms;
+    uint32_t off = 0;
+    for (int ti = 0; ti < 3; ti++) {
+      uint32_t *offs[4] = {&c->L.pex[ti].c_off, &c->L.pex[ti].s_off, &c->L.pex[ti].m_off, &c->L.pex[ti].p_off};
+      for (int k = 0; k < 4; k++) {
+        *offs[k] = off;
+        for (auto &pc : w.poseidon[ti].tab[k]) { cbuf.insert(cbuf.end(), pc.v, pc.v + 8); forms.push_back(pc.form); }
+        off += (uint32_t)w.poseidon[ti].tab[k].size();
+      }
+    }
+    int *dforms = nullptr;
+    CKR(upload(&c->consts, cbuf.data(), cbuf.size() * 4), "upload poseidon constants");
+    CKR(upload(&dforms, forms.data(), forms.size() * 4), "upload forms");
+    k_consts_to_mont<<<(off + 127) / 128, 128, 0, st>>>(c->consts, dforms, off);
+    std::vector<int32_t> s2w(c->L.n_signals, -1);
+    for (uint32_t i = 0; i < w.n_wires; i++) s2w[w.witness_map[i]] = (int32_t)i;
+    CKR(upload(&c->sig2wire, s2w.data(), s2w.size() * 4), "upload sig2wire");
+    CKR(cudaMalloc(&c->hc, 64), "alloc hc");
+    k_hash_consts<<<1, 1, 0, st>>>(c->L, c->consts, c->hc);
+    // template witness: the program itself on all-zero inputs, constant blocks included
+    CKR(cudaMalloc(&c->tmpl, (size_t)c->n_vars * 32), "alloc template");
+    CKR(cudaMemsetAsync(c->tmpl, 0, (size_t)c->n_vars * 32, st), "memset");
+    Fr *zin = nullptr;
+    int *zst = nullptr;
+    CKR(cudaMalloc(&zin, (size_t)c->L.n_inputs * 32), "alloc");
+    CKR(cudaMalloc(&zst, 4), "alloc");
+    CKR(cudaMemsetAsync(zin, 0, (size_t)c->L.n_inputs * 32, st), "memset");
+    CKR(cudaMemsetAsync(zst, 0, 4, st), "memset");
+    k_witness<<<dim3(1, 3), 32, 0, st>>>(c->L, c->consts, c->sig2wire, c->hc, zin, c->tmpl, zst, 1, 0);
+    CKR(cudaStreamSynchronize(st), "witness template");
+    cudaFree(zin); cudaFree(zst); cudaFree(dforms);
+  }
+
+  // coefficient matrices (CSR by row)
+  {
+    CoefCsr A, B;
+    build_csr(z, 0, A);
+    build_csr(z, 1, B);
+    size_t nA = A.wire.size(), nB = B.wire.size(), rp = (size_t)z.domain + 1;
+    std::vector<uint32_t> ibuf;
+    ibuf.insert(ibuf.end(), A.row_ptr.begin(), A.row_ptr.end());
+    ibuf.insert(ibuf.end(), B.row_ptr.begin(), B.row_ptr.end());
+    ibuf.insert(ibuf.end(), A.wire.begin(), A.wire.end());
+    ibuf.insert(ibuf.end(), B.wire.begin(), B.wire.end());
+    CKR(upload(&c->csr_buf, ibuf.data(), ibuf.size() * 4), "upload csr");
+    std::vector<uint8_t> vbuf(A.value);
+    vbuf.insert(vbuf.end(), B.value.begin(), B.value.end());
+    CKR(upload(&c->csr_val, vbuf.data(), vbuf.size()), "upload csr values");
+    c->csrA = {c->csr_buf, c->csr_buf + 2 * rp, c->csr_val};
+    c->csrB = {c->csr_buf + rp, c->csr_buf + 2 * rp + nA, c->csr_val + nA};
+    (void)nB;
+  }
+  CKR(c->ntt.init(z.power, st), "ntt plan");
+  // fixed-base MSM tables from sections 5-9
+  {
+    Affine<Fq> *d1 = nullptr;
+    Affine<Fq2> *d2 = nullptr;
+    auto build1 = [&](MsmTable<Fq> &t, const uint8_t *src, uint32_t n, uint32_t pad_front) -> int {
+      std::vector<uint8_t> tmp;
+      const uint8_t *p = src;
+      if (pad_front) { tmp.assign((size_t)(n + pad_front) * 64, 0); memcpy(tmp.data() + (size_t)pad_front * 64, src, (size_t)n * 64); p = tmp.data(); }
+      CKR(upload(&d1, p, (size_t)(n + pad_front) * 64), "upload bases");
+      CKR(msm_build_table<Fq>(t, d1, n + pad_front, st), "build table");
+      CKR(cudaStreamSynchronize(st), "build table");
+      cudaFree(d1);
+      return ZKB_OK;
+    };
+    int rc;
+    if ((rc = build1(c->tabA, z.a, z.n_vars, 0))) return rc;
+    if ((rc = build1(c->tabB1, z.b1, z.n_vars, 0))) return rc;
+    if ((rc = build1(c->tabC, z.c, z.n_vars - z.n_public - 1, z.n_public + 1))) return rc;
+    if ((rc = build1(c->tabH, z.h, z.domain, 0))) return rc;
+    CKR(upload(&d2, z.b2, (size_t)z.n_vars * 128), "upload bases");
+    CKR(msm_build_table<Fq2>(c->tabB2, d2, z.n_vars, st), "build table");
+    CKR(cudaStreamSynchronize(st), "build table");
+    cudaFree(d2);
+  }
+  // alpha1, beta1, beta2, delta tables
+  {
+    uint8_t f1[128];
+    memcpy(f1, z.alpha1, 64);
+    memcpy(f1 + 64, z.beta1, 64);
+    CKR(upload(&c->fix1, f1, 128), "upload");
+    CKR(upload(&c->fix2, z.beta2, 128), "upload");
+    Affine<Fq> *dl1 = nullptr;
+    Affine<Fq2> *dl2 = nullptr;
+    CKR(upload(&dl1, z.delta1, 64), "upload");
+    CKR(upload(&dl2, z.delta2, 128), "upload");
+    CKR(cudaMalloc(&c->d1tab, 64 * 15 * sizeof(Affine<Fq>)), "alloc");
+    CKR(cudaMalloc(&c->d2tab, 64 * 15 * sizeof(Affine<Fq2>)), "alloc");
+    CKR(launch_fixed_tables(c->d1tab, dl1, c->d2tab, dl2, st), "delta tables");
+    CKR(cudaStreamSynchronize(st), "delta tables");
+    cudaFree(dl1); cudaFree(dl2);
+  }
+  CKR(cudaGetLastError(), "load circuit");
+  *out = c.release();
+  return ZKB_OK;
+}
+
+static void destroy_circuit(Circuit *c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  cudaFree(c->consts); cudaFree(c->hc); cudaFree(c->tmpl); cudaFree(c->sig2wire); cudaFree(c->csr_buf);
+  cudaFree(c->csr_val); cudaFree(c->fix1); cudaFree(c->fix2); cudaFree(c->d1tab); cudaFree(c->d2tab);
+  cudaFree(c->tabA.tab); cudaFree(c->tabB1.tab); cudaFree(c->tabC.tab); cudaFree(c->tabH.tab); cudaFree(c->tabB2.tab);
+  c->ntt.destroy();
+  cudaFree(c->inputs); cudaFree(c->wtns); cudaFree(c->abc); cudaFree(c->hs); cudaFree(c->rs); cudaFree(c->status);
+  cudaFree(c->g1out); cudaFree(c->g2out); cudaFree(c->out); cudaFree(c->fin_scratch);
+  if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_inputs) cudaFreeHost(c->h_inputs);
+  if (c->h_rs) cudaFreeHost(c->h_rs);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->sortW.counts) c->sortW.free_all();
+  if (c->sortH.counts) c->sortH.free_all();
+  if (c->work1.buckets) c->work1.free_all();
+  if (c->work2.buckets) c->work2.free_all();
+  delete c;
+}
+
+static int copy_out(const std::string &s, char *buf, size_t *size) {
+  size_t need = s.size() + 1;
+  if (!buf || *size < need) { *size = need; return ZKB_SHORT_BUFFER; }
+  memcpy(buf, s.c_str(), need);
+  *size = s.size();
+  return ZKB_OK;
+}
+
+// upload h_inputs[0..n) + blinding, run, download results/status
+static int prove_group(Circuit *c, uint32_t n, bool with_witness, float *stage_ms) {
+  cudaStream_t st = c->ctx->stream;
+  if (with_witness)
+    CKR(cudaMemcpyAsync(c->inputs, c->h_inputs, (size_t)n * c->L.n_inputs * 32, cudaMemcpyHostToDevice, st), "h2d inputs");
+  fill_blinding(c, n);
+  CKR(cudaMemcpyAsync(c->rs, c->h_rs, (size_t)n * 64, cudaMemcpyHostToDevice, st), "h2d rs");
+  int rc = prove_resident(c, n, with_witness, stage_ms);
+  if (rc) return rc;
+  CKR(cudaMemcpyAsync(c->h_out, c->out, (size_t)n * c->out_stride(), cudaMemcpyDeviceToHost, st), "d2h");
+  if (with_witness) CKR(cudaMemcpyAsync(c->h_status, c->status, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "d2h status");
+  else memset(c->h_status, 0, (size_t)n * 4);
+  CKR(cudaStreamSynchronize(st), "sync");
+  return ZKB_OK;
+}
+
+}  // namespace zkb
+
+using namespace zkb;
+
+struct zkb_ctx { Ctx c; };
+struct zkb_circuit { Circuit *c; };
+
+extern "C" {
+
+int zkb_ctx_create(int device, zkb_ctx **out) {
+  if (require_device()) return ZKB_ERROR;
+  int n = 0;
+  cudaGetDeviceCount(&n);
+  if (device < 0 || device >= n) { set_error("invalid device index"); return ZKB_ERROR; }
+  CKR(cudaSetDevice(device), "set device");
+  zkb_ctx *x = new zkb_ctx();
+  x->c.device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&x->c.stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete x; return cuda_fail(e, "stream create"); }
+  *out = x;
+  return ZKB_OK;
+}
+
+void zkb_ctx_destroy(zkb_ctx *x) {
+  if (!x) return;
+  cudaSetDevice(x->c.device);
+  cudaStreamDestroy(x->c.stream);
+  delete x;
+}
+
+void *zkb_ctx_stream(zkb_ctx *x) { return (void *)x->c.stream; }
+
+int zkb_load_circuit(zkb_ctx *ctx, const void *zkey, size_t zkey_len, const void *wasm, size_t wasm_len,
+                     zkb_circuit **out) {
+  if (!ctx || !zkey || !out) { set_error("null argument"); return ZKB_ERROR; }
+  Circuit *c = nullptr;
+  int rc = load_circuit(&ctx->c, (const uint8_t *)zkey, zkey_len, (const uint8_t *)wasm, wasm_len, &c);
+  if (rc) return rc;
+  *out = new zkb_circuit{c};
+  return ZKB_OK;
+}
+
+void zkb_circuit_destroy(zkb_circuit *h) {
+  if (!h) return;
+  destroy_circuit(h->c);
+  delete h;
+}
+
+// info: n_vars, n_public, domain, n_inputs, n_levels_plus1, n_signals, chunk, cap
+int zkb_circuit_info(zkb_circuit *h, uint32_t *info) {
+  Circuit *c = h->c;
+  info[0] = c->n_vars; info[1] = c->n_public; info[2] = c->domain; info[3] = c->L.n_inputs;
+  info[4] = c->L.n; info[5] = c->L.n_signals; info[6] = c->chunk; info[7] = c->cap;
+  return ZKB_OK;
+}
+
+// r32 / s32: canonical little-endian scalars < r; both NULL restores random blinding
+int zkb_set_blinding(zkb_circuit *h, const uint8_t *r32, const uint8_t *s32) {
+  Circuit *c = h->c;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!r32 || !s32) { c->fixed_rs = false; return ZKB_OK; }
+  memcpy(c->fr, r32, 32);
+  memcpy(c->fs, s32, 32);
+  c->fixed_rs = true;
+  return ZKB_OK;
+}
+
+// ---- resident-input path (device-only timing of the hot path) ---------------------------------
+// inputs: n x n_inputs canonical 32-byte values in main-signal order (electionId[2], nullifier, voteHash[2],
+// sikRoot, censusRoot, voteWeight, availableWeight, address, password, signature, censusSiblings, sikSiblings)
+int zkb_batch_set_inputs(zkb_circuit *h, int n, const void *inputs) {
+  Circuit *c = h->c;
+  if (!c->consts) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  uint32_t chunk = env_u32("ZKB_CHUNK", 16);
+  int rc = ensure_workspace(c, (uint32_t)n, chunk);
+  if (rc) return rc;
+  CKR(cudaMemcpyAsync(c->inputs, inputs, (size_t)n * c->L.n_inputs * 32, cudaMemcpyHostToDevice, c->ctx->stream), "h2d inputs");
+  fill_blinding(c, n);
+  CKR(cudaMemcpyAsync(c->rs, c->h_rs, (size_t)n * 64, cudaMemcpyHostToDevice, c->ctx->stream), "h2d rs");
+  CKR(cudaStreamSynchronize(c->ctx->stream), "sync");
+  return ZKB_OK;
+}
+
+// runs witness + Groth16 on the resident inputs, results stay on the device.  stage_ms: 5 floats or NULL.
+int zkb_batch_prove_resident(zkb_circuit *h, int n, float *stage_ms) {
+  Circuit *c = h->c;
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  if ((uint32_t)n > c->cap) { set_error("more proofs than resident inputs"); return ZKB_ERROR; }
+  return prove_resident(c, (uint32_t)n, true, stage_ms);
+}
+
+// proofs256: n x 256 B; publics: n x n_public x 32 B; status: n ints (0 ok, 4 assert failed)
+int zkb_batch_get_results(zkb_circuit *h, int n, void *proofs256, void *publics, int *status) {
+  Circuit *c = h->c;
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  cudaStream_t st = c->ctx->stream;
+  CKR(cudaMemcpyAsync(c->h_out, c->out, (size_t)n * c->out_stride(), cudaMemcpyDeviceToHost, st), "d2h");
+  CKR(cudaMemcpyAsync(c->h_status, c->status, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "d2h status");
+  CKR(cudaStreamSynchronize(st), "sync");
+  for (int i = 0; i < n; i++) {
+    const uint8_t *o = c->h_out + (size_t)i * c->out_stride();
+    if (proofs256) memcpy((uint8_t *)proofs256 + (size_t)i * 256, o, 256);
+    if (publics) memcpy((uint8_t *)publics + (size_t)i * 32 * c->n_public, o + 256, 32 * (size_t)c->n_public);
+    if (status) status[i] = c->h_status[i];
+  }
+  return ZKB_OK;
+}
+
+// device copy of the n resident witnesses (n x n_vars x 32 B, canonical) - parity tests
+int zkb_batch_get_witness(zkb_circuit *h, int first, int n, void *wtns) {
+  Circuit *c = h->c;
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  CKR(cudaMemcpy(wtns, c->wtns + (size_t)first * c->n_vars, (size_t)n * c->n_vars * 32, cudaMemcpyDeviceToHost), "d2h witness");
+  return ZKB_OK;
+}
+
+uint64_t zkb_launch_count(void) { return g_launches.load(); }
+
+// Work actually executed by the MSM accumulate kernels for the last processed chunk (exact, counted on the device
+// outside any timed region): out[0] = G1 mixed adds (A + B1 + C + H), out[1] = G2 mixed adds (B2), out[2] = sorted
+// digit entries of the witness, out[3] = of the H scalars, out[4] = proofs in that chunk, out[5] = chunk capacity.
+int zkb_work_counters(zkb_circuit *h, uint64_t *out) {
+  Circuit *c = h->c;
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  cudaStream_t st = c->ctx->stream;
+  uint32_t m = c->last_chunk_m;
+  if (!m) { set_error("no chunk processed yet"); return ZKB_ERROR; }
+  unsigned long long t[5] = {0, 0, 0, 0, 0};
+  CKR(msm_count_madds<Fq>(c->sortW, c->tabA, m, &t[0], st), "count");
+  CKR(msm_count_madds<Fq>(c->sortW, c->tabB1, m, &t[1], st), "count");
+  CKR(msm_count_madds<Fq>(c->sortW, c->tabC, m, &t[2], st), "count");
+  CKR(msm_count_madds<Fq>(c->sortH, c->tabH, m, &t[3], st), "count");
+  CKR(msm_count_madds<Fq2>(c->sortW, c->tabB2, m, &t[4], st), "count");
+  out[0] = t[0] + t[1] + t[2] + t[3];
+  out[1] = t[4];
+  uint64_t ew = 0, eh = 0;
+  for (uint32_t b = 0; b < m; b++) {
+    uint32_t v;
+    CKR(cudaMemcpy(&v, c->sortW.offsets + (size_t)b * (MSM_BUCKETS + 1) + MSM_BUCKETS, 4, cudaMemcpyDeviceToHost), "d2h");
+    ew += v;
+    CKR(cudaMemcpy(&v, c->sortH.offsets + (size_t)b * (MSM_BUCKETS + 1) + MSM_BUCKETS, 4, cudaMemcpyDeviceToHost), "d2h");
+    eh += v;
+  }
+  out[2] = ew; out[3] = eh; out[4] = m; out[5] = c->chunk;
+  return ZKB_OK;
+}
+
+// MSM partial sums of the first proof of the last chunk, affine canonical: pi_a'(64) pi_b1'(64) pi_b'(128)
+// pi_c'(64) pi_h(64) = 384 B; and that proof's H scalars (domain x 32 B canonical) when h_out != NULL.
+int zkb_debug_partials(zkb_circuit *h, void *out384, void *h_out) {
+  Circuit *c = h->c;
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  XYZZ<Fq> g1[4];
+  XYZZ<Fq2> g2;
+  CKR(cudaMemcpy(g1, c->g1out, 3 * sizeof(XYZZ<Fq>), cudaMemcpyDeviceToHost), "d2h");
+  CKR(cudaMemcpy(g1 + 3, c->g1out + (size_t)3 * c->chunk, sizeof(XYZZ<Fq>), cudaMemcpyDeviceToHost), "d2h");
+  CKR(cudaMemcpy(&g2, c->g2out, sizeof(XYZZ<Fq2>), cudaMemcpyDeviceToHost), "d2h");
+  uint8_t *o = (uint8_t *)out384;
+  auto put1 = [&](const XYZZ<Fq> &p, uint8_t *dst) {   // host (portable) arithmetic, debug only
+    Affine<Fq> a = p.to_affine();
+    Fq x = a.x.from_mont(), y = a.y.from_mont();
+    memcpy(dst, x.v, 32); memcpy(dst + 32, y.v, 32);
+  };
+  put1(g1[0], o); put1(g1[1], o + 64); put1(g1[2], o + 256); put1(g1[3], o + 320);
+  Affine<Fq2> b = g2.to_affine();
+  Fq cc[4] = {b.x.a.from_mont(), b.x.b.from_mont(), b.y.a.from_mont(), b.y.b.from_mont()};
+  memcpy(o + 128, cc, 128);
+  if (h_out) CKR(cudaMemcpy(h_out, c->hs, (size_t)c->domain * 32, cudaMemcpyDeviceToHost), "d2h h");
+  return ZKB_OK;
+}
+
+// Batched Poseidon over the circuit's own constants (arity 2, 3 or 4): the hash of the census / SIK trees
+// (arbo HashFunctionPoseidon, internal/helpers.go:45-49) - used by the synthetic census generator.
+// in: n x arity canonical 32-byte values; out: n x 32 bytes.
+int zkb_poseidon_hash(zkb_circuit *h, int arity, int n, const void *in, void *out) {
+  Circuit *c = h->c;
+  if (!c->consts) { set_error("circuit was loaded without a wasm: no Poseidon constants"); return ZKB_ERROR; }
+  if (arity < 2 || arity > 4 || n < 0) { set_error("poseidon: arity must be 2, 3 or 4"); return ZKB_ERROR; }
+  if (n == 0) return ZKB_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  cudaStream_t st = c->ctx->stream;
+  Fr *din = nullptr, *dout = nullptr;
+  CKR(cudaMalloc(&din, (size_t)n * arity * 32), "alloc");
+  CKR(cudaMalloc(&dout, (size_t)n * 32), "alloc");
+  CKR(cudaMemcpyAsync(din, in, (size_t)n * arity * 32, cudaMemcpyHostToDevice, st), "h2d");
+  unsigned grid = (unsigned)((n + 63) / 64);
+  if (arity == 2) k_poseidon_batch<3><<<grid, 64, 0, st>>>(c->L, c->consts, din, dout, (uint32_t)n);
+  else if (arity == 3) k_poseidon_batch<4><<<grid, 64, 0, st>>>(c->L, c->consts, din, dout, (uint32_t)n);
+  else k_poseidon_batch<5><<<grid, 64, 0, st>>>(c->L, c->consts, din, dout, (uint32_t)n);
+  CKR(cudaGetLastError(), "poseidon launch");
+  CKR(cudaMemcpyAsync(out, dout, (size_t)n * 32, cudaMemcpyDeviceToHost, st), "d2h");
+  CKR(cudaStreamSynchronize(st), "sync");
+  cudaFree(din); cudaFree(dout);
+  return ZKB_OK;
+}
+
+// ---- reference-shaped entry points ---------------------------------------------------------------
+// n inputs.json documents -> n proof.json / public.json strings (NUL terminated) at the given strides.
+// status[i]: 0 ok, 1 malformed inputs, 4 circuit assert failed.  Returns 0 unless the batch as a whole failed.
+int zkb_fullprove_batch(zkb_circuit *h, int n, const char *const *inputs_json, const size_t *inputs_len, char *proofs,
+                        size_t proof_stride, char *publics, size_t public_stride, int *status) {
+  Circuit *c = h->c;
+  if (!c->consts) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
+  if (n <= 0) return ZKB_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  uint32_t chunk = env_u32("ZKB_CHUNK", 16), group = env_u32("ZKB_GROUP", 1024);
+  uint32_t cap = (uint32_t)n < group ? (uint32_t)n : group;
+  int rc = ensure_workspace(c, cap > c->cap ? cap : c->cap, chunk);
+  if (rc) return rc;
+  for (uint32_t first = 0; first < (uint32_t)n; first += c->cap) {
+    uint32_t m = (uint32_t)n - first < c->cap ? (uint32_t)n - first : c->cap;
+    std::vector<int> bad(m, 0);
+    std::vector<std::string> errs(m);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int i = 0; i < (int)m; i++) {
+      uint32_t *dst = c->h_inputs[(size_t)i * c->L.n_inputs].v;
+      memset(dst, 0, (size_t)c->L.n_inputs * 32);
+      if (pack_inputs(c, inputs_json[first + i], inputs_len[first + i], dst, errs[i])) bad[i] = 1;
+    }
+    rc = prove_group(c, m, true, nullptr);
+    if (rc) return rc;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int i = 0; i < (int)m; i++) {
+      const uint8_t *o = c->h_out + (size_t)i * c->out_stride();
+      int stt = bad[i] ? ZKB_ERROR : c->h_status[i];
+      status[first + i] = stt;
+      char *pb = proofs + (size_t)(first + i) * proof_stride, *qb = publics + (size_t)(first + i) * public_stride;
+      pb[0] = 0;
+      qb[0] = 0;
+      if (stt == 0) {
+        std::string pj = proof_to_json(o, false), sj = publics_to_json(o + 256, c->n_public);
+        if (pj.size() + 1 <= proof_stride && sj.size() + 1 <= public_stride) {
+          memcpy(pb, pj.c_str(), pj.size() + 1);
+          memcpy(qb, sj.c_str(), sj.size() + 1);
+        } else {
+          status[first + i] = ZKB_SHORT_BUFFER;
+        }
+      }
+    }
+    for (uint32_t i = 0; i < m; i++)
+      if (bad[i]) set_error(errs[i]);
+  }
+  return ZKB_OK;
+}
+
+// One proof: the drop-in for prover.Prove(zkey, wasm, inputs) once the circuit is loaded.
+// proof_size / public_size: in = buffer capacity, out = bytes written (or needed on ZKB_SHORT_BUFFER).
+int zkb_fullprove(zkb_circuit *h, const char *inputs_json, size_t inputs_len, char *proof_buf, size_t *proof_size,
+                  char *public_buf, size_t *public_size, char *err, size_t errmax) {
+  char pb[1024], qb[2048];
+  int status = 0;
+  const char *ins[1] = {inputs_json};
+  size_t lens[1] = {inputs_len};
+  int rc = zkb_fullprove_batch(h, 1, ins, lens, pb, sizeof pb, qb, sizeof qb, &status);
+  if (rc == 0 && status != 0) rc = status;
+  if (rc) {
+    if (rc == ZKB_ASSERT_FAILED) set_error("circuit assert failed (witness generation, exception code 4)");
+    if (err && errmax) snprintf(err, errmax, "%s", zkb_last_error());
+    return rc;
+  }
+  int r1 = copy_out(pb, proof_buf, proof_size), r2 = copy_out(qb, public_buf, public_size);
+  if (r1 || r2) {
+    if (err && errmax) snprintf(err, errmax, "short buffer");
+    return ZKB_SHORT_BUFFER;
+  }
+  return ZKB_OK;
+}
+
+// .wtns (snarkjs/circom binary witness) for one inputs.json; *wtns_len in = capacity, out = size
+int zkb_witness(zkb_circuit *h, const char *inputs_json, size_t inputs_len, void *wtns_out, size_t *wtns_len) {
+  Circuit *c = h->c;
+  if (!c->consts) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  size_t need = 4 + 4 + 4 + 12 + (4 + 32 + 4) + 12 + (size_t)c->n_vars * 32;
+  if (!wtns_out || *wtns_len < need) { *wtns_len = need; return ZKB_SHORT_BUFFER; }
+  int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : env_u32("ZKB_CHUNK", 16));
+  if (rc) return rc;
+  std::string err;
+  memset(c->h_inputs, 0, (size_t)c->L.n_inputs * 32);
+  if (pack_inputs(c, inputs_json, inputs_len, c->h_inputs[0].v, err)) { set_error(err); return ZKB_ERROR; }
+  cudaStream_t st = c->ctx->stream;
+  CKR(cudaMemcpyAsync(c->inputs, c->h_inputs, (size_t)c->L.n_inputs * 32, cudaMemcpyHostToDevice, st), "h2d");
+  if ((rc = run_witness(c, 1, st))) return rc;
+  uint8_t *o = (uint8_t *)wtns_out;
+  static const uint32_t RMOD[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+  auto p32 = [&](uint32_t v) { memcpy(o, &v, 4); o += 4; };
+  auto p64 = [&](uint64_t v) { memcpy(o, &v, 8); o += 8; };
+  memcpy(o, "wtns", 4); o += 4;
+  p32(2); p32(2);
+  p32(1); p64(40);
+  p32(32); memcpy(o, RMOD, 32); o += 32; p32(c->n_vars);
+  p32(2); p64((uint64_t)c->n_vars * 32);
+  CKR(cudaMemcpyAsync(o, c->wtns, (size_t)c->n_vars * 32, cudaMemcpyDeviceToHost, st), "d2h witness");
+  CKR(cudaMemcpyAsync(c->h_status, c->status, 4, cudaMemcpyDeviceToHost, st), "d2h status");
+  CKR(cudaStreamSynchronize(st), "sync");
+  *wtns_len = need;
+  if (c->h_status[0]) { set_error("circuit assert failed (exception code 4)"); return ZKB_ASSERT_FAILED; }
+  return ZKB_OK;
+}
+
+// Groth16 from a caller-supplied witness (.wtns bytes): what go-rapidsnark's Groth16ProverRaw does.
+int zkb_prove_wtns(zkb_circuit *h, const void *wtns, size_t wtns_size, char *proof_buf, size_t *proof_size,
+                   char *public_buf, size_t *public_size) {
+  Circuit *c = h->c;
+  const uint8_t *b = (const uint8_t *)wtns;
+  if (wtns_size < 12 || memcmp(b, "wtns", 4) != 0) { set_error("wtns: bad magic"); return ZKB_ERROR; }
+  uint32_t nsec;
+  memcpy(&nsec, b + 8, 4);
+  size_t p = 12;
+  const uint8_t *data = nullptr;
+  uint32_t nw = 0;
+  for (uint32_t i = 0; i < nsec && p + 12 <= wtns_size; i++) {
+    uint32_t id;
+    uint64_t sz;
+    memcpy(&id, b + p, 4);
+    memcpy(&sz, b + p + 4, 8);
+    p += 12;
+    if (sz > wtns_size - p) { set_error("wtns: truncated"); return ZKB_ERROR; }
+    if (id == 1 && sz >= 40) memcpy(&nw, b + p + 36, 4);
+    if (id == 2) data = b + p;
+    p += sz;
+  }
+  if (!data) { set_error("wtns: no data section"); return ZKB_ERROR; }
+  if (nw != c->n_vars) { set_error("wtns: witness length does not match the zkey"); return ZKB_INVALID_WITNESS_LENGTH; }
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : env_u32("ZKB_CHUNK", 16));
+  if (rc) return rc;
+  CKR(cudaMemcpyAsync(c->wtns, data, (size_t)nw * 32, cudaMemcpyHostToDevice, c->ctx->stream), "h2d witness");
+  if ((rc = prove_group(c, 1, false, nullptr))) return rc;
+  std::string pj = proof_to_json(c->h_out, false), sj = publics_to_json(c->h_out + 256, c->n_public);
+  int r1 = copy_out(pj, proof_buf, proof_size), r2 = copy_out(sj, public_buf, public_size);
+  return (r1 || r2) ? ZKB_SHORT_BUFFER : ZKB_OK;
+}
+
+// rapidsnark's prover.h entry point, same symbol and signature (go-rapidsnark links against it):
+// returns 0 PROVER_OK, 1 PROVER_ERROR, 2 PROVER_ERROR_SHORT_BUFFER.  The parsed key + device tables are cached
+// per (pointer, size, checksum) so repeated calls with the same zkey do not re-upload it.
+int groth16_prover(const void *zkey_buffer, unsigned long zkey_size, const void *wtns_buffer, unsigned long wtns_size,
+                   char *proof_buffer, unsigned long *proof_size, char *public_buffer, unsigned long *public_size,
+                   char *error_msg, unsigned long error_msg_maxsize) {
+  static std::mutex mu;
+  static zkb_ctx *ctx = nullptr;
+  static zkb_circuit *cached = nullptr;
+  static uint64_t cached_sum = 0;
+  static unsigned long cached_size = 0;
+  auto fail = [&](int rc) {
+    if (error_msg && error_msg_maxsize) snprintf(error_msg, error_msg_maxsize, "%s", zkb_last_error());
+    return rc == ZKB_SHORT_BUFFER ? 2 : 1;
+  };
+  std::lock_guard<std::mutex> g(mu);
+  if (!ctx && zkb_ctx_create((int)env_u32("ZKB_DEVICE", 0) % (zkb_device_count() ? zkb_device_count() : 1), &ctx)) return fail(1);
+  uint64_t sum = 1469598103934665603ull;
+  const uint8_t *zb = (const uint8_t *)zkey_buffer;
+  for (unsigned long i = 0; i < zkey_size; i += 4099) { sum ^= zb[i]; sum *= 1099511628211ull; }
+  if (!cached || cached_sum != sum || cached_size != zkey_size) {
+    if (cached) { zkb_circuit_destroy(cached); cached = nullptr; }
+    int rc = zkb_load_circuit(ctx, zkey_buffer, zkey_size, nullptr, 0, &cached);
+    if (rc) return fail(rc);
+    cached_sum = sum;
+    cached_size = zkey_size;
+  }
+  size_t ps = *proof_size, qs = *public_size;
+  int rc = zkb_prove_wtns(cached, wtns_buffer, wtns_size, proof_buffer, &ps, public_buffer, &qs);
+  *proof_size = ps;
+  *public_size = qs;
+  if (rc) return fail(rc);
+  return 0;
+}
+
+}  // extern "C"
