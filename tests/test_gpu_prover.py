@@ -201,8 +201,8 @@ def test_stage_timing_and_work_counters(circuit):
     assert prover.launch_count() > n0
     assert st.shape == (8,) and (st > 0).all()
     wc = circuit.work_counters()
-    # dense bound: 16 windows x 82,754 scalars x 3 tables + 16 x 131,072 (H); executed is below it, above half
-    dense = 16 * (3 * 82754 + 131072)
-    assert 0.5 * dense < wc["g1_madds_per_proof"] < dense
-    assert wc["g2_madds_per_proof"] < 16 * 82754
+    # H is dense (131,072 full-width scalars x 16 windows, minus zero digits and one free add per bucket); the four
+    # witness MSMs only see the wires that differ from the per-key template, far below 16 x 82,754
+    assert 16 * 131072 * 0.9 < wc["g1_madds_per_proof"] < 16 * 131072 + 3 * 16 * 82754 * 0.25
+    assert 0 < wc["g2_madds_per_proof"] < 16 * 82754 * 0.25
     print("stage ms for 32 proofs:", [round(float(x), 2) for x in st], wc)

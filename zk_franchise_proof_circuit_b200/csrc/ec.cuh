@@ -19,19 +19,22 @@ struct alignas(16) Fq2 {
   ZKB_HD Fq2 operator+(const Fq2 &o) const { return {a + o.a, b + o.b}; }
   ZKB_HD Fq2 operator-(const Fq2 &o) const { return {a - o.a, b - o.b}; }
   ZKB_HD Fq2 neg() const { return {a.neg(), b.neg()}; }
+  ZKB_HD static Fq2 select(bool c, const Fq2 &x, const Fq2 &y) { return {Fq::select(c, x.a, y.a), Fq::select(c, x.b, y.b)}; }
   ZKB_HD Fq2 dbl() const { return {a.dbl(), b.dbl()}; }
   ZKB_HD Fq2 operator*(const Fq2 &o) const {  // Karatsuba: 3 Fq products
-    Fq t0 = a * o.a, t1 = b * o.b;
-    Fq t2 = (a + b) * (o.a + o.b);
+    Fq t0 = a.mulc(o.a), t1 = b.mulc(o.b);
+    Fq t2 = (a + b).mulc(o.a + o.b);
     return {t0 - t1, t2 - t0 - t1};
   }
   ZKB_HD Fq2 sqr() const {  // complex squaring: 2 Fq products
-    Fq t = a * b;
-    return {(a + b) * (a - b), t + t};
+    Fq t = a.mulc(b);
+    return {(a + b).mulc(a - b), t + t};
   }
+  ZKB_HD Fq2 mulc(const Fq2 &o) const { return *this * o; }
+  ZKB_HD Fq2 sqrc() const { return sqr(); }
   ZKB_HD Fq2 inv() const {
-    Fq n = (a.sqr() + b.sqr()).inv();
-    return {a * n, (b * n).neg()};
+    Fq n = (a.sqrc() + b.sqrc()).inv();
+    return {a.mulc(n), b.mulc(n).neg()};
   }
 };
 
@@ -57,20 +60,20 @@ struct alignas(16) XYZZ {
   // 2*P for affine P (mdbl-2008-s-1)
   ZKB_HD static XYZZ dbl_affine(const Affine<F> &p) {
     if (p.is_inf()) return infinity();
-    F U = p.y.dbl(), V = U.sqr(), W = U * V, S = p.x * V;
-    F x2 = p.x.sqr(), M = x2.dbl() + x2;
-    F X3 = M.sqr() - S.dbl();
-    F Y3 = M * (S - X3) - W * p.y;
+    F U = p.y.dbl(), V = U.sqrc(), W = U.mulc(V), S = p.x.mulc(V);
+    F x2 = p.x.sqrc(), M = x2.dbl() + x2;
+    F X3 = M.sqrc() - S.dbl();
+    F Y3 = M.mulc(S - X3) - W.mulc(p.y);
     return {X3, Y3, V, W};
   }
   // dbl-2008-s-1
   ZKB_HD XYZZ dbl() const {
     if (is_inf()) return *this;
-    F U = Y.dbl(), V = U.sqr(), W = U * V, S = X * V;
-    F x2 = X.sqr(), M = x2.dbl() + x2;
-    F X3 = M.sqr() - S.dbl();
-    F Y3 = M * (S - X3) - W * Y;
-    return {X3, Y3, V * ZZ, W * ZZZ};
+    F U = Y.dbl(), V = U.sqrc(), W = U.mulc(V), S = X.mulc(V);
+    F x2 = X.sqrc(), M = x2.dbl() + x2;
+    F X3 = M.sqrc() - S.dbl();
+    F Y3 = M.mulc(S - X3) - W.mulc(Y);
+    return {X3, Y3, V.mulc(ZZ), W.mulc(ZZZ)};
   }
   // this += affine p (madd-2008-s), all special cases handled
   ZKB_HD void add_affine(const Affine<F> &p) {
@@ -79,44 +82,44 @@ struct alignas(16) XYZZ {
       X = p.x; Y = p.y; ZZ = F::one(); ZZZ = F::one();
       return;
     }
-    F U2 = p.x * ZZ, S2 = p.y * ZZZ;
+    F U2 = p.x.mulc(ZZ), S2 = p.y.mulc(ZZZ);
     F P = U2 - X, R = S2 - Y;
     if (P.is_zero()) {
       if (R.is_zero()) *this = dbl_affine(p);
       else *this = infinity();
       return;
     }
-    F PP = P.sqr(), PPP = P * PP, Q = X * PP;
-    F X3 = R.sqr() - PPP - Q.dbl();
-    Y = R * (Q - X3) - Y * PPP;
+    F PP = P.sqrc(), PPP = P.mulc(PP), Q = X.mulc(PP);
+    F X3 = R.sqrc() - PPP - Q.dbl();
+    Y = R.mulc(Q - X3) - Y.mulc(PPP);
     X = X3;
-    ZZ = ZZ * PP;
-    ZZZ = ZZZ * PPP;
+    ZZ = ZZ.mulc(PP);
+    ZZZ = ZZZ.mulc(PPP);
   }
   // this += o (add-2008-s)
   ZKB_HD void add(const XYZZ &o) {
     if (o.is_inf()) return;
     if (is_inf()) { *this = o; return; }
-    F U1 = X * o.ZZ, U2 = o.X * ZZ, S1 = Y * o.ZZZ, S2 = o.Y * ZZZ;
+    F U1 = X.mulc(o.ZZ), U2 = o.X.mulc(ZZ), S1 = Y.mulc(o.ZZZ), S2 = o.Y.mulc(ZZZ);
     F P = U2 - U1, R = S2 - S1;
     if (P.is_zero()) {
       if (R.is_zero()) *this = dbl();
       else *this = infinity();
       return;
     }
-    F PP = P.sqr(), PPP = P * PP, Q = U1 * PP;
-    F X3 = R.sqr() - PPP - Q.dbl();
-    Y = R * (Q - X3) - S1 * PPP;
+    F PP = P.sqrc(), PPP = P.mulc(PP), Q = U1.mulc(PP);
+    F X3 = R.sqrc() - PPP - Q.dbl();
+    Y = R.mulc(Q - X3) - S1.mulc(PPP);
     X = X3;
-    ZZ = ZZ * o.ZZ * PP;
-    ZZZ = ZZZ * o.ZZZ * PPP;
+    ZZ = ZZ.mulc(o.ZZ).mulc(PP);
+    ZZZ = ZZZ.mulc(o.ZZZ).mulc(PPP);
   }
   ZKB_HD Affine<F> to_affine() const {
     if (is_inf()) return {F::zero(), F::zero()};
     F i3 = ZZZ.inv();        // 1/z^3
-    F i1 = i3 * ZZ;          // 1/z
-    F i2 = i1.sqr();         // 1/z^2
-    return {X * i2, Y * i3};
+    F i1 = i3.mulc(ZZ);          // 1/z
+    F i2 = i1.sqrc();         // 1/z^2
+    return {X.mulc(i2), Y.mulc(i3)};
   }
   // k * this, k = plain 256-bit integer (8 limbs LE); double-and-add from the top bit
   ZKB_HD XYZZ mul(const uint32_t k[8]) const {

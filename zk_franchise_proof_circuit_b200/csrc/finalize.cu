@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
     const Fr r = P.rs[2 * p], s = P.rs[2 * p + 1];
     if (warp == 0) {
       fin_point<Fq>(P.g1 + 3 * p, P.alpha1, P.d1tab, r.v, &sh[0]);
+      if (P.tconst1) xyzz_add_ni(&sh[0], P.tconst1);
       Affine<Fq> a;
       xyzz_to_affine_ni(&sh[0], &a);
       Fq x = a.x.from_mont(), y = a.y.from_mont();
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
       var_mul<Fq>(&sh[0], s.v, scratch, &sh[1]);
     } else if (warp == 1) {
       fin_point<Fq>(P.g1 + 3 * p + 1, P.beta1, P.d1tab, s.v, &sh[2]);
+      if (P.tconst1) xyzz_add_ni(&sh[2], P.tconst1 + 1);
       var_mul<Fq>(&sh[2], r.v, scratch + 15, &sh[3]);
     } else if (warp == 2) {
       fin_neg_rs_delta(P.d1tab, r, s, &sh[4]);
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
       for (uint32_t i = 0; i < P.n_public; i++) memcpy(out + 256 + 32 * i, w[1 + i].v, 32);
     } else {
       fin_point<Fq2>(P.g2 + p, P.beta2, P.d2tab, s.v, &shB);
+      if (P.tconst2) xyzz_add_ni(&shB, P.tconst2);
       Affine<Fq2> b;
       xyzz_to_affine_ni(&shB, &b);
       Fq c[4] = {b.x.a.from_mont(), b.x.b.from_mont(), b.y.a.from_mont(), b.y.b.from_mont()};
@@ -61,6 +64,7 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
     xyzz_add_ni(&sh[1], &sh[4]);
     xyzz_add_ni(&sh[1], P.g1 + 3 * p + 2);
     xyzz_add_ni(&sh[1], P.g1h + p);
+    if (P.tconst1) xyzz_add_ni(&sh[1], P.tconst1 + 2);
     Affine<Fq> c;
     xyzz_to_affine_ni(&sh[1], &c);
     Fq x = c.x.from_mont(), y = c.y.from_mont();

@@ -14,6 +14,8 @@ struct FinalizeParams {
   size_t wtns_stride;
   const Affine<Fq> *alpha1, *beta1, *d1tab;
   const Affine<Fq2> *beta2, *d2tab;
+  const XYZZ<Fq> *tconst1; // [3] per-key constant parts of pi_a', pi_b1', pi_c' (NULL = none)
+  const XYZZ<Fq2> *tconst2; // [1] of pi_b'
   XYZZ<Fq> *scratch;       // [n][2][15] window tables of the two variable-base products
   uint8_t *out;            // [n][256 + n_public*32]
   uint32_t n_public, n;

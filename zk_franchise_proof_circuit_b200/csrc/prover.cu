@@ -96,6 +96,20 @@ __global__ void k_fill_template(uint4 *dst, const uint4 *tmpl, size_t per_proof_
     dst[i] = tmpl[i % per_proof_u4];
 }
 
+__device__ __forceinline__ Fr ldg_fr8(const Fr *p);
+__device__ __forceinline__ void stg_fr8(Fr *p, const Fr &x);
+
+// d[b][i] = w[b][i] - tmpl[i] mod r.  ~91 % of the census wires are identical in every proof (the
+// Poseidon2(0,0) blocks below the leaf level, the oldKey = 0 sub-circuits), so d is zero there and the four
+// witness MSMs only see the wires that differ:  sum_i w_i P_i = sum_i tmpl_i P_i + sum_i d_i P_i, with the first
+// sum computed once per key.  Decided per wire on the data, exact for any tree depth.
+__global__ void k_witness_diff(const Fr *wtns, size_t wtns_stride, const Fr *tmpl, Fr *d, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr w = ldg_fr8(wtns + (size_t)blockIdx.y * wtns_stride + i);
+  stg_fr8(d + (size_t)blockIdx.y * n + i, tmpl ? w - ldg_fr8(tmpl + i) : w);
+}
+
 __device__ __forceinline__ Fr ldg_fr8(const Fr *p) {
   const uint4 *q = reinterpret_cast<const uint4 *>(p);
   uint4 a = __ldg(q), b = __ldg(q + 1);
@@ -173,7 +187,9 @@ struct Circuit {
   // batch workspace
   uint32_t cap = 0;                // proofs resident at once (witness group)
   uint32_t chunk = 0;              // proofs per NTT/MSM chunk
-  Fr *inputs = nullptr, *wtns = nullptr, *abc = nullptr, *hs = nullptr, *rs = nullptr;
+  Fr *inputs = nullptr, *wtns = nullptr, *abc = nullptr, *hs = nullptr, *rs = nullptr, *dw = nullptr;
+  XYZZ<Fq> *tconst1 = nullptr;     // sum_i tmpl_i * {A_i, B1_i, C_i}
+  XYZZ<Fq2> *tconst2 = nullptr;    // sum_i tmpl_i * B2_i
   int *status = nullptr;
   MsmSort sortW, sortH;
   MsmWork<Fq> work1;
@@ -211,7 +227,7 @@ static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
   if (c->cap >= cap && c->chunk >= chunk) return ZKB_OK;
   // (re)allocate everything; sizes are small next to the 180 GB of HBM
   cudaFree(c->inputs); cudaFree(c->wtns); cudaFree(c->abc); cudaFree(c->hs); cudaFree(c->rs); cudaFree(c->status);
-  cudaFree(c->g1out); cudaFree(c->g2out); cudaFree(c->out); cudaFree(c->fin_scratch);
+  cudaFree(c->g1out); cudaFree(c->g2out); cudaFree(c->out); cudaFree(c->fin_scratch); cudaFree(c->dw);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_inputs) cudaFreeHost(c->h_inputs);
   if (c->h_rs) cudaFreeHost(c->h_rs);
@@ -226,6 +242,7 @@ static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
   CKR(cudaMalloc(&c->wtns, (size_t)cap * c->n_vars * 32), "alloc witness");
   CKR(cudaMalloc(&c->abc, (size_t)chunk * 3 * c->domain * 32), "alloc abc");
   CKR(cudaMalloc(&c->hs, (size_t)chunk * c->domain * 32), "alloc h");
+  CKR(cudaMalloc(&c->dw, (size_t)chunk * c->n_vars * 32), "alloc witness diff");
   CKR(cudaMalloc(&c->rs, (size_t)cap * 64), "alloc rs");
   CKR(cudaMalloc(&c->status, (size_t)cap * 4), "alloc status");
   CKR(cudaMalloc(&c->g1out, (size_t)chunk * 4 * sizeof(XYZZ<Fq>)), "alloc g1out");
@@ -267,7 +284,9 @@ static int run_prove_chunk(Circuit *c, uint32_t first, uint32_t m, cudaStream_t 
   dim3 g2((c->domain + 255) / 256, m);
   k_join<<<g2, 256, 0, st>>>(c->abc, c->hs, c->domain);
   if (ev) cudaEventRecord(ev[2], st);
-  CKR(c->sortW.run(w, c->n_vars, m, st), "sort witness digits");
+  k_witness_diff<<<dim3((c->n_vars + 255) / 256, m), 256, 0, st>>>(w, c->n_vars, c->tconst1 ? c->tmpl : nullptr, c->dw, c->n_vars);
+  g_launches += 1;
+  CKR(c->sortW.run(c->dw, c->n_vars, m, st), "sort witness digits");
   CKR(c->sortH.run(c->hs, c->domain, m, st), "sort h digits");
   if (ev) cudaEventRecord(ev[3], st);
   // bucket sums: G1 over the witness (A, B1, C share one sort) -> slots [0, 3m); H -> slots [3*chunk, 3*chunk + m)
@@ -294,6 +313,8 @@ static int run_prove_chunk(Circuit *c, uint32_t first, uint32_t m, cudaStream_t 
   P.d1tab = c->d1tab;
   P.beta2 = c->fix2;
   P.d2tab = c->d2tab;
+  P.tconst1 = c->tconst1;
+  P.tconst2 = c->tconst2;
   P.scratch = c->fin_scratch;
   P.out = c->out + (size_t)first * c->out_stride();
   P.n_public = c->n_public;
@@ -494,6 +515,23 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
     CKR(cudaStreamSynchronize(st), "build table");
     cudaFree(d2);
   }
+  // constant part of the four witness MSMs: sum_i tmpl_i * base_i (once per key)
+  if (c->tmpl) {
+    MsmSort s1;
+    MsmWork<Fq> w1;
+    MsmWork<Fq2> w2;
+    CKR(s1.alloc(z.n_vars, 1), "alloc");
+    CKR(w1.alloc(3), "alloc");
+    CKR(w2.alloc(1), "alloc");
+    CKR(cudaMalloc(&c->tconst1, 3 * sizeof(XYZZ<Fq>)), "alloc");
+    CKR(cudaMalloc(&c->tconst2, sizeof(XYZZ<Fq2>)), "alloc");
+    CKR(s1.run(c->tmpl, z.n_vars, 1, st), "sort template");
+    MsmTable<Fq> tabs[3] = {c->tabA, c->tabB1, c->tabC};
+    CKR(msm_run<Fq>(s1, tabs, 3, 1, w1, c->tconst1, st), "template msm g1");
+    CKR(msm_run<Fq2>(s1, &c->tabB2, 1, 1, w2, c->tconst2, st), "template msm g2");
+    CKR(cudaStreamSynchronize(st), "template msm");
+    s1.free_all(); w1.free_all(); w2.free_all();
+  }
   // alpha1, beta1, beta2, delta tables
   {
     uint8_t f1[128];
@@ -521,6 +559,7 @@ static void destroy_circuit(Circuit *c) {
   cudaSetDevice(c->ctx->device);
   cudaFree(c->consts); cudaFree(c->hc); cudaFree(c->tmpl); cudaFree(c->sig2wire); cudaFree(c->csr_buf);
   cudaFree(c->csr_val); cudaFree(c->fix1); cudaFree(c->fix2); cudaFree(c->d1tab); cudaFree(c->d2tab);
+  cudaFree(c->tconst1); cudaFree(c->tconst2); cudaFree(c->dw);
   cudaFree(c->tabA.tab); cudaFree(c->tabB1.tab); cudaFree(c->tabC.tab); cudaFree(c->tabH.tab); cudaFree(c->tabB2.tab);
   c->ntt.destroy();
   cudaFree(c->inputs); cudaFree(c->wtns); cudaFree(c->abc); cudaFree(c->hs); cudaFree(c->rs); cudaFree(c->status);
@@ -635,7 +674,7 @@ int zkb_batch_set_inputs(zkb_circuit *h, int n, const void *inputs) {
   if (!c->consts) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
   std::lock_guard<std::mutex> g(c->mu);
   CKR(cudaSetDevice(c->ctx->device), "set device");
-  uint32_t chunk = env_u32("ZKB_CHUNK", 16);
+  uint32_t chunk = env_u32("ZKB_CHUNK", 128);
   int rc = ensure_workspace(c, (uint32_t)n, chunk);
   if (rc) return rc;
   CKR(cudaMemcpyAsync(c->inputs, inputs, (size_t)n * c->L.n_inputs * 32, cudaMemcpyHostToDevice, c->ctx->stream), "h2d inputs");
@@ -724,6 +763,14 @@ int zkb_debug_partials(zkb_circuit *h, void *out384, void *h_out) {
   CKR(cudaMemcpy(g1, c->g1out, 3 * sizeof(XYZZ<Fq>), cudaMemcpyDeviceToHost), "d2h");
   CKR(cudaMemcpy(g1 + 3, c->g1out + (size_t)3 * c->chunk, sizeof(XYZZ<Fq>), cudaMemcpyDeviceToHost), "d2h");
   CKR(cudaMemcpy(&g2, c->g2out, sizeof(XYZZ<Fq2>), cudaMemcpyDeviceToHost), "d2h");
+  if (c->tconst1) {   // the device sums cover w - tmpl; add the per-key constant part back (host arithmetic, debug only)
+    XYZZ<Fq> t1[3];
+    XYZZ<Fq2> t2;
+    CKR(cudaMemcpy(t1, c->tconst1, sizeof t1, cudaMemcpyDeviceToHost), "d2h");
+    CKR(cudaMemcpy(&t2, c->tconst2, sizeof t2, cudaMemcpyDeviceToHost), "d2h");
+    for (int i = 0; i < 3; i++) g1[i].add(t1[i]);
+    g2.add(t2);
+  }
   uint8_t *o = (uint8_t *)out384;
   auto put1 = [&](const XYZZ<Fq> &p, uint8_t *dst) {   // host (portable) arithmetic, debug only
     Affine<Fq> a = p.to_affine();
@@ -774,7 +821,7 @@ int zkb_fullprove_batch(zkb_circuit *h, int n, const char *const *inputs_json, c
   if (n <= 0) return ZKB_OK;
   std::lock_guard<std::mutex> g(c->mu);
   CKR(cudaSetDevice(c->ctx->device), "set device");
-  uint32_t chunk = env_u32("ZKB_CHUNK", 16), group = env_u32("ZKB_GROUP", 1024);
+  uint32_t chunk = env_u32("ZKB_CHUNK", 128), group = env_u32("ZKB_GROUP", 1024);
   uint32_t cap = (uint32_t)n < group ? (uint32_t)n : group;
   int rc = ensure_workspace(c, cap > c->cap ? cap : c->cap, chunk);
   if (rc) return rc;
@@ -845,7 +892,7 @@ int zkb_witness(zkb_circuit *h, const char *inputs_json, size_t inputs_len, void
   CKR(cudaSetDevice(c->ctx->device), "set device");
   size_t need = 4 + 4 + 4 + 12 + (4 + 32 + 4) + 12 + (size_t)c->n_vars * 32;
   if (!wtns_out || *wtns_len < need) { *wtns_len = need; return ZKB_SHORT_BUFFER; }
-  int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : env_u32("ZKB_CHUNK", 16));
+  int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : env_u32("ZKB_CHUNK", 128));
   if (rc) return rc;
   std::string err;
   memset(c->h_inputs, 0, (size_t)c->L.n_inputs * 32);
@@ -897,7 +944,7 @@ int zkb_prove_wtns(zkb_circuit *h, const void *wtns, size_t wtns_size, char *pro
   if (nw != c->n_vars) { set_error("wtns: witness length does not match the zkey"); return ZKB_INVALID_WITNESS_LENGTH; }
   std::lock_guard<std::mutex> g(c->mu);
   CKR(cudaSetDevice(c->ctx->device), "set device");
-  int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : env_u32("ZKB_CHUNK", 16));
+  int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : env_u32("ZKB_CHUNK", 128));
   if (rc) return rc;
   CKR(cudaMemcpyAsync(c->wtns, data, (size_t)nw * 32, cudaMemcpyHostToDevice, c->ctx->stream), "h2d witness");
   if ((rc = prove_group(c, 1, false, nullptr))) return rc;
