@@ -124,8 +124,10 @@ def _scalars(rng, shape_n, special=True):
     return s
 
 
-def test_msm_g1_small_matches_oracle():
+@pytest.mark.parametrize("window", [16, 13, 12])
+def test_msm_g1_small_matches_oracle(window, monkeypatch):
     from zk_franchise_proof_circuit_b200 import raw
+    monkeypatch.setenv("ZKB_RAW_MSM_C", str(window))       # signed-digit window size (bits)
     n = 700
     bases = _g1_points(n, 1)
     bases[10] = 0                     # point at infinity

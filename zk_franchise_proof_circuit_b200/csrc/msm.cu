@@ -1,9 +1,10 @@
 // Batched fixed-base Pippenger MSM for the Groth16 prover.
 //
-// The bases of a proving key never change, so every base is expanded once into its 16 window
-// multiples 2^(16 j) P (affine).  A 254-bit scalar then contributes 16 signed 16-bit digits that all
-// land in ONE set of 2^15 buckets:  sum_k s_k P_k = sum_b (b+1) * B_b,
-// B_b = sum of +-2^(16 j) P_k over the (k, j) whose |digit| is b+1.  Per batch item:
+// The bases of a proving key never change, so every base is expanded once into its window multiples
+// 2^(c j) P (affine).  A 254-bit scalar then contributes ceil(254/c) signed c-bit digits that all land in
+// ONE set of 2^(c-1) buckets:  sum_k s_k P_k = sum_b (b+1) * B_b,
+// B_b = sum of +-2^(c j) P_k over the (k, j) whose |digit| is b+1.  c = 16 for the dense H MSM, c = 13
+// for the four witness MSMs (few thousand non-zero scalars after the template difference).  Per batch item:
 //   1. digits + counting sort of (k, j) by bucket      (k_digits<false>, k_scan, k_digits<true>)
 //   2. one thread per bucket sums its list in XYZZ     (k_accumulate) - the IMAD-bound bulk
 //   3. weighted bucket reduction, running sums over chunks of 32, then a warp (k_reduce1/2)
@@ -16,7 +17,6 @@ namespace zkb {
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
 static constexpr int RED_CHUNK = 32;
-static constexpr int RED_PARTS = MSM_BUCKETS / RED_CHUNK;   // 1024
 
 template <class T>
 __device__ __forceinline__ T ldg_pod(const T *p) {
@@ -40,50 +40,54 @@ __device__ __forceinline__ void stg_pod(T *p, const T &v) {
 // table build
 // ---------------------------------------------------------------------------------------------
 template <class F>
-__global__ void k_table(Affine<F> *tab, const Affine<F> *bases, uint32_t n) {
+__global__ void k_table(Affine<F> *tab, const Affine<F> *bases, uint32_t n, int c, int windows) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   Affine<F> p = ldg_pod(bases + k);
   XYZZ<F> acc = XYZZ<F>::from_affine(p);
-  for (int j = 0; j < MSM_WINDOWS; j++) {
+  for (int j = 0; j < windows; j++) {
     Affine<F> a;
     xyzz_to_affine_ni(&acc, &a);
     stg_pod(tab + (size_t)j * n + k, a);
-    if (j + 1 < MSM_WINDOWS)
-      for (int i = 0; i < MSM_C; i++) xyzz_dbl_ni(&acc);
+    if (j + 1 < windows)
+      for (int i = 0; i < c; i++) xyzz_dbl_ni(&acc);
   }
 }
 
 template <class F>
-cudaError_t msm_build_table(MsmTable<F> &t, const Affine<F> *bases, uint32_t n, cudaStream_t st) {
+cudaError_t msm_build_table(MsmTable<F> &t, const Affine<F> *bases, uint32_t n, MsmCfg cfg, cudaStream_t st) {
   t.n = n;
-  CK(cudaMalloc(&t.tab, (size_t)n * MSM_WINDOWS * sizeof(Affine<F>)));
-  k_table<F><<<(n + 63) / 64, 64, 0, st>>>(t.tab, bases, n);
+  t.cfg = cfg;
+  CK(cudaMalloc(&t.tab, (size_t)n * cfg.windows * sizeof(Affine<F>)));
+  k_table<F><<<(n + 63) / 64, 64, 0, st>>>(t.tab, bases, n, cfg.c, cfg.windows);
   return cudaGetLastError();
 }
-template cudaError_t msm_build_table<Fq>(MsmTable<Fq> &, const Affine<Fq> *, uint32_t, cudaStream_t);
-template cudaError_t msm_build_table<Fq2>(MsmTable<Fq2> &, const Affine<Fq2> *, uint32_t, cudaStream_t);
+template cudaError_t msm_build_table<Fq>(MsmTable<Fq> &, const Affine<Fq> *, uint32_t, MsmCfg, cudaStream_t);
+template cudaError_t msm_build_table<Fq2>(MsmTable<Fq2> &, const Affine<Fq2> *, uint32_t, MsmCfg, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
 // digits + counting sort
 // ---------------------------------------------------------------------------------------------
 template <bool SCATTER>
-__global__ void k_digits(const Fr *scalars, size_t scalar_stride, uint32_t n, uint32_t *counts_or_cursor,
-                         uint32_t *entries) {
+__global__ void k_digits(const Fr *scalars, size_t scalar_stride, uint32_t n, int c, int windows, uint32_t buckets,
+                         uint32_t *counts_or_cursor, uint32_t *entries) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t b = blockIdx.y;
   if (k >= n) return;
   const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + (size_t)b * scalar_stride + k);
   uint4 lo = sp[0], hi = sp[1];
-  uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-  uint32_t *cc = counts_or_cursor + (size_t)b * MSM_BUCKETS;
-  uint32_t *ent = entries + (size_t)b * n * MSM_WINDOWS;
+  uint32_t w[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0u};
+  if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) return;
+  uint32_t *cc = counts_or_cursor + (size_t)b * buckets;
+  uint32_t *ent = entries + (size_t)b * n * windows;
+  const uint32_t mask = (1u << c) - 1, full = 1u << c;
   uint32_t carry = 0;
-#pragma unroll
-  for (int j = 0; j < MSM_WINDOWS; j++) {
-    uint32_t v = ((w[j >> 1] >> (16 * (j & 1))) & 0xffffu) + carry;
-    uint32_t neg = v > (uint32_t)MSM_BUCKETS;        // v in [0, 65536]
-    uint32_t mag = neg ? 65536u - v : v;             // |digit| in [0, 32768]
+  for (int j = 0; j < windows; j++) {
+    int bit = j * c, wd = bit >> 5, sh = bit & 31;
+    uint64_t two = (uint64_t)w[wd] | ((uint64_t)(wd < 8 ? w[wd + 1] : 0u) << 32);
+    uint32_t v = ((uint32_t)(two >> sh) & mask) + carry;     // in [0, 2^c]
+    uint32_t neg = v > buckets;
+    uint32_t mag = neg ? full - v : v;                         // |digit| in [0, 2^(c-1)]
     carry = neg;
     if (mag) {
       if (SCATTER) {
@@ -96,15 +100,17 @@ __global__ void k_digits(const Fr *scalars, size_t scalar_stride, uint32_t n, ui
   }
 }
 
-// offsets[b][0..BUCKETS] = exclusive scan of counts[b]; cursor[b] = offsets[b][0..BUCKETS)
-__global__ void __launch_bounds__(1024) k_scan(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor) {
+// offsets[b][0..buckets] = exclusive scan of counts[b]; cursor[b] = offsets[b][0..buckets).  One CTA of 1024
+// threads per batch item, each thread owning buckets/1024 consecutive counters (<= 32).
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor,
+                                               uint32_t buckets) {
   __shared__ uint32_t warp_tot[32];
-  uint32_t b = blockIdx.x, t = threadIdx.x;
-  const uint32_t *c = counts + (size_t)b * MSM_BUCKETS + t * 32;
+  const uint32_t b = blockIdx.x, t = threadIdx.x, per = buckets / 1024;
+  const uint32_t *c = counts + (size_t)b * buckets + t * per;
   uint32_t loc[32], sum = 0;
 #pragma unroll
-  for (int i = 0; i < 32; i++) { loc[i] = sum; sum += c[i]; }
-  // block exclusive scan of `sum`
+  for (int i = 0; i < 32; i++)
+    if ((uint32_t)i < per) { loc[i] = sum; sum += c[i]; }
   uint32_t x = sum;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -124,20 +130,23 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t *counts, uint32_t 
   }
   __syncthreads();
   uint32_t base = warp_tot[t >> 5] + x - sum;
-  uint32_t *o = offsets + (size_t)b * (MSM_BUCKETS + 1) + t * 32;
-  uint32_t *cu = cursor + (size_t)b * MSM_BUCKETS + t * 32;
+  uint32_t *o = offsets + (size_t)b * (buckets + 1) + t * per;
+  uint32_t *cu = cursor + (size_t)b * buckets + t * per;
 #pragma unroll
-  for (int i = 0; i < 32; i++) { o[i] = base + loc[i]; cu[i] = base + loc[i]; }
-  if (t == 1023) offsets[(size_t)b * (MSM_BUCKETS + 1) + MSM_BUCKETS] = base + sum;
+  for (int i = 0; i < 32; i++)
+    if ((uint32_t)i < per) { o[i] = base + loc[i]; cu[i] = base + loc[i]; }
+  if (t == 1023) offsets[(size_t)b * (buckets + 1) + buckets] = base + sum;
 }
 
-cudaError_t MsmSort::alloc(uint32_t n_, uint32_t batch_) {
+cudaError_t MsmSort::alloc(uint32_t n_, uint32_t batch_, MsmCfg cfg_) {
   n = n_;
   batch = batch_;
-  CK(cudaMalloc(&counts, (size_t)batch * MSM_BUCKETS * 4));
-  CK(cudaMalloc(&offsets, (size_t)batch * (MSM_BUCKETS + 1) * 4));
-  CK(cudaMalloc(&cursor, (size_t)batch * MSM_BUCKETS * 4));
-  CK(cudaMalloc(&entries, (size_t)batch * n * MSM_WINDOWS * 4));
+  cfg = cfg_;
+  if (cfg.buckets < 2048 || cfg.buckets > 32768) return cudaErrorInvalidValue;
+  CK(cudaMalloc(&counts, (size_t)batch * cfg.buckets * 4));
+  CK(cudaMalloc(&offsets, (size_t)batch * (cfg.buckets + 1) * 4));
+  CK(cudaMalloc(&cursor, (size_t)batch * cfg.buckets * 4));
+  CK(cudaMalloc(&entries, (size_t)batch * n * cfg.windows * 4));
   return cudaSuccess;
 }
 void MsmSort::free_all() {
@@ -146,11 +155,11 @@ void MsmSort::free_all() {
 }
 cudaError_t MsmSort::run(const Fr *scalars, size_t scalar_stride, uint32_t nbatch, cudaStream_t st) {
   if (nbatch > batch) return cudaErrorInvalidValue;
-  CK(cudaMemsetAsync(counts, 0, (size_t)nbatch * MSM_BUCKETS * 4, st));
+  CK(cudaMemsetAsync(counts, 0, (size_t)nbatch * cfg.buckets * 4, st));
   dim3 grid((n + 255) / 256, nbatch);
-  k_digits<false><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, counts, nullptr);
-  k_scan<<<nbatch, 1024, 0, st>>>(counts, offsets, cursor);
-  k_digits<true><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cursor, entries);
+  k_digits<false><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cfg.c, cfg.windows, cfg.buckets, counts, nullptr);
+  k_scan<<<nbatch, 1024, 0, st>>>(counts, offsets, cursor, cfg.buckets);
+  k_digits<true><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cfg.c, cfg.windows, cfg.buckets, cursor, entries);
   return cudaGetLastError();
 }
 
@@ -166,14 +175,14 @@ struct TablePtrs { const Affine<F> *tab[4]; };
 // the lanes then ran their lists one after another - ncu showed 2.4 of 32 threads active per instruction.)
 // The P == +-acc cases are handled in a rare slow path taken only when some lane of the warp needs it.
 template <class F, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_accumulate(TablePtrs<F> tabs, int ntab, uint32_t n,
-                                                        const uint32_t *__restrict__ offsets,
+__global__ void __launch_bounds__(THREADS) k_accumulate(TablePtrs<F> tabs, int ntab, uint32_t n, int windows,
+                                                        uint32_t nbuckets, const uint32_t *__restrict__ offsets,
                                                         const uint32_t *__restrict__ entries, XYZZ<F> *buckets) {
   uint32_t bucket = blockIdx.x * THREADS + threadIdx.x;
   uint32_t t = blockIdx.y, b = blockIdx.z;
   const Affine<F> *tab = t == 0 ? tabs.tab[0] : (t == 1 ? tabs.tab[1] : (t == 2 ? tabs.tab[2] : tabs.tab[3]));
-  const uint32_t *off = offsets + (size_t)b * (MSM_BUCKETS + 1);
-  const uint32_t *ent = entries + (size_t)b * n * MSM_WINDOWS;
+  const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
+  const uint32_t *ent = entries + (size_t)b * n * windows;
   const uint32_t beg = off[bucket], len = off[bucket + 1] - beg;
   const uint32_t maxlen = __reduce_max_sync(0xffffffffu, len);
   XYZZ<F> acc = XYZZ<F>::infinity();
@@ -207,7 +216,7 @@ __global__ void __launch_bounds__(THREADS) k_accumulate(TablePtrs<F> tabs, int n
     }
   }
   if (acc_inf) acc = XYZZ<F>::infinity();
-  stg_pod(buckets + ((size_t)(b * ntab + t) * MSM_BUCKETS + bucket), acc);
+  stg_pod(buckets + ((size_t)(b * ntab + t) * nbuckets + bucket), acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -215,10 +224,12 @@ __global__ void __launch_bounds__(THREADS) k_accumulate(TablePtrs<F> tabs, int n
 // ---------------------------------------------------------------------------------------------
 // level 1: thread = chunk of 32 buckets:  R = sum (u+1) B[32t+u],  S = sum B[32t+u]
 template <class F, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_reduce1(const XYZZ<F> *buckets, XYZZ<F> *part_r, XYZZ<F> *part_s) {
+__global__ void __launch_bounds__(THREADS) k_reduce1(const XYZZ<F> *buckets, XYZZ<F> *part_r, XYZZ<F> *part_s,
+                                                     uint32_t nbuckets) {
   uint32_t t = blockIdx.x * THREADS + threadIdx.x;   // chunk
   uint32_t slot = blockIdx.y;
-  const XYZZ<F> *B = buckets + (size_t)slot * MSM_BUCKETS + (size_t)t * RED_CHUNK;
+  const uint32_t parts = nbuckets / RED_CHUNK;
+  const XYZZ<F> *B = buckets + (size_t)slot * nbuckets + (size_t)t * RED_CHUNK;
   XYZZ<F> run = XYZZ<F>::infinity(), acc = XYZZ<F>::infinity();
   for (int u = RED_CHUNK - 1; u >= 0; u--) {
     XYZZ<F> x = ldg_pod(B + u);
@@ -227,25 +238,27 @@ __global__ void __launch_bounds__(THREADS) k_reduce1(const XYZZ<F> *buckets, XYZ
     xyzz_add_ni(&acc, &run);
     __syncwarp();
   }
-  stg_pod(part_r + (size_t)slot * RED_PARTS + t, acc);
-  stg_pod(part_s + (size_t)slot * RED_PARTS + t, run);
+  stg_pod(part_r + (size_t)slot * parts + t, acc);
+  stg_pod(part_s + (size_t)slot * parts + t, run);
 }
 
-// level 2: one warp per slot.  total = sum_t R_t + 32 * sum_t t * S_t
+// level 2: one warp per slot, lane l owns span = parts/32 consecutive chunks.
+// total = sum_t R_t + 32 * sum_t t * S_t,   sum_t t S_t = span * sum_l l sigma_l + sum_l rho_l
 template <class F>
-__global__ void __launch_bounds__(32) k_reduce2(const XYZZ<F> *part_r, const XYZZ<F> *part_s, XYZZ<F> *out) {
+__global__ void __launch_bounds__(32) k_reduce2(const XYZZ<F> *part_r, const XYZZ<F> *part_s, XYZZ<F> *out,
+                                                uint32_t parts) {
   __shared__ XYZZ<F> sh_r[32], sh_sig[32], sh_rho[32];
-  uint32_t slot = blockIdx.x, l = threadIdx.x;
-  const XYZZ<F> *R = part_r + (size_t)slot * RED_PARTS + l * 32;
-  const XYZZ<F> *S = part_s + (size_t)slot * RED_PARTS + l * 32;
+  const uint32_t slot = blockIdx.x, l = threadIdx.x, span = parts / 32;
+  const XYZZ<F> *R = part_r + (size_t)slot * parts + l * span;
+  const XYZZ<F> *S = part_s + (size_t)slot * parts + l * span;
   XYZZ<F> r = XYZZ<F>::infinity(), x;
-  for (int u = 0; u < 32; u++) {
+  for (uint32_t u = 0; u < span; u++) {
     x = ldg_pod(R + u);
     xyzz_add_ni(&r, &x);
     __syncwarp();
   }
   XYZZ<F> run = XYZZ<F>::infinity(), rho = XYZZ<F>::infinity();
-  for (int u = 31; u >= 1; u--) {
+  for (uint32_t u = span - 1; u >= 1; u--) {
     x = ldg_pod(S + u);
     xyzz_add_ni(&run, &x);
     __syncwarp();
@@ -266,20 +279,21 @@ __global__ void __launch_bounds__(32) k_reduce2(const XYZZ<F> *part_r, const XYZ
       xyzz_add_ni(&run2, &sh_sig[i]);
       xyzz_add_ni(&lt, &run2);    // lt = sum_l l * sigma_l
     }
-    for (int i = 0; i < 5; i++) xyzz_dbl_ni(&lt);  // * 32
-    xyzz_add_ni(&lt, &pt);                         // sum_t t * S_t
-    for (int i = 0; i < 5; i++) xyzz_dbl_ni(&lt);  // * 32 (chunk size)
+    for (uint32_t s = span; s > 1; s >>= 1) xyzz_dbl_ni(&lt);   // * span
+    xyzz_add_ni(&lt, &pt);                                      // sum_t t * S_t
+    for (int i = 0; i < 5; i++) xyzz_dbl_ni(&lt);               // * 32 (chunk size)
     xyzz_add_ni(&lt, &rt);
     stg_pod(out + slot, lt);
   }
 }
 
 template <class F>
-cudaError_t MsmWork<F>::alloc(uint32_t slots_) {
+cudaError_t MsmWork<F>::alloc(uint32_t slots_, MsmCfg cfg_) {
   slots = slots_;
-  CK(cudaMalloc(&buckets, (size_t)slots * MSM_BUCKETS * sizeof(XYZZ<F>)));
-  CK(cudaMalloc(&part_r, (size_t)slots * RED_PARTS * sizeof(XYZZ<F>)));
-  CK(cudaMalloc(&part_s, (size_t)slots * RED_PARTS * sizeof(XYZZ<F>)));
+  cfg = cfg_;
+  CK(cudaMalloc(&buckets, (size_t)slots * cfg.buckets * sizeof(XYZZ<F>)));
+  CK(cudaMalloc(&part_r, (size_t)slots * cfg.parts() * sizeof(XYZZ<F>)));
+  CK(cudaMalloc(&part_s, (size_t)slots * cfg.parts() * sizeof(XYZZ<F>)));
   return cudaSuccess;
 }
 template <class F>
@@ -301,11 +315,13 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
   TablePtrs<F> tp;
   for (int i = 0; i < 4; i++) tp.tab[i] = i < ntab ? tables[i].tab : nullptr;
   for (int i = 0; i < ntab; i++)
-    if (tables[i].n != sort.n) return cudaErrorInvalidValue;
+    if (tables[i].n != sort.n || tables[i].cfg.c != sort.cfg.c) return cudaErrorInvalidValue;
+  if (work.cfg.c != sort.cfg.c) return cudaErrorInvalidValue;
   constexpr int TH = AccCfg<F>::THREADS;
-  dim3 grid(MSM_BUCKETS / TH, ntab, nbatch);
-  k_accumulate<F, TH><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.offsets, sort.entries,
-                                           work.buckets + (size_t)slot0 * MSM_BUCKETS);
+  const uint32_t nb = sort.cfg.buckets;
+  dim3 grid(nb / TH, ntab, nbatch);
+  k_accumulate<F, TH><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries,
+                                           work.buckets + (size_t)slot0 * nb);
   return cudaGetLastError();
 }
 
@@ -314,10 +330,11 @@ template <class F>
 cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F> *out, cudaStream_t st) {
   if (slot0 + nslots > work.slots) return cudaErrorInvalidValue;
   constexpr int RT = AccCfg<F>::RED_THREADS;
-  dim3 g1(RED_PARTS / RT, nslots);
-  k_reduce1<F, RT><<<g1, RT, 0, st>>>(work.buckets + (size_t)slot0 * MSM_BUCKETS, work.part_r + (size_t)slot0 * RED_PARTS,
-                                      work.part_s + (size_t)slot0 * RED_PARTS);
-  k_reduce2<F><<<nslots, 32, 0, st>>>(work.part_r + (size_t)slot0 * RED_PARTS, work.part_s + (size_t)slot0 * RED_PARTS, out);
+  const uint32_t nb = work.cfg.buckets, parts = work.cfg.parts();
+  dim3 g1(parts / RT, nslots);
+  k_reduce1<F, RT><<<g1, RT, 0, st>>>(work.buckets + (size_t)slot0 * nb, work.part_r + (size_t)slot0 * parts,
+                                      work.part_s + (size_t)slot0 * parts, nb);
+  k_reduce2<F><<<nslots, 32, 0, st>>>(work.part_r + (size_t)slot0 * parts, work.part_s + (size_t)slot0 * parts, out, parts);
   return cudaGetLastError();
 }
 
@@ -330,12 +347,12 @@ cudaError_t msm_run(const MsmSort &sort, const MsmTable<F> *tables, int ntab, ui
 }
 
 // executed mixed adds of one accumulate launch: per bucket (non-infinity entries - 1)+, summed
-__global__ void k_count_madds(const uint8_t *inf_mask, uint32_t n, const uint32_t *offsets, const uint32_t *entries,
-                              unsigned long long *total) {
+__global__ void k_count_madds(const uint8_t *inf_mask, uint32_t n, int windows, uint32_t nbuckets, const uint32_t *offsets,
+                              const uint32_t *entries, unsigned long long *total) {
   uint32_t bucket = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t b = blockIdx.y;
-  const uint32_t *off = offsets + (size_t)b * (MSM_BUCKETS + 1);
-  const uint32_t *ent = entries + (size_t)b * n * MSM_WINDOWS;
+  const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
+  const uint32_t *ent = entries + (size_t)b * n * windows;
   uint32_t cnt = 0;
   for (uint32_t e = off[bucket]; e < off[bucket + 1]; e++) cnt += inf_mask[(ent[e] & 0x7fffffffu) % n] ? 0u : 1u;
   if (cnt > 1) atomicAdd(total, (unsigned long long)(cnt - 1));
@@ -356,8 +373,8 @@ cudaError_t msm_count_madds(const MsmSort &sort, const MsmTable<F> &table, uint3
   CK(cudaMalloc(&dtot, 8));
   CK(cudaMemsetAsync(dtot, 0, 8, st));
   k_inf_mask<F><<<(table.n + 255) / 256, 256, 0, st>>>(table.tab, table.n, mask);
-  dim3 grid(MSM_BUCKETS / 128, nbatch);
-  k_count_madds<<<grid, 128, 0, st>>>(mask, sort.n, sort.offsets, sort.entries, dtot);
+  dim3 grid(sort.cfg.buckets / 128, nbatch);
+  k_count_madds<<<grid, 128, 0, st>>>(mask, sort.n, sort.cfg.windows, sort.cfg.buckets, sort.offsets, sort.entries, dtot);
   CK(cudaMemcpyAsync(host_total, dtot, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   cudaFree(mask);

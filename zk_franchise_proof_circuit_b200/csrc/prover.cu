@@ -191,8 +191,9 @@ struct Circuit {
   XYZZ<Fq> *tconst1 = nullptr;     // sum_i tmpl_i * {A_i, B1_i, C_i}
   XYZZ<Fq2> *tconst2 = nullptr;    // sum_i tmpl_i * B2_i
   int *status = nullptr;
+  MsmCfg cfgW, cfgH;              // window sizes: witness MSMs (sparse after the template difference), H MSM (dense)
   MsmSort sortW, sortH;
-  MsmWork<Fq> work1;
+  MsmWork<Fq> work1, workH;
   MsmWork<Fq2> work2;
   XYZZ<Fq> *g1out = nullptr;
   XYZZ<Fq2> *g2out = nullptr;
@@ -235,6 +236,7 @@ static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
   if (c->sortW.counts) c->sortW.free_all();
   if (c->sortH.counts) c->sortH.free_all();
   if (c->work1.buckets) c->work1.free_all();
+  if (c->workH.buckets) c->workH.free_all();
   if (c->work2.buckets) c->work2.free_all();
   c->cap = cap;
   c->chunk = chunk;
@@ -253,10 +255,11 @@ static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
   CKR(cudaMallocHost(&c->h_inputs, (size_t)cap * c->L.n_inputs * 32), "alloc pinned inputs");
   CKR(cudaMallocHost(&c->h_rs, (size_t)cap * 64), "alloc pinned rs");
   CKR(cudaMallocHost(&c->h_status, (size_t)cap * 4), "alloc pinned status");
-  CKR(c->sortW.alloc(c->n_vars, chunk), "alloc sortW");
-  CKR(c->sortH.alloc(c->domain, chunk), "alloc sortH");
-  CKR(c->work1.alloc(chunk * 4), "alloc msm work g1");
-  CKR(c->work2.alloc(chunk), "alloc msm work g2");
+  CKR(c->sortW.alloc(c->n_vars, chunk, c->cfgW), "alloc sortW");
+  CKR(c->sortH.alloc(c->domain, chunk, c->cfgH), "alloc sortH");
+  CKR(c->work1.alloc(chunk * 3, c->cfgW), "alloc msm work g1");
+  CKR(c->workH.alloc(chunk, c->cfgH), "alloc msm work g1 (H)");
+  CKR(c->work2.alloc(chunk, c->cfgW), "alloc msm work g2");
   return ZKB_OK;
 }
 
@@ -292,12 +295,12 @@ static int run_prove_chunk(Circuit *c, uint32_t first, uint32_t m, cudaStream_t 
   // bucket sums: G1 over the witness (A, B1, C share one sort) -> slots [0, 3m); H -> slots [3*chunk, 3*chunk + m)
   MsmTable<Fq> tabs[3] = {c->tabA, c->tabB1, c->tabC};
   CKR(msm_accumulate<Fq>(c->sortW, tabs, 3, m, c->work1, 0, st), "msm accumulate g1 (A,B1,C)");
-  CKR(msm_accumulate<Fq>(c->sortH, &c->tabH, 1, m, c->work1, 3 * c->chunk, st), "msm accumulate g1 (H)");
+  CKR(msm_accumulate<Fq>(c->sortH, &c->tabH, 1, m, c->workH, 0, st), "msm accumulate g1 (H)");
   if (ev) cudaEventRecord(ev[4], st);
   CKR(msm_accumulate<Fq2>(c->sortW, &c->tabB2, 1, m, c->work2, 0, st), "msm accumulate g2 (B2)");
   if (ev) cudaEventRecord(ev[5], st);
   CKR(msm_reduce<Fq>(c->work1, 0, 3 * m, c->g1out, st), "msm reduce g1");
-  CKR(msm_reduce<Fq>(c->work1, 3 * c->chunk, m, c->g1out + (size_t)3 * c->chunk, st), "msm reduce g1 (H)");
+  CKR(msm_reduce<Fq>(c->workH, 0, m, c->g1out + (size_t)3 * c->chunk, st), "msm reduce g1 (H)");
   CKR(msm_reduce<Fq2>(c->work2, 0, m, c->g2out, st), "msm reduce g2");
   if (ev) cudaEventRecord(ev[6], st);
   g_launches += 6 + 2 + 1 + 6;
@@ -495,23 +498,25 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
   {
     Affine<Fq> *d1 = nullptr;
     Affine<Fq2> *d2 = nullptr;
-    auto build1 = [&](MsmTable<Fq> &t, const uint8_t *src, uint32_t n, uint32_t pad_front) -> int {
+    c->cfgW = msm_cfg((int)env_u32("ZKB_C_WITNESS", c->tmpl ? 13 : 16));
+    c->cfgH = msm_cfg((int)env_u32("ZKB_C_H", 16));
+    auto build1 = [&](MsmTable<Fq> &t, const uint8_t *src, uint32_t n, uint32_t pad_front, MsmCfg cfg) -> int {
       std::vector<uint8_t> tmp;
       const uint8_t *p = src;
       if (pad_front) { tmp.assign((size_t)(n + pad_front) * 64, 0); memcpy(tmp.data() + (size_t)pad_front * 64, src, (size_t)n * 64); p = tmp.data(); }
       CKR(upload(&d1, p, (size_t)(n + pad_front) * 64), "upload bases");
-      CKR(msm_build_table<Fq>(t, d1, n + pad_front, st), "build table");
+      CKR(msm_build_table<Fq>(t, d1, n + pad_front, cfg, st), "build table");
       CKR(cudaStreamSynchronize(st), "build table");
       cudaFree(d1);
       return ZKB_OK;
     };
     int rc;
-    if ((rc = build1(c->tabA, z.a, z.n_vars, 0))) return rc;
-    if ((rc = build1(c->tabB1, z.b1, z.n_vars, 0))) return rc;
-    if ((rc = build1(c->tabC, z.c, z.n_vars - z.n_public - 1, z.n_public + 1))) return rc;
-    if ((rc = build1(c->tabH, z.h, z.domain, 0))) return rc;
+    if ((rc = build1(c->tabA, z.a, z.n_vars, 0, c->cfgW))) return rc;
+    if ((rc = build1(c->tabB1, z.b1, z.n_vars, 0, c->cfgW))) return rc;
+    if ((rc = build1(c->tabC, z.c, z.n_vars - z.n_public - 1, z.n_public + 1, c->cfgW))) return rc;
+    if ((rc = build1(c->tabH, z.h, z.domain, 0, c->cfgH))) return rc;
     CKR(upload(&d2, z.b2, (size_t)z.n_vars * 128), "upload bases");
-    CKR(msm_build_table<Fq2>(c->tabB2, d2, z.n_vars, st), "build table");
+    CKR(msm_build_table<Fq2>(c->tabB2, d2, z.n_vars, c->cfgW, st), "build table");
     CKR(cudaStreamSynchronize(st), "build table");
     cudaFree(d2);
   }
@@ -520,9 +525,9 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
     MsmSort s1;
     MsmWork<Fq> w1;
     MsmWork<Fq2> w2;
-    CKR(s1.alloc(z.n_vars, 1), "alloc");
-    CKR(w1.alloc(3), "alloc");
-    CKR(w2.alloc(1), "alloc");
+    CKR(s1.alloc(z.n_vars, 1, c->cfgW), "alloc");
+    CKR(w1.alloc(3, c->cfgW), "alloc");
+    CKR(w2.alloc(1, c->cfgW), "alloc");
     CKR(cudaMalloc(&c->tconst1, 3 * sizeof(XYZZ<Fq>)), "alloc");
     CKR(cudaMalloc(&c->tconst2, sizeof(XYZZ<Fq2>)), "alloc");
     CKR(s1.run(c->tmpl, z.n_vars, 1, st), "sort template");
@@ -571,6 +576,7 @@ static void destroy_circuit(Circuit *c) {
   if (c->sortW.counts) c->sortW.free_all();
   if (c->sortH.counts) c->sortH.free_all();
   if (c->work1.buckets) c->work1.free_all();
+  if (c->workH.buckets) c->workH.free_all();
   if (c->work2.buckets) c->work2.free_all();
   delete c;
 }
@@ -743,9 +749,9 @@ int zkb_work_counters(zkb_circuit *h, uint64_t *out) {
   uint64_t ew = 0, eh = 0;
   for (uint32_t b = 0; b < m; b++) {
     uint32_t v;
-    CKR(cudaMemcpy(&v, c->sortW.offsets + (size_t)b * (MSM_BUCKETS + 1) + MSM_BUCKETS, 4, cudaMemcpyDeviceToHost), "d2h");
+    CKR(cudaMemcpy(&v, c->sortW.offsets + (size_t)b * (c->cfgW.buckets + 1) + c->cfgW.buckets, 4, cudaMemcpyDeviceToHost), "d2h");
     ew += v;
-    CKR(cudaMemcpy(&v, c->sortH.offsets + (size_t)b * (MSM_BUCKETS + 1) + MSM_BUCKETS, 4, cudaMemcpyDeviceToHost), "d2h");
+    CKR(cudaMemcpy(&v, c->sortH.offsets + (size_t)b * (c->cfgH.buckets + 1) + c->cfgH.buckets, 4, cudaMemcpyDeviceToHost), "d2h");
     eh += v;
   }
   out[2] = ew; out[3] = eh; out[4] = m; out[5] = c->chunk;

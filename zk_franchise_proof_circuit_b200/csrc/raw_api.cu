@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include "common.h"
 #include "ntt.cuh"
@@ -109,6 +110,10 @@ template <class F>
 static int raw_msm(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
                    float *table_ms) {
   if (require_device()) return ZKB_ERROR;
+  const char *ce = getenv("ZKB_RAW_MSM_C");
+  int cw = ce ? atoi(ce) : 16;
+  if (cw < 12 || cw > 16) { set_error("ZKB_RAW_MSM_C must be in [12, 16]"); return ZKB_ERROR; }
+  const MsmCfg cfg = msm_cfg(cw);
   const size_t psz = sizeof(Affine<F>);
   DevBuf db, ds, dout, daff;
   CKR(db.alloc(n * psz), "alloc");
@@ -123,12 +128,12 @@ static int raw_msm(const void *bases, size_t n, const void *scalars, int nbatch,
   cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
   MsmTable<F> tab;
   cudaEventRecord(e0);
-  CKR(msm_build_table<F>(tab, db.as<Affine<F>>(), (uint32_t)n, 0), "table");
+  CKR(msm_build_table<F>(tab, db.as<Affine<F>>(), (uint32_t)n, cfg, 0), "table");
   cudaEventRecord(e1);
   MsmSort sort;
   MsmWork<F> work;
-  CKR(sort.alloc((uint32_t)n, nbatch), "sort alloc");
-  CKR(work.alloc(nbatch), "work alloc");
+  CKR(sort.alloc((uint32_t)n, nbatch, cfg), "sort alloc");
+  CKR(work.alloc(nbatch, cfg), "work alloc");
   CKR(cudaEventSynchronize(e1), "table build");
   int reps = kernel_ms ? 2 : 1;
   for (int r = 0; r < reps; r++) {
