@@ -9,6 +9,14 @@
 
 namespace zkb {
 
+struct Fq2;
+#if defined(__CUDACC__)
+// Out-of-line Fq2 product / square whose 3 (2) Fq products are inlined, so they interleave on the IMAD pipe
+// (instruction-level parallelism 3) while the call keeps the G2 point formulas small.
+template <int TAG = 0> __device__ __noinline__ Fq2 fq2_mul_call(const Fq2 &a, const Fq2 &b);
+template <int TAG = 0> __device__ __noinline__ Fq2 fq2_sqr_call(const Fq2 &a);
+#endif
+
 struct alignas(16) Fq2 {
   Fq a, b;  // a + b*u, u^2 = -1
   ZKB_HD static Fq2 zero() { return {Fq::zero(), Fq::zero()}; }
@@ -21,22 +29,39 @@ struct alignas(16) Fq2 {
   ZKB_HD Fq2 neg() const { return {a.neg(), b.neg()}; }
   ZKB_HD static Fq2 select(bool c, const Fq2 &x, const Fq2 &y) { return {Fq::select(c, x.a, y.a), Fq::select(c, x.b, y.b)}; }
   ZKB_HD Fq2 dbl() const { return {a.dbl(), b.dbl()}; }
-  ZKB_HD Fq2 operator*(const Fq2 &o) const {  // Karatsuba: 3 Fq products
-    Fq t0 = a.mulc(o.a), t1 = b.mulc(o.b);
-    Fq t2 = (a + b).mulc(o.a + o.b);
+  ZKB_HD Fq2 operator*(const Fq2 &o) const {  // Karatsuba: 3 Fq products (inlined)
+    Fq t0 = a * o.a, t1 = b * o.b;
+    Fq t2 = (a + b) * (o.a + o.b);
     return {t0 - t1, t2 - t0 - t1};
   }
-  ZKB_HD Fq2 sqr() const {  // complex squaring: 2 Fq products
-    Fq t = a.mulc(b);
-    return {(a + b).mulc(a - b), t + t};
+  ZKB_HD Fq2 sqr() const {  // complex squaring: 2 Fq products (inlined)
+    Fq t = a * b;
+    return {(a + b) * (a - b), t + t};
   }
-  ZKB_HD Fq2 mulc(const Fq2 &o) const { return *this * o; }
-  ZKB_HD Fq2 sqrc() const { return sqr(); }
+  ZKB_HD Fq2 mulc(const Fq2 &o) const {
+#if defined(__CUDA_ARCH__)
+    return fq2_mul_call<0>(*this, o);
+#else
+    return *this * o;
+#endif
+  }
+  ZKB_HD Fq2 sqrc() const {
+#if defined(__CUDA_ARCH__)
+    return fq2_sqr_call<0>(*this);
+#else
+    return sqr();
+#endif
+  }
   ZKB_HD Fq2 inv() const {
     Fq n = (a.sqrc() + b.sqrc()).inv();
     return {a.mulc(n), b.mulc(n).neg()};
   }
 };
+
+#if defined(__CUDACC__)
+template <int TAG> __device__ __noinline__ Fq2 fq2_mul_call(const Fq2 &a, const Fq2 &b) { return a * b; }
+template <int TAG> __device__ __noinline__ Fq2 fq2_sqr_call(const Fq2 &a) { return a.sqr(); }
+#endif
 
 template <class F>
 struct alignas(16) Affine {

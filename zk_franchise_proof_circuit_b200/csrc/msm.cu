@@ -11,6 +11,7 @@
 // A/B1/B2/C share the witness as scalars, so they share one sort; bases at infinity ((0,0)) are
 // skipped by the mixed add.  Integer pipe (IMAD.WIDE carry chains) only - no tensor-core work here.
 #include "msm.cuh"
+#include <cstdlib>
 
 namespace zkb {
 
@@ -174,8 +175,12 @@ struct TablePtrs { const Affine<F> *tab[4]; };
 // version returned early from the add for empty accumulators / infinity bases; with independent thread scheduling
 // the lanes then ran their lists one after another - ncu showed 2.4 of 32 threads active per instruction.)
 // The P == +-acc cases are handled in a rare slow path taken only when some lane of the warp needs it.
-template <class F, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_accumulate(TablePtrs<F> tabs, int ntab, uint32_t n, int windows,
+template <bool INL, class F> __device__ __forceinline__ F mulx(const F &a, const F &b) {
+  if constexpr (INL) return a * b; else return a.mulc(b);
+}
+
+template <class F, int THREADS, int MINB, bool INL>
+__global__ void __launch_bounds__(THREADS, MINB) k_accumulate(TablePtrs<F> tabs, int ntab, uint32_t n, int windows,
                                                         uint32_t nbuckets, const uint32_t *__restrict__ offsets,
                                                         const uint32_t *__restrict__ entries, XYZZ<F> *buckets) {
   uint32_t bucket = blockIdx.x * THREADS + threadIdx.x;
@@ -194,13 +199,13 @@ __global__ void __launch_bounds__(THREADS) k_accumulate(TablePtrs<F> tabs, int n
     const bool use = active && !p.is_inf();
     p.y = F::select((x >> 31) != 0, p.y.neg(), p.y);
     // madd-2008-s, unconditionally
-    F U2 = p.x.mulc(acc.ZZ), S2 = p.y.mulc(acc.ZZZ);
+    F U2 = mulx<INL>(p.x, acc.ZZ), S2 = mulx<INL>(p.y, acc.ZZZ);
     F P = U2 - acc.X, R = S2 - acc.Y;
     const bool special = use && !acc_inf && P.is_zero();
-    F PP = P.sqrc(), PPP = P.mulc(PP), Q = acc.X.mulc(PP);
-    F X3 = R.sqrc() - PPP - Q.dbl();
-    F Y3 = R.mulc(Q - X3) - acc.Y.mulc(PPP);
-    F ZZ3 = acc.ZZ.mulc(PP), ZZZ3 = acc.ZZZ.mulc(PPP);
+    F PP = mulx<INL>(P, P), PPP = mulx<INL>(P, PP), Q = mulx<INL>(acc.X, PP);
+    F X3 = mulx<INL>(R, R) - PPP - Q.dbl();
+    F Y3 = mulx<INL>(R, Q - X3) - mulx<INL>(acc.Y, PPP);
+    F ZZ3 = mulx<INL>(acc.ZZ, PP), ZZZ3 = mulx<INL>(acc.ZZZ, PPP);
     const bool normal = use && !acc_inf && !special, first = use && acc_inf;
     acc.X = F::select(normal, X3, F::select(first, p.x, acc.X));
     acc.Y = F::select(normal, Y3, F::select(first, p.y, acc.Y));
@@ -320,8 +325,26 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
   constexpr int TH = AccCfg<F>::THREADS;
   const uint32_t nb = sort.cfg.buckets;
   dim3 grid(nb / TH, ntab, nbatch);
-  k_accumulate<F, TH><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries,
-                                           work.buckets + (size_t)slot0 * nb);
+  XYZZ<F> *dst = work.buckets + (size_t)slot0 * nb;
+  static const int variant = getenv("ZKB_ACC_VARIANT") ? atoi(getenv("ZKB_ACC_VARIANT")) : 0;
+#define ZKB_ACC(MINB, INL) k_accumulate<F, TH, MINB, INL><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, dst)
+  if constexpr (sizeof(F) == 32) {
+    switch (variant) {
+      case 1: ZKB_ACC(4, false); break;
+      case 2: ZKB_ACC(5, false); break;
+      case 3: ZKB_ACC(3, true); break;
+      case 4: ZKB_ACC(5, true); break;
+      default: ZKB_ACC(4, true); break;     // measured best on B200: inlined products, 128 registers
+    }
+  } else {
+    switch (variant) {
+      case 1: ZKB_ACC(4, false); break;
+      case 2: ZKB_ACC(5, false); break;
+      case 3: ZKB_ACC(6, false); break;
+      default: ZKB_ACC(8, false); break;
+    }
+  }
+#undef ZKB_ACC
   return cudaGetLastError();
 }
 
