@@ -139,6 +139,46 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t *counts, uint32_t 
   if (t == 1023) offsets[(size_t)b * (buckets + 1) + buckets] = base + sum;
 }
 
+// order[b][i] = bucket ids of batch item b sorted by descending size (counting sort on the size, sizes >= 1023
+// share the first bin).  The accumulate kernel walks buckets in this order, so the 32 lanes of a warp get lists of
+// (nearly) equal length and the longest lists start first.
+__global__ void __launch_bounds__(1024) k_order(const uint32_t *counts, uint32_t *order, uint32_t buckets) {
+  __shared__ uint32_t hist[1024];
+  const uint32_t b = blockIdx.x, t = threadIdx.x;
+  const uint32_t *c = counts + (size_t)b * buckets;
+  hist[t] = 0;
+  __syncthreads();
+  for (uint32_t i = t; i < buckets; i += 1024) atomicAdd(&hist[1023u - min(c[i], 1023u)], 1u);   // bin 0 = largest
+  __syncthreads();
+  // exclusive scan of hist (1024 entries, one per thread)
+  uint32_t v = hist[t], x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if ((t & 31) >= d) x += y;
+  }
+  __shared__ uint32_t wt[32];
+  if ((t & 31) == 31) wt[t >> 5] = x;
+  __syncthreads();
+  if (t < 32) {
+    uint32_t w = wt[t], z = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, z, d);
+      if (t >= d) z += y;
+    }
+    wt[t] = z - w;
+  }
+  __syncthreads();
+  hist[t] = wt[t >> 5] + x - v;
+  __syncthreads();
+  uint32_t *o = order + (size_t)b * buckets;
+  for (uint32_t i = t; i < buckets; i += 1024) {
+    uint32_t pos = atomicAdd(&hist[1023u - min(c[i], 1023u)], 1u);
+    o[pos] = i;
+  }
+}
+
 cudaError_t MsmSort::alloc(uint32_t n_, uint32_t batch_, MsmCfg cfg_) {
   n = n_;
   batch = batch_;
@@ -148,11 +188,12 @@ cudaError_t MsmSort::alloc(uint32_t n_, uint32_t batch_, MsmCfg cfg_) {
   CK(cudaMalloc(&offsets, (size_t)batch * (cfg.buckets + 1) * 4));
   CK(cudaMalloc(&cursor, (size_t)batch * cfg.buckets * 4));
   CK(cudaMalloc(&entries, (size_t)batch * n * cfg.windows * 4));
+  CK(cudaMalloc(&order, (size_t)batch * cfg.buckets * 4));
   return cudaSuccess;
 }
 void MsmSort::free_all() {
-  cudaFree(counts); cudaFree(offsets); cudaFree(cursor); cudaFree(entries);
-  counts = offsets = cursor = entries = nullptr;
+  cudaFree(counts); cudaFree(offsets); cudaFree(cursor); cudaFree(entries); cudaFree(order);
+  counts = offsets = cursor = entries = order = nullptr;
 }
 cudaError_t MsmSort::run(const Fr *scalars, size_t scalar_stride, uint32_t nbatch, cudaStream_t st) {
   if (nbatch > batch) return cudaErrorInvalidValue;
@@ -160,6 +201,7 @@ cudaError_t MsmSort::run(const Fr *scalars, size_t scalar_stride, uint32_t nbatc
   dim3 grid((n + 255) / 256, nbatch);
   k_digits<false><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cfg.c, cfg.windows, cfg.buckets, counts, nullptr);
   k_scan<<<nbatch, 1024, 0, st>>>(counts, offsets, cursor, cfg.buckets);
+  k_order<<<nbatch, 1024, 0, st>>>(counts, order, cfg.buckets);
   k_digits<true><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cfg.c, cfg.windows, cfg.buckets, cursor, entries);
   return cudaGetLastError();
 }
@@ -182,9 +224,10 @@ template <bool INL, class F> __device__ __forceinline__ F mulx(const F &a, const
 template <class F, int THREADS, int MINB, bool INL>
 __global__ void __launch_bounds__(THREADS, MINB) k_accumulate(TablePtrs<F> tabs, int ntab, uint32_t n, int windows,
                                                         uint32_t nbuckets, const uint32_t *__restrict__ offsets,
-                                                        const uint32_t *__restrict__ entries, XYZZ<F> *buckets) {
-  uint32_t bucket = blockIdx.x * THREADS + threadIdx.x;
+                                                        const uint32_t *__restrict__ entries,
+                                                        const uint32_t *__restrict__ order, XYZZ<F> *buckets) {
   uint32_t t = blockIdx.y, b = blockIdx.z;
+  const uint32_t bucket = order[(size_t)b * nbuckets + blockIdx.x * THREADS + threadIdx.x];
   const Affine<F> *tab = t == 0 ? tabs.tab[0] : (t == 1 ? tabs.tab[1] : (t == 2 ? tabs.tab[2] : tabs.tab[3]));
   const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
   const uint32_t *ent = entries + (size_t)b * n * windows;
@@ -327,7 +370,7 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
   dim3 grid(nb / TH, ntab, nbatch);
   XYZZ<F> *dst = work.buckets + (size_t)slot0 * nb;
   static const int variant = getenv("ZKB_ACC_VARIANT") ? atoi(getenv("ZKB_ACC_VARIANT")) : 0;
-#define ZKB_ACC(MINB, INL) k_accumulate<F, TH, MINB, INL><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, dst)
+#define ZKB_ACC(MINB, INL) k_accumulate<F, TH, MINB, INL><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order, dst)
   if constexpr (sizeof(F) == 32) {
     switch (variant) {
       case 1: ZKB_ACC(4, false); break;

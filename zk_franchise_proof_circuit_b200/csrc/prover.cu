@@ -163,6 +163,30 @@ static const char *INPUT_NAMES[12] = {"electionId", "nullifier", "voteHash", "si
                                       "availableWeight", "address", "password", "signature", "censusSiblings",
                                       "sikSiblings"};
 
+// Per-chunk working set.  Chunks alternate between lanes (each with its own stream), so the latency-bound kernels
+// of one chunk (witness, bucket reduction, proof assembly, scans) overlap the IMAD-bound accumulation of the other.
+struct Lane {
+  cudaStream_t st = nullptr;
+  cudaEvent_t done = nullptr;
+  Fr *abc = nullptr, *hs = nullptr, *dw = nullptr;
+  MsmSort sortW, sortH;
+  MsmWork<Fq> work1, workH;
+  MsmWork<Fq2> work2;
+  XYZZ<Fq> *g1out = nullptr;
+  XYZZ<Fq2> *g2out = nullptr;
+  XYZZ<Fq> *fin_scratch = nullptr;
+  void free_all() {
+    cudaFree(abc); cudaFree(hs); cudaFree(dw); cudaFree(g1out); cudaFree(g2out); cudaFree(fin_scratch);
+    abc = hs = dw = nullptr; g1out = fin_scratch = nullptr; g2out = nullptr;
+    if (sortW.counts) sortW.free_all();
+    if (sortH.counts) sortH.free_all();
+    if (work1.buckets) work1.free_all();
+    if (workH.buckets) workH.free_all();
+    if (work2.buckets) work2.free_all();
+  }
+};
+static constexpr int MAX_LANES = 4;
+
 struct Circuit {
   Ctx *ctx = nullptr;
   uint32_t n_vars = 0, n_public = 0, domain = 0, power = 0;
@@ -187,17 +211,13 @@ struct Circuit {
   // batch workspace
   uint32_t cap = 0;                // proofs resident at once (witness group)
   uint32_t chunk = 0;              // proofs per NTT/MSM chunk
-  Fr *inputs = nullptr, *wtns = nullptr, *abc = nullptr, *hs = nullptr, *rs = nullptr, *dw = nullptr;
+  Fr *inputs = nullptr, *wtns = nullptr, *rs = nullptr;
+  Lane lanes[MAX_LANES];
+  int n_lanes = 0;
   XYZZ<Fq> *tconst1 = nullptr;     // sum_i tmpl_i * {A_i, B1_i, C_i}
   XYZZ<Fq2> *tconst2 = nullptr;    // sum_i tmpl_i * B2_i
   int *status = nullptr;
   MsmCfg cfgW, cfgH;              // window sizes: witness MSMs (sparse after the template difference), H MSM (dense)
-  MsmSort sortW, sortH;
-  MsmWork<Fq> work1, workH;
-  MsmWork<Fq2> work2;
-  XYZZ<Fq> *g1out = nullptr;
-  XYZZ<Fq2> *g2out = nullptr;
-  XYZZ<Fq> *fin_scratch = nullptr;
   uint8_t *out = nullptr;          // device results
   uint8_t *h_out = nullptr;        // pinned
   Fr *h_inputs = nullptr;          // pinned
@@ -205,6 +225,7 @@ struct Circuit {
   int *h_status = nullptr;         // pinned
   std::mutex mu;
   uint32_t last_chunk_m = 0;
+  int last_lane = 0;
   std::mt19937_64 rng;
   // stage timing of the last device pass (ms)
   float t_witness = 0, t_abc = 0, t_ntt = 0, t_msm = 0, t_fin = 0;
@@ -224,90 +245,107 @@ static void random_fr(std::mt19937_64 &g, uint32_t out[8]) {
   }
 }
 
+static uint32_t env_u32(const char *name, uint32_t dflt) {
+  const char *v = getenv(name);
+  if (!v || !*v) return dflt;
+  long x = atol(v);
+  return x > 0 ? (uint32_t)x : dflt;
+}
+
 static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
   if (c->cap >= cap && c->chunk >= chunk) return ZKB_OK;
   // (re)allocate everything; sizes are small next to the 180 GB of HBM
-  cudaFree(c->inputs); cudaFree(c->wtns); cudaFree(c->abc); cudaFree(c->hs); cudaFree(c->rs); cudaFree(c->status);
-  cudaFree(c->g1out); cudaFree(c->g2out); cudaFree(c->out); cudaFree(c->fin_scratch); cudaFree(c->dw);
+  cudaFree(c->inputs); cudaFree(c->wtns); cudaFree(c->rs); cudaFree(c->status); cudaFree(c->out);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_inputs) cudaFreeHost(c->h_inputs);
   if (c->h_rs) cudaFreeHost(c->h_rs);
   if (c->h_status) cudaFreeHost(c->h_status);
-  if (c->sortW.counts) c->sortW.free_all();
-  if (c->sortH.counts) c->sortH.free_all();
-  if (c->work1.buckets) c->work1.free_all();
-  if (c->workH.buckets) c->workH.free_all();
-  if (c->work2.buckets) c->work2.free_all();
+  for (int i = 0; i < MAX_LANES; i++) c->lanes[i].free_all();
   c->cap = cap;
   c->chunk = chunk;
+  // more than one lane only pays when there is more than one chunk
+  int want = (int)env_u32("ZKB_LANES", 2);
+  if (want > MAX_LANES) want = MAX_LANES;
+  c->n_lanes = cap > chunk ? want : 1;
   CKR(cudaMalloc(&c->inputs, (size_t)cap * c->L.n_inputs * 32), "alloc inputs");
   CKR(cudaMalloc(&c->wtns, (size_t)cap * c->n_vars * 32), "alloc witness");
-  CKR(cudaMalloc(&c->abc, (size_t)chunk * 3 * c->domain * 32), "alloc abc");
-  CKR(cudaMalloc(&c->hs, (size_t)chunk * c->domain * 32), "alloc h");
-  CKR(cudaMalloc(&c->dw, (size_t)chunk * c->n_vars * 32), "alloc witness diff");
   CKR(cudaMalloc(&c->rs, (size_t)cap * 64), "alloc rs");
   CKR(cudaMalloc(&c->status, (size_t)cap * 4), "alloc status");
-  CKR(cudaMalloc(&c->g1out, (size_t)chunk * 4 * sizeof(XYZZ<Fq>)), "alloc g1out");
-  CKR(cudaMalloc(&c->g2out, (size_t)chunk * sizeof(XYZZ<Fq2>)), "alloc g2out");
-  CKR(cudaMalloc(&c->fin_scratch, (size_t)chunk * 30 * sizeof(XYZZ<Fq>)), "alloc finalize scratch");
   CKR(cudaMalloc(&c->out, (size_t)cap * c->out_stride()), "alloc out");
   CKR(cudaMallocHost(&c->h_out, (size_t)cap * c->out_stride()), "alloc pinned out");
   CKR(cudaMallocHost(&c->h_inputs, (size_t)cap * c->L.n_inputs * 32), "alloc pinned inputs");
   CKR(cudaMallocHost(&c->h_rs, (size_t)cap * 64), "alloc pinned rs");
   CKR(cudaMallocHost(&c->h_status, (size_t)cap * 4), "alloc pinned status");
-  CKR(c->sortW.alloc(c->n_vars, chunk, c->cfgW), "alloc sortW");
-  CKR(c->sortH.alloc(c->domain, chunk, c->cfgH), "alloc sortH");
-  CKR(c->work1.alloc(chunk * 3, c->cfgW), "alloc msm work g1");
-  CKR(c->workH.alloc(chunk, c->cfgH), "alloc msm work g1 (H)");
-  CKR(c->work2.alloc(chunk, c->cfgW), "alloc msm work g2");
+  for (int i = 0; i < c->n_lanes; i++) {
+    Lane &ln = c->lanes[i];
+    if (!ln.st) {
+      CKR(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking), "lane stream");
+      CKR(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming), "lane event");
+    }
+    CKR(cudaMalloc(&ln.abc, (size_t)chunk * 3 * c->domain * 32), "alloc abc");
+    CKR(cudaMalloc(&ln.hs, (size_t)chunk * c->domain * 32), "alloc h");
+    CKR(cudaMalloc(&ln.dw, (size_t)chunk * c->n_vars * 32), "alloc witness diff");
+    CKR(cudaMalloc(&ln.g1out, (size_t)chunk * 4 * sizeof(XYZZ<Fq>)), "alloc g1out");
+    CKR(cudaMalloc(&ln.g2out, (size_t)chunk * sizeof(XYZZ<Fq2>)), "alloc g2out");
+    CKR(cudaMalloc(&ln.fin_scratch, (size_t)chunk * 30 * sizeof(XYZZ<Fq>)), "alloc finalize scratch");
+    CKR(ln.sortW.alloc(c->n_vars, chunk, c->cfgW), "alloc sortW");
+    CKR(ln.sortH.alloc(c->domain, chunk, c->cfgH), "alloc sortH");
+    CKR(ln.work1.alloc(chunk * 3, c->cfgW), "alloc msm work g1");
+    CKR(ln.workH.alloc(chunk, c->cfgH), "alloc msm work g1 (H)");
+    CKR(ln.work2.alloc(chunk, c->cfgW), "alloc msm work g2");
+  }
   return ZKB_OK;
 }
 
-// witness for proofs [0, n) already in c->inputs
-static int run_witness(Circuit *c, uint32_t n, cudaStream_t st) {
-  CKR(cudaMemsetAsync(c->status, 0, (size_t)n * 4, st), "memset status");
+// witness for proofs [first, first + n) of c->inputs
+static int run_witness(Circuit *c, uint32_t first, uint32_t n, cudaStream_t st) {
+  CKR(cudaMemsetAsync(c->status + first, 0, (size_t)n * 4, st), "memset status");
   size_t per = (size_t)c->n_vars * 2;   // uint4 per proof
-  k_fill_template<<<1184, 256, 0, st>>>(reinterpret_cast<uint4 *>(c->wtns), reinterpret_cast<const uint4 *>(c->tmpl),
-                                        per, n);
+  Fr *w = c->wtns + (size_t)first * c->n_vars;
+  k_fill_template<<<1184, 256, 0, st>>>(reinterpret_cast<uint4 *>(w), reinterpret_cast<const uint4 *>(c->tmpl), per, n);
   dim3 grid((n + 31) / 32, 3);
-  k_witness<<<grid, 32, 0, st>>>(c->L, c->consts, c->sig2wire, c->hc, c->inputs, c->wtns, c->status, n, 1);
+  k_witness<<<grid, 32, 0, st>>>(c->L, c->consts, c->sig2wire, c->hc, c->inputs + (size_t)first * c->L.n_inputs, w,
+                                 c->status + first, n, 1);
   g_launches += 2;
   return cudaGetLastError() == cudaSuccess ? ZKB_OK : cuda_fail(cudaGetLastError(), "witness launch");
 }
 
-// Groth16 for proofs [first, first + m) of the resident witnesses, m <= chunk
-static int run_prove_chunk(Circuit *c, uint32_t first, uint32_t m, cudaStream_t st, cudaEvent_t *ev) {
+// witness (optional) + Groth16 for proofs [first, first + m), m <= chunk, on lane ln
+static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, bool with_witness, cudaEvent_t *ev) {
+  cudaStream_t st = ln.st;
+  if (with_witness) { int rc = run_witness(c, first, m, st); if (rc) return rc; }
+  if (ev) cudaEventRecord(ev[1], st);
   const Fr *w = c->wtns + (size_t)first * c->n_vars;
   dim3 g1((c->domain + 127) / 128, m);
-  k_build_abc<<<g1, 128, 0, st>>>(c->csrA, c->csrB, w, c->n_vars, c->abc, c->domain);
+  k_build_abc<<<g1, 128, 0, st>>>(c->csrA, c->csrB, w, c->n_vars, ln.abc, c->domain);
   g_launches += 1 + 4 + 1;   // build_abc, 2 DIF + 2 DIT passes, join
-  if (ev) cudaEventRecord(ev[1], st);
-  CKR(c->ntt.dif(c->abc, 3 * m, c->domain, true, true, st), "ntt dif");
-  CKR(c->ntt.dit(c->abc, 3 * m, c->domain, false, st), "ntt dit");
-  dim3 g2((c->domain + 255) / 256, m);
-  k_join<<<g2, 256, 0, st>>>(c->abc, c->hs, c->domain);
   if (ev) cudaEventRecord(ev[2], st);
-  k_witness_diff<<<dim3((c->n_vars + 255) / 256, m), 256, 0, st>>>(w, c->n_vars, c->tconst1 ? c->tmpl : nullptr, c->dw, c->n_vars);
-  g_launches += 1;
-  CKR(c->sortW.run(c->dw, c->n_vars, m, st), "sort witness digits");
-  CKR(c->sortH.run(c->hs, c->domain, m, st), "sort h digits");
+  CKR(c->ntt.dif(ln.abc, 3 * m, c->domain, true, true, st), "ntt dif");
+  CKR(c->ntt.dit(ln.abc, 3 * m, c->domain, false, st), "ntt dit");
+  dim3 g2((c->domain + 255) / 256, m);
+  k_join<<<g2, 256, 0, st>>>(ln.abc, ln.hs, c->domain);
   if (ev) cudaEventRecord(ev[3], st);
-  // bucket sums: G1 over the witness (A, B1, C share one sort) -> slots [0, 3m); H -> slots [3*chunk, 3*chunk + m)
-  MsmTable<Fq> tabs[3] = {c->tabA, c->tabB1, c->tabC};
-  CKR(msm_accumulate<Fq>(c->sortW, tabs, 3, m, c->work1, 0, st), "msm accumulate g1 (A,B1,C)");
-  CKR(msm_accumulate<Fq>(c->sortH, &c->tabH, 1, m, c->workH, 0, st), "msm accumulate g1 (H)");
+  k_witness_diff<<<dim3((c->n_vars + 255) / 256, m), 256, 0, st>>>(w, c->n_vars, c->tconst1 ? c->tmpl : nullptr, ln.dw, c->n_vars);
+  g_launches += 1;
+  CKR(ln.sortW.run(ln.dw, c->n_vars, m, st), "sort witness digits");
+  CKR(ln.sortH.run(ln.hs, c->domain, m, st), "sort h digits");
   if (ev) cudaEventRecord(ev[4], st);
-  CKR(msm_accumulate<Fq2>(c->sortW, &c->tabB2, 1, m, c->work2, 0, st), "msm accumulate g2 (B2)");
+  // bucket sums: G1 over the witness difference (A, B1, C share one sort), H over h, G2 (B2) over the witness difference
+  MsmTable<Fq> tabs[3] = {c->tabA, c->tabB1, c->tabC};
+  CKR(msm_accumulate<Fq>(ln.sortW, tabs, 3, m, ln.work1, 0, st), "msm accumulate g1 (A,B1,C)");
+  CKR(msm_accumulate<Fq>(ln.sortH, &c->tabH, 1, m, ln.workH, 0, st), "msm accumulate g1 (H)");
   if (ev) cudaEventRecord(ev[5], st);
-  CKR(msm_reduce<Fq>(c->work1, 0, 3 * m, c->g1out, st), "msm reduce g1");
-  CKR(msm_reduce<Fq>(c->workH, 0, m, c->g1out + (size_t)3 * c->chunk, st), "msm reduce g1 (H)");
-  CKR(msm_reduce<Fq2>(c->work2, 0, m, c->g2out, st), "msm reduce g2");
+  CKR(msm_accumulate<Fq2>(ln.sortW, &c->tabB2, 1, m, ln.work2, 0, st), "msm accumulate g2 (B2)");
   if (ev) cudaEventRecord(ev[6], st);
-  g_launches += 6 + 2 + 1 + 6;
+  CKR(msm_reduce<Fq>(ln.work1, 0, 3 * m, ln.g1out, st), "msm reduce g1");
+  CKR(msm_reduce<Fq>(ln.workH, 0, m, ln.g1out + (size_t)3 * c->chunk, st), "msm reduce g1 (H)");
+  CKR(msm_reduce<Fq2>(ln.work2, 0, m, ln.g2out, st), "msm reduce g2");
+  if (ev) cudaEventRecord(ev[7], st);
+  g_launches += 8 + 2 + 1 + 6;   // 2 sorts x (count, scan, order, scatter), 2 + 1 accumulate, 3 x 2 reduce
   FinalizeParams P;
-  P.g1 = c->g1out;
-  P.g1h = c->g1out + (size_t)3 * c->chunk;
-  P.g2 = c->g2out;
+  P.g1 = ln.g1out;
+  P.g1h = ln.g1out + (size_t)3 * c->chunk;
+  P.g2 = ln.g2out;
   P.rs = c->rs + (size_t)first * 2;
   P.wtns = w;
   P.wtns_stride = c->n_vars;
@@ -318,45 +356,55 @@ static int run_prove_chunk(Circuit *c, uint32_t first, uint32_t m, cudaStream_t 
   P.d2tab = c->d2tab;
   P.tconst1 = c->tconst1;
   P.tconst2 = c->tconst2;
-  P.scratch = c->fin_scratch;
+  P.scratch = ln.fin_scratch;
   P.out = c->out + (size_t)first * c->out_stride();
   P.n_public = c->n_public;
   P.n = m;
   CKR(launch_finalize(P, st), "finalize");
   g_launches += 1;
-  if (ev) cudaEventRecord(ev[7], st);
+  if (ev) cudaEventRecord(ev[8], st);
   CKR(cudaGetLastError(), "prove chunk launch");
   return ZKB_OK;
 }
 
 // full device pass over the n resident proofs; stage_ms (optional, 8 floats): witness, build_abc, ntt+join,
-// msm sort, msm accumulate G1, msm accumulate G2, msm reduce, finalize
+// msm sort, msm accumulate G1, msm accumulate G2, msm reduce, finalize - summed over chunks.  The instrumented pass is
+// serial (one lane); without stage_ms chunks alternate over the lanes and overlap.
 static int prove_resident(Circuit *c, uint32_t n, bool with_witness, float *stage_ms) {
   cudaStream_t st = c->ctx->stream;
   std::vector<cudaEvent_t> evs;
   auto newev = [&]() { cudaEvent_t e; cudaEventCreate(&e); evs.push_back(e); return e; };
-  cudaEvent_t w0 = nullptr, w1 = nullptr;
-  if (stage_ms) { w0 = newev(); w1 = newev(); cudaEventRecord(w0, st); }
-  if (with_witness) { int rc = run_witness(c, n, st); if (rc) return rc; }
-  if (stage_ms) cudaEventRecord(w1, st);
+  cudaEvent_t start;
+  CKR(cudaEventCreateWithFlags(&start, cudaEventDisableTiming), "event");
+  cudaEventRecord(start, st);            // inputs / blinding were queued on the context stream
+  // an instrumented pass runs on one lane: event-bracketed stage times are then not shared with another stream
+  const int n_lanes = stage_ms ? 1 : c->n_lanes;
+  for (int i = 0; i < n_lanes; i++) cudaStreamWaitEvent(c->lanes[i].st, start, 0);
   std::vector<cudaEvent_t> chunk_ev;
-  for (uint32_t first = 0; first < n; first += c->chunk) {
+  uint32_t k = 0;
+  for (uint32_t first = 0; first < n; first += c->chunk, k++) {
     uint32_t m = n - first < c->chunk ? n - first : c->chunk;
-    cudaEvent_t ev[8];
+    Lane &ln = c->lanes[k % n_lanes];
+    cudaEvent_t ev[9];
     if (stage_ms) {
-      for (int i = 0; i < 8; i++) { ev[i] = newev(); chunk_ev.push_back(ev[i]); }
-      cudaEventRecord(ev[0], st);
+      for (int i = 0; i < 9; i++) { ev[i] = newev(); chunk_ev.push_back(ev[i]); }
+      cudaEventRecord(ev[0], ln.st);
     }
-    int rc = run_prove_chunk(c, first, m, st, stage_ms ? ev : nullptr);
+    int rc = run_prove_chunk(c, ln, first, m, with_witness, stage_ms ? ev : nullptr);
     if (rc) return rc;
     c->last_chunk_m = m;
+    c->last_lane = (int)(k % n_lanes);
+  }
+  for (int i = 0; i < n_lanes; i++) {
+    cudaEventRecord(c->lanes[i].done, c->lanes[i].st);
+    cudaStreamWaitEvent(st, c->lanes[i].done, 0);
   }
   CKR(cudaStreamSynchronize(st), "prove");
+  cudaEventDestroy(start);
   if (stage_ms) {
     for (int i = 0; i < 8; i++) stage_ms[i] = 0;
-    cudaEventElapsedTime(&stage_ms[0], w0, w1);
-    for (size_t k = 0; k + 7 < chunk_ev.size(); k += 8)
-      for (int i = 0; i < 7; i++) { float t; cudaEventElapsedTime(&t, chunk_ev[k + i], chunk_ev[k + i + 1]); stage_ms[1 + i] += t; }
+    for (size_t q = 0; q + 8 < chunk_ev.size(); q += 9)
+      for (int i = 0; i < 8; i++) { float t; cudaEventElapsedTime(&t, chunk_ev[q + i], chunk_ev[q + i + 1]); stage_ms[i] += t; }
   }
   for (auto e : evs) cudaEventDestroy(e);
   return ZKB_OK;
@@ -385,13 +433,6 @@ static int pack_inputs(const Circuit *c, const char *json, size_t len, uint32_t 
   if (m.size() != 12) { err = "inputs: unexpected signal (not an input of the census circuit)"; return ZKB_ERROR; }
   if (total != c->L.n_inputs) { err = "inputs: size mismatch"; return ZKB_ERROR; }
   return ZKB_OK;
-}
-
-static uint32_t env_u32(const char *name, uint32_t dflt) {
-  const char *v = getenv(name);
-  if (!v || !*v) return dflt;
-  long x = atol(v);
-  return x > 0 ? (uint32_t)x : dflt;
 }
 
 template <class T>
@@ -564,20 +605,18 @@ static void destroy_circuit(Circuit *c) {
   cudaSetDevice(c->ctx->device);
   cudaFree(c->consts); cudaFree(c->hc); cudaFree(c->tmpl); cudaFree(c->sig2wire); cudaFree(c->csr_buf);
   cudaFree(c->csr_val); cudaFree(c->fix1); cudaFree(c->fix2); cudaFree(c->d1tab); cudaFree(c->d2tab);
-  cudaFree(c->tconst1); cudaFree(c->tconst2); cudaFree(c->dw);
+  cudaFree(c->tconst1); cudaFree(c->tconst2);
   cudaFree(c->tabA.tab); cudaFree(c->tabB1.tab); cudaFree(c->tabC.tab); cudaFree(c->tabH.tab); cudaFree(c->tabB2.tab);
   c->ntt.destroy();
-  cudaFree(c->inputs); cudaFree(c->wtns); cudaFree(c->abc); cudaFree(c->hs); cudaFree(c->rs); cudaFree(c->status);
-  cudaFree(c->g1out); cudaFree(c->g2out); cudaFree(c->out); cudaFree(c->fin_scratch);
+  cudaFree(c->inputs); cudaFree(c->wtns); cudaFree(c->rs); cudaFree(c->status); cudaFree(c->out);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_inputs) cudaFreeHost(c->h_inputs);
   if (c->h_rs) cudaFreeHost(c->h_rs);
   if (c->h_status) cudaFreeHost(c->h_status);
-  if (c->sortW.counts) c->sortW.free_all();
-  if (c->sortH.counts) c->sortH.free_all();
-  if (c->work1.buckets) c->work1.free_all();
-  if (c->workH.buckets) c->workH.free_all();
-  if (c->work2.buckets) c->work2.free_all();
+  for (int i = 0; i < MAX_LANES; i++) {
+    c->lanes[i].free_all();
+    if (c->lanes[i].st) { cudaStreamDestroy(c->lanes[i].st); cudaEventDestroy(c->lanes[i].done); }
+  }
   delete c;
 }
 
@@ -739,19 +778,20 @@ int zkb_work_counters(zkb_circuit *h, uint64_t *out) {
   uint32_t m = c->last_chunk_m;
   if (!m) { set_error("no chunk processed yet"); return ZKB_ERROR; }
   unsigned long long t[5] = {0, 0, 0, 0, 0};
-  CKR(msm_count_madds<Fq>(c->sortW, c->tabA, m, &t[0], st), "count");
-  CKR(msm_count_madds<Fq>(c->sortW, c->tabB1, m, &t[1], st), "count");
-  CKR(msm_count_madds<Fq>(c->sortW, c->tabC, m, &t[2], st), "count");
-  CKR(msm_count_madds<Fq>(c->sortH, c->tabH, m, &t[3], st), "count");
-  CKR(msm_count_madds<Fq2>(c->sortW, c->tabB2, m, &t[4], st), "count");
+  Lane &ln = c->lanes[c->last_lane];
+  CKR(msm_count_madds<Fq>(ln.sortW, c->tabA, m, &t[0], st), "count");
+  CKR(msm_count_madds<Fq>(ln.sortW, c->tabB1, m, &t[1], st), "count");
+  CKR(msm_count_madds<Fq>(ln.sortW, c->tabC, m, &t[2], st), "count");
+  CKR(msm_count_madds<Fq>(ln.sortH, c->tabH, m, &t[3], st), "count");
+  CKR(msm_count_madds<Fq2>(ln.sortW, c->tabB2, m, &t[4], st), "count");
   out[0] = t[0] + t[1] + t[2] + t[3];
   out[1] = t[4];
   uint64_t ew = 0, eh = 0;
   for (uint32_t b = 0; b < m; b++) {
     uint32_t v;
-    CKR(cudaMemcpy(&v, c->sortW.offsets + (size_t)b * (c->cfgW.buckets + 1) + c->cfgW.buckets, 4, cudaMemcpyDeviceToHost), "d2h");
+    CKR(cudaMemcpy(&v, ln.sortW.offsets + (size_t)b * (c->cfgW.buckets + 1) + c->cfgW.buckets, 4, cudaMemcpyDeviceToHost), "d2h");
     ew += v;
-    CKR(cudaMemcpy(&v, c->sortH.offsets + (size_t)b * (c->cfgH.buckets + 1) + c->cfgH.buckets, 4, cudaMemcpyDeviceToHost), "d2h");
+    CKR(cudaMemcpy(&v, ln.sortH.offsets + (size_t)b * (c->cfgH.buckets + 1) + c->cfgH.buckets, 4, cudaMemcpyDeviceToHost), "d2h");
     eh += v;
   }
   out[2] = ew; out[3] = eh; out[4] = m; out[5] = c->chunk;
@@ -766,9 +806,10 @@ int zkb_debug_partials(zkb_circuit *h, void *out384, void *h_out) {
   CKR(cudaSetDevice(c->ctx->device), "set device");
   XYZZ<Fq> g1[4];
   XYZZ<Fq2> g2;
-  CKR(cudaMemcpy(g1, c->g1out, 3 * sizeof(XYZZ<Fq>), cudaMemcpyDeviceToHost), "d2h");
-  CKR(cudaMemcpy(g1 + 3, c->g1out + (size_t)3 * c->chunk, sizeof(XYZZ<Fq>), cudaMemcpyDeviceToHost), "d2h");
-  CKR(cudaMemcpy(&g2, c->g2out, sizeof(XYZZ<Fq2>), cudaMemcpyDeviceToHost), "d2h");
+  Lane &ln = c->lanes[c->last_lane];
+  CKR(cudaMemcpy(g1, ln.g1out, 3 * sizeof(XYZZ<Fq>), cudaMemcpyDeviceToHost), "d2h");
+  CKR(cudaMemcpy(g1 + 3, ln.g1out + (size_t)3 * c->chunk, sizeof(XYZZ<Fq>), cudaMemcpyDeviceToHost), "d2h");
+  CKR(cudaMemcpy(&g2, ln.g2out, sizeof(XYZZ<Fq2>), cudaMemcpyDeviceToHost), "d2h");
   if (c->tconst1) {   // the device sums cover w - tmpl; add the per-key constant part back (host arithmetic, debug only)
     XYZZ<Fq> t1[3];
     XYZZ<Fq2> t2;
@@ -787,7 +828,7 @@ int zkb_debug_partials(zkb_circuit *h, void *out384, void *h_out) {
   Affine<Fq2> b = g2.to_affine();
   Fq cc[4] = {b.x.a.from_mont(), b.x.b.from_mont(), b.y.a.from_mont(), b.y.b.from_mont()};
   memcpy(o + 128, cc, 128);
-  if (h_out) CKR(cudaMemcpy(h_out, c->hs, (size_t)c->domain * 32, cudaMemcpyDeviceToHost), "d2h h");
+  if (h_out) CKR(cudaMemcpy(h_out, ln.hs, (size_t)c->domain * 32, cudaMemcpyDeviceToHost), "d2h h");
   return ZKB_OK;
 }
 
@@ -905,7 +946,7 @@ int zkb_witness(zkb_circuit *h, const char *inputs_json, size_t inputs_len, void
   if (pack_inputs(c, inputs_json, inputs_len, c->h_inputs[0].v, err)) { set_error(err); return ZKB_ERROR; }
   cudaStream_t st = c->ctx->stream;
   CKR(cudaMemcpyAsync(c->inputs, c->h_inputs, (size_t)c->L.n_inputs * 32, cudaMemcpyHostToDevice, st), "h2d");
-  if ((rc = run_witness(c, 1, st))) return rc;
+  if ((rc = run_witness(c, 0, 1, st))) return rc;
   uint8_t *o = (uint8_t *)wtns_out;
   static const uint32_t RMOD[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
                                    0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
