@@ -30,6 +30,7 @@ extern "C" {
 #define ZKB_INVALID_WITNESS_LENGTH 3
 #define ZKB_ASSERT_FAILED 4
 #define ZKB_UNSUPPORTED_CIRCUIT 5
+#define ZKB_INVALID_PROOF 6
 
 typedef struct zkb_ctx zkb_ctx;         /* one GPU + its stream */
 typedef struct zkb_circuit zkb_circuit; /* a proving key (+ witness calculator) resident on that GPU */
@@ -85,6 +86,16 @@ int zkb_prove_wtns(zkb_circuit *c, const void *wtns, size_t wtns_size, char *pro
 int groth16_prover(const void *zkey_buffer, unsigned long zkey_size, const void *wtns_buffer, unsigned long wtns_size,
                    char *proof_buffer, unsigned long *proof_size, char *public_buffer, unsigned long *public_size,
                    char *error_msg, unsigned long error_msg_maxsize);
+
+/* Groth16 verification on the GPU (one proof per thread): (*Proof).Verify(vkey) of zk_census_test.go:122 /
+ * `snarkjs groth16 verify`.  Documents are the reference's JSON files (verification_key.json, signals.json,
+ * proof.json).  zkb_verify returns ZKB_OK when the proof is valid and ZKB_INVALID_PROOF when it is not;
+ * the batch form writes ok[i] = 1 / 0.  Encodings outside [0,q) / [0,r) and points off the curve or outside the
+ * G2 subgroup are rejected. */
+int zkb_verify(const char *vkey_json, size_t vkey_len, const char *public_json, size_t public_len,
+               const char *proof_json, size_t proof_len);
+int zkb_verify_batch(const char *vkey_json, size_t vkey_len, int n, const char *const *publics_json,
+                     const size_t *publics_len, const char *const *proofs_json, const size_t *proofs_len, int *ok);
 
 /* Batched Poseidon with the circuit's constants (arity 2..4): the hash function of the census and SIK trees
  * (arbo.HashFunctionPoseidon, internal/helpers.go:45-49; circomlibjs in ts_inputs/src/inputs.ts:16,33).

@@ -125,3 +125,25 @@ def test_census_tree_builder_matches_oracle_generator(art_dir):
     one = CT.SparseMerkleTree(hasher, {5: 7})
     assert one.root == P([5, 7, 1]) and one.siblings(5) == []
     assert CT.bytes_to_arbo(b"x") == G.bytes_to_arbo(b"x")
+
+
+def test_host_build_of_pairing_verifies_reference_fixture(tmp_path):
+    """csrc/pairing.cuh compiled for the host (portable path): the reference's proof.json verifies under its
+    verification_key.json; tampering is rejected (the same code runs per thread in zkb_verify on the GPU)."""
+    import oracle_lib as O
+    src = os.path.join(H.ROOT, "tests", "host_emul", "pairing_host.cc")
+    so = str(tmp_path / "libpairing_host.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
+    L = ctypes.CDLL(so)
+    vk = json.load(open(H.GOLDEN + "/verification_key.json"))
+    pf = json.load(open(H.GOLDEN + "/proof.json"))
+    pub = json.load(open(H.GOLDEN + "/signals.json"))
+    vkb, ic, n = O.vkey_bin(vk)
+    call = lambda pub_, pf_: L.host_groth16_verify(O._buf(vkb), O._buf(ic), n, O._buf(O.pub_bin(pub_)), O._buf(O.proof_bin(pf_)))
+    assert call(pub, pf) == 1
+    bad = list(pub)
+    bad[0] = "1"
+    assert call(bad, pf) == 0
+    pf2 = json.loads(json.dumps(pf))
+    pf2["pi_c"] = pf["pi_a"]
+    assert call(pub, pf2) == 0

@@ -206,3 +206,39 @@ def test_stage_timing_and_work_counters(circuit):
     assert 16 * 131072 * 0.9 < wc["g1_madds_per_proof"] < 16 * 131072 + 3 * 16 * 82754 * 0.25
     assert 0 < wc["g2_madds_per_proof"] < 16 * 82754 * 0.25
     print("stage ms for 32 proofs:", [round(float(x), 2) for x in st], wc)
+
+
+def test_gpu_verifier_reference_fixture_and_own_proofs(circuit):
+    """zkb_verify: the reference's committed proof verifies under its committed vkey; tampering and
+    out-of-range encodings are rejected; our own proofs verify under the dev vkey and agree with the oracle verifier."""
+    from zk_franchise_proof_circuit_b200 import prover
+    vk = open(H.GOLDEN + "/verification_key.json", "rb").read()
+    pf = open(H.GOLDEN + "/proof.json", "rb").read()
+    pub = open(H.GOLDEN + "/signals.json", "rb").read()
+    proof = prover.parse_proof(pf, pub)                                  # zk_census_test.go:118
+    proof.verify(vk)                                                     # :122 - no exception
+    assert prover.groth16.verify(vk, json.loads(pub), json.loads(pf)) is True
+    sig = json.loads(pub)
+    bad = list(sig)
+    bad[7] = "6"
+    assert prover.groth16.verify(vk, bad, json.loads(pf)) is False
+    R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    aliased = list(sig)
+    aliased[7] = str(int(sig[7]) + R)                                    # same residue, must still be rejected
+    assert prover.groth16.verify(vk, aliased, json.loads(pf)) is False
+    swapped = json.loads(pf)
+    swapped["pi_a"], swapped["pi_c"] = swapped["pi_c"], swapped["pi_a"]
+    assert prover.groth16.verify(vk, sig, swapped) is False
+    with pytest.raises(prover.NativeError) as ei:
+        prover.parse_proof(json.dumps(swapped).encode(), pub).verify(vk)
+    assert ei.value.code == prover.INVALID_PROOF
+    # own proofs, batch
+    vs = H.voters(64)[:16]
+    proofs, pubs, status = circuit.fullprove_batch([json.dumps(v) for v in vs])
+    dev_vk = json.dumps(H.dev_vkey()).encode()
+    ok = prover.verify_batch(dev_vk, pubs, proofs)
+    assert ok == [1] * 16
+    assert prover.verify_batch(dev_vk, pubs[:2], [proofs[1], proofs[0]]) == [0, 0]
+    assert prover.verify_batch(vk, pubs[:1], proofs[:1]) == [0]          # wrong key
+    for p, q in zip(proofs[:4], pubs[:4]):
+        assert O.verify(H.dev_vkey(), json.loads(q), json.loads(p))

@@ -9,6 +9,7 @@
 #define ZKB_INVALID_WITNESS_LENGTH 3
 #define ZKB_ASSERT_FAILED 4
 #define ZKB_UNSUPPORTED_CIRCUIT 5
+#define ZKB_INVALID_PROOF 6
 
 extern "C" int zkb_device_count(void);
 extern "C" const char *zkb_last_error(void);

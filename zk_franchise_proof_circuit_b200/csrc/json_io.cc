@@ -11,25 +11,35 @@ namespace zkb {
 static const uint32_t RMOD[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
                                  0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
 
-static bool geq_r(const uint32_t v[9]) {
+static const uint32_t QMOD[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                                 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+
+static bool geq_m(const uint32_t v[9], const uint32_t *M) {
   if (v[8]) return true;
   for (int i = 7; i >= 0; i--) {
-    if (v[i] > RMOD[i]) return true;
-    if (v[i] < RMOD[i]) return false;
+    if (v[i] > M[i]) return true;
+    if (v[i] < M[i]) return false;
   }
   return true;
 }
-static void sub_r(uint32_t v[9]) {
+static void sub_m(uint32_t v[9], const uint32_t *M) {
   uint64_t br = 0;
   for (int i = 0; i < 8; i++) {
-    uint64_t d = (uint64_t)v[i] - RMOD[i] - br;
+    uint64_t d = (uint64_t)v[i] - M[i] - br;
     v[i] = (uint32_t)d;
     br = (d >> 32) & 1;
   }
   v[8] -= (uint32_t)br;
 }
 
-bool dec_to_fr(const char *s, size_t len, uint32_t out[8]) {
+static thread_local bool g_reduced = false;   // set when a parsed value was >= the modulus (or negative)
+static bool dec_to_mod(const char *s, size_t len, uint32_t out[8], const uint32_t *RMOD);
+bool dec_to_fr(const char *s, size_t len, uint32_t out[8]) { return dec_to_mod(s, len, out, RMOD); }
+bool dec_to_fq(const char *s, size_t len, uint32_t out[8]) { return dec_to_mod(s, len, out, QMOD); }
+bool json_value_was_reduced() { return g_reduced; }
+void json_reset_reduced() { g_reduced = false; }
+
+static bool dec_to_mod(const char *s, size_t len, uint32_t out[8], const uint32_t *RMOD) {
   uint32_t v[9] = {0};
   bool neg = false;
   size_t i = 0;
@@ -44,9 +54,10 @@ bool dec_to_fr(const char *s, size_t len, uint32_t out[8]) {
       v[k] = (uint32_t)c;
       c >>= 32;
     }
-    while (geq_r(v)) sub_r(v);
+    while (geq_m(v, RMOD)) { sub_m(v, RMOD); g_reduced = true; }
   }
   if (neg) {
+    g_reduced = true;
     bool zero = true;
     for (int k = 0; k < 8; k++) zero = zero && v[k] == 0;
     if (!zero) {
@@ -115,17 +126,24 @@ struct P {
   }
 };
 
-bool flatten(P &p, std::vector<uint32_t> &out, int depth) {
+// strict = false: a non-decimal scalar (e.g. "groth16") marks the whole value as non-numeric instead of failing
+bool flatten(P &p, std::vector<uint32_t> &out, int depth, bool base_field = false, bool strict = true,
+             bool *non_numeric = nullptr) {
   if (depth > 8) return false;
   if (p.eat('[')) {
     if (p.eat(']')) return true;
-    do { if (!flatten(p, out, depth + 1)) return false; } while (p.eat(','));
+    do { if (!flatten(p, out, depth + 1, base_field, strict, non_numeric)) return false; } while (p.eat(','));
     return p.eat(']');
   }
   std::string tok;
   if (!p.scalar(tok)) return false;
   uint32_t v[8];
-  if (!dec_to_fr(tok.data(), tok.size(), v)) return false;
+  bool ok = base_field ? dec_to_fq(tok.data(), tok.size(), v) : dec_to_fr(tok.data(), tok.size(), v);
+  if (!ok) {
+    if (strict) return false;
+    if (non_numeric) *non_numeric = true;
+    return true;
+  }
   out.insert(out.end(), v, v + 8);
   return true;
 }
@@ -143,6 +161,31 @@ bool parse_inputs_json(const char *s, size_t len, std::map<std::string, std::vec
     out[key] = std::move(vals);
   } while (p.eat(','));
   if (!p.eat('}')) { err = "inputs: expected }"; return false; }
+  return true;
+}
+
+// Generic {"key": number | "decimal" | nested arrays of those | "text"} reader used for verification_key.json
+// and proof.json: numeric values are flattened and reduced mod q (base_field) or mod r; text values are skipped.
+bool parse_json_numbers(const char *s, size_t len, bool base_field, std::map<std::string, std::vector<uint32_t>> &out,
+                        std::string &err) {
+  P p{s, 0, len};
+  if (!p.eat('{')) { err = "expected a JSON object"; return false; }
+  if (p.eat('}')) return true;
+  do {
+    std::string key;
+    if (!p.str(key) || !p.eat(':')) { err = "bad key"; return false; }
+    std::vector<uint32_t> vals;
+    bool non_numeric = false;
+    if (!flatten(p, vals, 0, base_field, false, &non_numeric)) { err = "bad value for " + key; return false; }
+    if (!non_numeric) out[key] = std::move(vals);
+  } while (p.eat(','));
+  if (!p.eat('}')) { err = "expected }"; return false; }
+  return true;
+}
+
+bool parse_json_array(const char *s, size_t len, std::vector<uint32_t> &out, std::string &err) {
+  P p{s, 0, len};
+  if (!p.peek('[') || !flatten(p, out, 0)) { err = "expected a JSON array of decimal strings"; return false; }
   return true;
 }
 

@@ -20,7 +20,7 @@ import numpy as np
 from . import _native
 from ._native import NativeError  # noqa: F401  (re-export)
 
-OK, ERROR, SHORT_BUFFER, INVALID_WITNESS_LENGTH, ASSERT_FAILED, UNSUPPORTED_CIRCUIT = range(6)
+OK, ERROR, SHORT_BUFFER, INVALID_WITNESS_LENGTH, ASSERT_FAILED, UNSUPPORTED_CIRCUIT, INVALID_PROOF = range(7)
 
 _vp, _sz, _i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
 _bound = False
@@ -45,6 +45,8 @@ def _lib():
         L.zkb_debug_partials.argtypes = [_vp, _vp, _vp]
         L.zkb_poseidon_hash.argtypes = [_vp, _i32, _i32, _vp, _vp]
         L.zkb_launch_count.restype = ctypes.c_uint64
+        L.zkb_verify.argtypes = [ctypes.c_char_p, _sz, ctypes.c_char_p, _sz, ctypes.c_char_p, _sz]
+        L.zkb_verify_batch.argtypes = [ctypes.c_char_p, _sz, _i32, _vp, _vp, _vp, _vp, _vp]
         L.zkb_work_counters.argtypes = [_vp, _vp]
         L.zkb_fullprove_batch.argtypes = [_vp, _i32, _vp, _vp, _vp, _sz, _vp, _sz, _vp]
         L.zkb_fullprove.argtypes = [_vp, ctypes.c_char_p, _sz, _vp, ctypes.POINTER(_sz), _vp, ctypes.POINTER(_sz),
@@ -229,6 +231,12 @@ class Proof:
         self.data = data
         self.pub_signals = pub_signals
 
+    def verify(self, vkey: bytes) -> None:
+        """(*Proof).Verify(vkey []byte) error  -  zk_census_test.go:122.  Raises NativeError(INVALID_PROOF) when the
+        proof does not verify; the pairing check runs on the GPU (zkb_verify)."""
+        pj, sj = self.bytes()
+        verify(vkey, sj, pj)
+
     def bytes(self):
         """(*Proof).Bytes(): compact JSON of pi_a/pi_b/pi_c only, and of the public signals (zk_census_test.go:93)."""
         d = {k: self.data[k] for k in ("pi_a", "pi_b", "pi_c")}
@@ -271,9 +279,40 @@ def parse_proof(proof_data: bytes, pub_signals: bytes) -> Proof:
     return Proof(d, json.loads(pub_signals))
 
 
+def verify(vkey: bytes, public_signals: bytes, proof: bytes) -> None:
+    """Groth16 verification of JSON documents on the GPU; raises NativeError (code INVALID_PROOF) if invalid."""
+    as_b = lambda x: x if isinstance(x, bytes) else (x.encode() if isinstance(x, str) else json.dumps(x).encode())
+    vk, ps, pf = as_b(vkey), as_b(public_signals), as_b(proof)
+    _native.check(_lib().zkb_verify(vk, len(vk), ps, len(ps), pf, len(pf)))
+
+
+def verify_batch(vkey: bytes, public_signals: list, proofs: list) -> list:
+    """ok flags (1/0) for n (public signals, proof) JSON pairs under one verification key (zkb_verify_batch)."""
+    n = len(proofs)
+    as_b = lambda x: x if isinstance(x, bytes) else (x.encode() if isinstance(x, str) else json.dumps(x).encode())
+    vk = as_b(vkey)
+    ps, pf = [as_b(x) for x in public_signals], [as_b(x) for x in proofs]
+    pa, fa = (ctypes.c_char_p * n)(*ps), (ctypes.c_char_p * n)(*pf)
+    pl, fl = (ctypes.c_size_t * n)(*[len(x) for x in ps]), (ctypes.c_size_t * n)(*[len(x) for x in pf])
+    ok = (ctypes.c_int * n)()
+    _native.check(_lib().zkb_verify_batch(vk, len(vk), n, pa, pl, fa, fl, ok))
+    return list(ok)
+
+
 # ---- snarkjs-shaped API -------------------------------------------------------------------------------
 
 class groth16:  # noqa: N801  (mirrors `import { groth16 } from "snarkjs"`)
+    @staticmethod
+    def verify(vkey, public_signals, proof) -> bool:
+        """groth16.verify(vKey, publicSignals, proof) -> boolean"""
+        try:
+            verify(vkey, public_signals, proof)
+            return True
+        except NativeError as e:
+            if e.code == INVALID_PROOF:
+                return False
+            raise
+
     @staticmethod
     def full_prove(inputs, wasm_file, zkey_file):
         """groth16.fullProve(input, wasmFile, zkeyFile) -> {proof, publicSignals}  -  ts_inputs/src/example.ts:358"""
