@@ -142,7 +142,11 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t *counts, uint32_t 
 // order[b][i] = bucket ids of batch item b sorted by descending size (counting sort on the size, sizes >= 1023
 // share the first bin).  The accumulate kernel walks buckets in this order, so the 32 lanes of a warp get lists of
 // (nearly) equal length and the longest lists start first.
-__global__ void __launch_bounds__(1024) k_order(const uint32_t *counts, uint32_t *order, uint32_t buckets) {
+static constexpr uint32_t LONG_BUCKET = 128;   // lists longer than this are summed by a whole warp
+static constexpr uint32_t MAX_LONG = 256;      // at most this many per batch item (the rest stay with one thread)
+
+__global__ void __launch_bounds__(1024) k_order(const uint32_t *counts, uint32_t *order, uint32_t *n_long,
+                                                uint32_t buckets) {
   __shared__ uint32_t hist[1024];
   const uint32_t b = blockIdx.x, t = threadIdx.x;
   const uint32_t *c = counts + (size_t)b * buckets;
@@ -172,6 +176,8 @@ __global__ void __launch_bounds__(1024) k_order(const uint32_t *counts, uint32_t
   __syncthreads();
   hist[t] = wt[t >> 5] + x - v;
   __syncthreads();
+  if (t == 1023u - LONG_BUCKET) n_long[b] = min(hist[t], MAX_LONG);   // buckets in bins before t: size > LONG_BUCKET
+  __syncthreads();
   uint32_t *o = order + (size_t)b * buckets;
   for (uint32_t i = t; i < buckets; i += 1024) {
     uint32_t pos = atomicAdd(&hist[1023u - min(c[i], 1023u)], 1u);
@@ -189,11 +195,12 @@ cudaError_t MsmSort::alloc(uint32_t n_, uint32_t batch_, MsmCfg cfg_) {
   CK(cudaMalloc(&cursor, (size_t)batch * cfg.buckets * 4));
   CK(cudaMalloc(&entries, (size_t)batch * n * cfg.windows * 4));
   CK(cudaMalloc(&order, (size_t)batch * cfg.buckets * 4));
+  CK(cudaMalloc(&n_long, (size_t)batch * 4));
   return cudaSuccess;
 }
 void MsmSort::free_all() {
-  cudaFree(counts); cudaFree(offsets); cudaFree(cursor); cudaFree(entries); cudaFree(order);
-  counts = offsets = cursor = entries = order = nullptr;
+  cudaFree(counts); cudaFree(offsets); cudaFree(cursor); cudaFree(entries); cudaFree(order); cudaFree(n_long);
+  counts = offsets = cursor = entries = order = n_long = nullptr;
 }
 cudaError_t MsmSort::run(const Fr *scalars, size_t scalar_stride, uint32_t nbatch, cudaStream_t st) {
   if (nbatch > batch) return cudaErrorInvalidValue;
@@ -201,7 +208,7 @@ cudaError_t MsmSort::run(const Fr *scalars, size_t scalar_stride, uint32_t nbatc
   dim3 grid((n + 255) / 256, nbatch);
   k_digits<false><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cfg.c, cfg.windows, cfg.buckets, counts, nullptr);
   k_scan<<<nbatch, 1024, 0, st>>>(counts, offsets, cursor, cfg.buckets);
-  k_order<<<nbatch, 1024, 0, st>>>(counts, order, cfg.buckets);
+  k_order<<<nbatch, 1024, 0, st>>>(counts, order, n_long, cfg.buckets);
   k_digits<true><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cfg.c, cfg.windows, cfg.buckets, cursor, entries);
   return cudaGetLastError();
 }
@@ -225,13 +232,17 @@ template <class F, int THREADS, int MINB, bool INL>
 __global__ void __launch_bounds__(THREADS, MINB) k_accumulate(TablePtrs<F> tabs, int ntab, uint32_t n, int windows,
                                                         uint32_t nbuckets, const uint32_t *__restrict__ offsets,
                                                         const uint32_t *__restrict__ entries,
-                                                        const uint32_t *__restrict__ order, XYZZ<F> *buckets) {
+                                                        const uint32_t *__restrict__ order,
+                                                        const uint32_t *__restrict__ n_long, XYZZ<F> *buckets) {
   uint32_t t = blockIdx.y, b = blockIdx.z;
-  const uint32_t bucket = order[(size_t)b * nbuckets + blockIdx.x * THREADS + threadIdx.x];
+  const uint32_t pos = blockIdx.x * THREADS + threadIdx.x;
+  if ((pos | 31u) < n_long[b]) return;     // this whole warp's buckets belong to k_accumulate_long
+  const bool mine = pos >= n_long[b];
+  const uint32_t bucket = order[(size_t)b * nbuckets + pos];
   const Affine<F> *tab = t == 0 ? tabs.tab[0] : (t == 1 ? tabs.tab[1] : (t == 2 ? tabs.tab[2] : tabs.tab[3]));
   const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
   const uint32_t *ent = entries + (size_t)b * n * windows;
-  const uint32_t beg = off[bucket], len = off[bucket + 1] - beg;
+  const uint32_t beg = off[bucket], len = mine ? off[bucket + 1] - beg : 0u;
   const uint32_t maxlen = __reduce_max_sync(0xffffffffu, len);
   XYZZ<F> acc = XYZZ<F>::infinity();
   bool acc_inf = true;
@@ -264,7 +275,65 @@ __global__ void __launch_bounds__(THREADS, MINB) k_accumulate(TablePtrs<F> tabs,
     }
   }
   if (acc_inf) acc = XYZZ<F>::infinity();
-  stg_pod(buckets + ((size_t)(b * ntab + t) * nbuckets + bucket), acc);
+  if (mine) stg_pod(buckets + ((size_t)(b * ntab + t) * nbuckets + bucket), acc);
+}
+
+// One warp per long bucket (the n_long[b] largest): lanes take entries l, l + 32, ... with the same branch-free
+// mixed add, then the 32 partial sums are folded with shuffles.  Long lists come from many scalars sharing a digit
+// (e.g. hundreds of 0/1-valued wires that flip with respect to the template all have the difference +-1).
+template <class F>
+__global__ void __launch_bounds__(32) k_accumulate_long(TablePtrs<F> tabs, int ntab, uint32_t n, int windows,
+                                                        uint32_t nbuckets, const uint32_t *__restrict__ offsets,
+                                                        const uint32_t *__restrict__ entries,
+                                                        const uint32_t *__restrict__ order,
+                                                        const uint32_t *__restrict__ n_long, XYZZ<F> *buckets) {
+  const uint32_t t = blockIdx.y, b = blockIdx.z, lane = threadIdx.x;
+  if (blockIdx.x >= n_long[b]) return;
+  const Affine<F> *tab = t == 0 ? tabs.tab[0] : (t == 1 ? tabs.tab[1] : (t == 2 ? tabs.tab[2] : tabs.tab[3]));
+  const uint32_t bucket = order[(size_t)b * nbuckets + blockIdx.x];
+  const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
+  const uint32_t *ent = entries + (size_t)b * n * windows;
+  const uint32_t beg = off[bucket], len = off[bucket + 1] - beg;
+  XYZZ<F> acc = XYZZ<F>::infinity();
+  bool acc_inf = true;
+  for (uint32_t i = lane; i < len + lane; i += 32) {      // same trip count on every lane
+    const bool active = i < len;
+    const uint32_t x = active ? ent[beg + i] : 0u;
+    Affine<F> p = ldg_pod(tab + (x & 0x7fffffffu));
+    const bool use = active && !p.is_inf();
+    p.y = F::select((x >> 31) != 0, p.y.neg(), p.y);
+    F U2 = p.x.mulc(acc.ZZ), S2 = p.y.mulc(acc.ZZZ);
+    F P = U2 - acc.X, R = S2 - acc.Y;
+    const bool special = use && !acc_inf && P.is_zero();
+    F PP = P.sqrc(), PPP = P.mulc(PP), Q = acc.X.mulc(PP);
+    F X3 = R.sqrc() - PPP - Q.dbl();
+    F Y3 = R.mulc(Q - X3) - acc.Y.mulc(PPP);
+    F ZZ3 = acc.ZZ.mulc(PP), ZZZ3 = acc.ZZZ.mulc(PPP);
+    const bool normal = use && !acc_inf && !special, first = use && acc_inf;
+    acc.X = F::select(normal, X3, F::select(first, p.x, acc.X));
+    acc.Y = F::select(normal, Y3, F::select(first, p.y, acc.Y));
+    acc.ZZ = F::select(normal, ZZ3, F::select(first, F::one(), acc.ZZ));
+    acc.ZZZ = F::select(normal, ZZZ3, F::select(first, F::one(), acc.ZZZ));
+    acc_inf = acc_inf && !first;
+    if (__any_sync(0xffffffffu, special)) {
+      if (special) {
+        if (R.is_zero()) { acc = XYZZ<F>::dbl_affine(p); }
+        else { acc = XYZZ<F>::infinity(); acc_inf = true; }
+      }
+      __syncwarp();
+    }
+  }
+  if (acc_inf) acc = XYZZ<F>::infinity();
+  constexpr int WORDS = sizeof(XYZZ<F>) / 4;
+  for (int d = 16; d >= 1; d >>= 1) {
+    XYZZ<F> other;
+    uint32_t *src = reinterpret_cast<uint32_t *>(&acc), *dst = reinterpret_cast<uint32_t *>(&other);
+#pragma unroll
+    for (int w = 0; w < WORDS; w++) dst[w] = __shfl_down_sync(0xffffffffu, src[w], d);
+    if (lane < (uint32_t)d) xyzz_add_ni(&acc, &other);
+    __syncwarp();
+  }
+  if (lane == 0) stg_pod(buckets + ((size_t)(b * ntab + t) * nbuckets + bucket), acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -290,48 +359,57 @@ __global__ void __launch_bounds__(THREADS) k_reduce1(const XYZZ<F> *buckets, XYZ
   stg_pod(part_s + (size_t)slot * parts + t, run);
 }
 
-// level 2: one warp per slot, lane l owns span = parts/32 consecutive chunks.
-// total = sum_t R_t + 32 * sum_t t * S_t,   sum_t t S_t = span * sum_l l sigma_l + sum_l rho_l
+// level 2: one CTA of min(parts, 256) threads per slot.  total = sum_t R_t + 32 * sum_t t * S_t: a thread folds its
+// span of parts, forms t * sigma_t by double-and-add over the bits of t, and both sums are folded by a shared-memory
+// tree, so the depth is ~4 log2(threads) group operations instead of a serial pass over the parts.
 template <class F>
-__global__ void __launch_bounds__(32) k_reduce2(const XYZZ<F> *part_r, const XYZZ<F> *part_s, XYZZ<F> *out,
-                                                uint32_t parts) {
-  __shared__ XYZZ<F> sh_r[32], sh_sig[32], sh_rho[32];
-  const uint32_t slot = blockIdx.x, l = threadIdx.x, span = parts / 32;
-  const XYZZ<F> *R = part_r + (size_t)slot * parts + l * span;
-  const XYZZ<F> *S = part_s + (size_t)slot * parts + l * span;
-  XYZZ<F> r = XYZZ<F>::infinity(), x;
+__device__ void block_tree_sum(XYZZ<F> *sm, XYZZ<F> &v, uint32_t t, uint32_t parts) {
+  stg_pod(sm + t, v);
+  __syncthreads();
+  for (uint32_t stride = parts / 2; stride >= 1; stride >>= 1) {
+    if (t < stride) {
+      xyzz_add_ni(&v, sm + t + stride);
+      stg_pod(sm + t, v);
+    }
+    __syncthreads();
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) k_reduce2(const XYZZ<F> *part_r, const XYZZ<F> *part_s, XYZZ<F> *out,
+                                                 uint32_t parts) {
+  extern __shared__ uint4 sm_raw[];
+  XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(sm_raw);
+  const uint32_t slot = blockIdx.x, t = threadIdx.x, nthr = blockDim.x, span = parts / nthr;   // span = 1 or 4
+  const XYZZ<F> *R = part_r + (size_t)slot * parts + t * span, *S = part_s + (size_t)slot * parts + t * span;
+  // own span: r = sum R, sigma = sum S, rho = sum_u u * S_u
+  XYZZ<F> r = XYZZ<F>::infinity(), sigma = XYZZ<F>::infinity(), rho = XYZZ<F>::infinity(), x;
   for (uint32_t u = 0; u < span; u++) {
     x = ldg_pod(R + u);
     xyzz_add_ni(&r, &x);
-    __syncwarp();
   }
-  XYZZ<F> run = XYZZ<F>::infinity(), rho = XYZZ<F>::infinity();
   for (uint32_t u = span - 1; u >= 1; u--) {
     x = ldg_pod(S + u);
-    xyzz_add_ni(&run, &x);
-    __syncwarp();
-    xyzz_add_ni(&rho, &run);      // rho = sum_u u * S_u
-    __syncwarp();
+    xyzz_add_ni(&sigma, &x);
+    xyzz_add_ni(&rho, &sigma);
   }
   x = ldg_pod(S);
-  xyzz_add_ni(&run, &x);          // sigma = sum_u S_u
-  sh_r[l] = r;
-  sh_sig[l] = run;
-  sh_rho[l] = rho;
-  __syncwarp();
-  if (l == 0) {
-    XYZZ<F> rt = XYZZ<F>::infinity(), pt = XYZZ<F>::infinity();
-    for (int i = 0; i < 32; i++) { xyzz_add_ni(&rt, &sh_r[i]); xyzz_add_ni(&pt, &sh_rho[i]); }
-    XYZZ<F> run2 = XYZZ<F>::infinity(), lt = XYZZ<F>::infinity();
-    for (int i = 31; i >= 1; i--) {
-      xyzz_add_ni(&run2, &sh_sig[i]);
-      xyzz_add_ni(&lt, &run2);    // lt = sum_l l * sigma_l
-    }
-    for (uint32_t s = span; s > 1; s >>= 1) xyzz_dbl_ni(&lt);   // * span
-    xyzz_add_ni(&lt, &pt);                                      // sum_t t * S_t
-    for (int i = 0; i < 5; i++) xyzz_dbl_ni(&lt);               // * 32 (chunk size)
-    xyzz_add_ni(&lt, &rt);
-    stg_pod(out + slot, lt);
+  xyzz_add_ni(&sigma, &x);
+  block_tree_sum<F>(sm, r, t, nthr);               // thread 0: sum_t R_t
+  // sum over the span of (t*span + u) * S = span * (t * sigma) + rho
+  XYZZ<F> w = XYZZ<F>::infinity();
+  for (int bit = 31 - __clz((int)nthr) - 1; bit >= 0; bit--) {   // t < nthr
+    xyzz_dbl_ni(&w);
+    if ((t >> bit) & 1u) xyzz_add_ni(&w, &sigma);
+  }
+  for (uint32_t s = span; s > 1; s >>= 1) xyzz_dbl_ni(&w);
+  xyzz_add_ni(&w, &rho);
+  __syncthreads();
+  block_tree_sum<F>(sm, w, t, nthr);               // thread 0: sum_t t * S_t
+  if (t == 0) {
+    for (int i = 0; i < 5; i++) xyzz_dbl_ni(&w);   // * 32 (chunk size)
+    xyzz_add_ni(&w, &r);
+    stg_pod(out + slot, w);
   }
 }
 
@@ -370,7 +448,7 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
   dim3 grid(nb / TH, ntab, nbatch);
   XYZZ<F> *dst = work.buckets + (size_t)slot0 * nb;
   static const int variant = getenv("ZKB_ACC_VARIANT") ? atoi(getenv("ZKB_ACC_VARIANT")) : 0;
-#define ZKB_ACC(MINB, INL) k_accumulate<F, TH, MINB, INL><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order, dst)
+#define ZKB_ACC(MINB, INL) k_accumulate<F, TH, MINB, INL><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order, sort.n_long, dst)
   if constexpr (sizeof(F) == 32) {
     switch (variant) {
       case 1: ZKB_ACC(4, false); break;
@@ -388,6 +466,9 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
     }
   }
 #undef ZKB_ACC
+  dim3 glong(MAX_LONG, ntab, nbatch);
+  k_accumulate_long<F><<<glong, 32, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order,
+                                             sort.n_long, dst);
   return cudaGetLastError();
 }
 
@@ -400,7 +481,14 @@ cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F
   dim3 g1(parts / RT, nslots);
   k_reduce1<F, RT><<<g1, RT, 0, st>>>(work.buckets + (size_t)slot0 * nb, work.part_r + (size_t)slot0 * parts,
                                       work.part_s + (size_t)slot0 * parts, nb);
-  k_reduce2<F><<<nslots, 32, 0, st>>>(work.part_r + (size_t)slot0 * parts, work.part_s + (size_t)slot0 * parts, out, parts);
+  const uint32_t nthr = parts < 256 ? parts : 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_reduce2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * (int)sizeof(XYZZ<F>));
+    attr_set = true;
+  }
+  k_reduce2<F><<<nslots, nthr, nthr * sizeof(XYZZ<F>), st>>>(work.part_r + (size_t)slot0 * parts,
+                                                              work.part_s + (size_t)slot0 * parts, out, parts);
   return cudaGetLastError();
 }
 

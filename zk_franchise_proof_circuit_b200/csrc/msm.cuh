@@ -40,6 +40,7 @@ struct MsmSort {
   uint32_t *cursor = nullptr;   // [batch][buckets]      scatter cursors
   uint32_t *entries = nullptr;  // [batch][n * windows]
   uint32_t *order = nullptr;    // [batch][buckets]      bucket ids by descending size
+  uint32_t *n_long = nullptr;   // [batch]               how many leading buckets of `order` a whole warp sums
   cudaError_t alloc(uint32_t n, uint32_t batch, MsmCfg cfg);
   void free_all();
   // scalars: [batch] vectors of n canonical 256-bit values, `scalar_stride` elements apart

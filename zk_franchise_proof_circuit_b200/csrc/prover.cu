@@ -341,7 +341,7 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
   CKR(msm_reduce<Fq>(ln.workH, 0, m, ln.g1out + (size_t)3 * c->chunk, st), "msm reduce g1 (H)");
   CKR(msm_reduce<Fq2>(ln.work2, 0, m, ln.g2out, st), "msm reduce g2");
   if (ev) cudaEventRecord(ev[7], st);
-  g_launches += 8 + 2 + 1 + 6;   // 2 sorts x (count, scan, order, scatter), 2 + 1 accumulate, 3 x 2 reduce
+  g_launches += 8 + 4 + 2 + 6;   // 2 sorts x (count, scan, order, scatter), (2 + 1) x 2 accumulate, 3 x 2 reduce
   FinalizeParams P;
   P.g1 = ln.g1out;
   P.g1h = ln.g1out + (size_t)3 * c->chunk;
