@@ -21,20 +21,25 @@ int host_witness(const uint32_t *consts, const uint32_t *lens, const int32_t *si
     L.pex[i].m_off = off; off += lens[4 * i + 2];
     L.pex[i].p_off = off; off += lens[4 * i + 3];
   }
+  std::vector<Fr> stage(L.n_signals, Fr::zero());
   WitnessEnv e;
   e.L = &L;
   e.consts = reinterpret_cast<const Fr *>(consts);
-  e.sig2wire = sig2wire;
-  e.out = reinterpret_cast<Fr *>(out);
+  e.stage = stage.data();
   e.status = 0;
   const Fr *in = reinterpret_cast<const Fr *>(inputs);
   Fr zero2[2] = {Fr::zero(), Fr::zero()};
   Fr h00 = poseidon_ex<3>(e, 0, zero2, false);
   Fr z3[3] = {Fr::zero(), Fr::zero(), Fr::one()};
   Fr h001 = poseidon_ex<4>(e, 0, z3, false);
-  census_main_task(e, in);
-  census_tree_task(e, 0, in, h00, h001, skip_const != 0);
-  census_tree_task(e, 1, in, h00, h001, skip_const != 0);
+  for (int task = 0; task < WITNESS_TASKS; task++) census_witness_task(e, task, in, h00, h001, skip_const != 0);
+  // gather: `out` holds the template on entry when skip_const (as the device kernel reads it)
+  Fr *o = reinterpret_cast<Fr *>(out);
+  for (uint32_t s = 0, w = 0; s < n_signals; s++) {
+    if (sig2wire[s] < 0) continue;
+    w = (uint32_t)sig2wire[s];
+    o[w] = witness_gather_one(stage.data(), s, skip_const ? o : nullptr, w);
+  }
   return e.status;
 }
 uint32_t host_layout_signals(uint32_t n_levels_plus1) {

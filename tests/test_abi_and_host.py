@@ -95,15 +95,15 @@ def test_shard_plan_two_ranks_gloo(tmp_path):
         "lo, hi = bench.shard_range(1000, r, w)\n"
         "t = bench.max_over_ranks(float(10 + r), 'cpu')\n"
         "tot = bench.sum_over_ranks(float(hi - lo), 'cpu')\n"
-        "print(json.dumps({'rank': r, 'lo': lo, 'hi': hi, 'tmax': t, 'tot': tot}))\n"
+        f"open(os.path.join({str(tmp_path)!r}, 'rank%d.json' % r), 'w').write("
+        "json.dumps({'rank': r, 'lo': lo, 'hi': hi, 'tmax': t, 'tot': tot}))\n"
         "dist.destroy_process_group()\n")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
-    rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
-    rows.sort(key=lambda x: x["rank"])
+    rows = [json.load(open(tmp_path / f"rank{r}.json")) for r in range(2)]   # per-rank files: stdout can interleave
     assert [(r["lo"], r["hi"]) for r in rows] == [(0, 500), (500, 1000)]
     assert all(r["tmax"] == 11.0 and r["tot"] == 1000.0 for r in rows)
 

@@ -4,10 +4,17 @@
 // every circom signal is produced at circom's own signal number and stored through the wasm's
 // witness->signal table, so the output is the 82,754-wire witness in wasm order, canonical form.
 //
-// One proof is split into three independent tasks (one thread each in the batched kernel):
-//   task 0: censusVerifier = SMTVerifier(161) on (address, availableWeight)
-//   task 1: sik = Poseidon3(address,password,signature), sikVerifier = SMTVerifier(161) on (address, sik)
+// One proof is split into five independent tasks (one thread each in the batched kernel); the two "chain" tasks
+// carry the sequential Poseidon work, everything that does not depend on it (bit decompositions, the IsZero
+// inversions, the state machine) runs beside them:
+//   task 0: censusVerifier chain: hash1New, levels[160..0] (switcher + Poseidon2 per level), checkRoot
+//   task 1: sik = Poseidon3(address,password,signature), then the sikVerifier chain
 //   task 2: main inputs, checkWeight = LessEqThan(252), computedNullifier = Poseidon4, checkNullifier
+//   task 3 / 4: censusVerifier / sikVerifier side: own inputs, Num2Bits_strict + AliasCheck, SMTLevIns (IsZero
+//               inverses), SMTVerifierSM, areKeyEquals, keysOk (and the oldKey = 0 sub-circuits in dense mode)
+// Signals are written to a per-proof staging array indexed by circom signal number (one 32-byte store, tagged
+// "written" / "Montgomery" in the two spare top bits); witness_gather_one then builds each wire from its signal
+// (or from the template when the signal was not produced), converting out of Montgomery form in parallel.
 // Below a leaf's insertion level every SMT level hashes Poseidon2(0,0): those 770-signal blocks (and
 // the oldKey=0 / oldValue=0 sub-circuits) are identical in every proof.  With skip_const they are not
 // recomputed: the output buffer is pre-filled from a template produced once per circuit by running
@@ -117,31 +124,41 @@ static inline bool census_layout_build(CensusLayout &L, uint32_t n_levels_plus1)
 // Env: where signals go.  consts = Poseidon tables (Montgomery form), sig2wire = inverse of the
 // wasm's witness->signal table (-1 = signal eliminated), out = this proof's witness (canonical).
 // ---------------------------------------------------------------------------------------------
+static constexpr uint32_t TAG_WRITTEN = 0x40000000u, TAG_MONT = 0x80000000u;   // top bits of limb 7 (values < 2^254)
+
 struct WitnessEnv {
   const CensusLayout *L;
   const Fr *consts;
-  const int32_t *sig2wire;
-  Fr *out;
+  Fr *stage;          // [n_signals] this proof's staging array (zeroed before the tasks run)
   int status;
 
   ZKB_HD void put_norm(uint32_t sig, const Fr &v) {       // v already canonical
-    int32_t w = sig2wire[sig];
-    if (w >= 0) out[w] = v;
+    Fr t = v;
+    t.v[7] |= TAG_WRITTEN;
+    stage[sig] = t;
   }
-  ZKB_HDN void put(uint32_t sig, const Fr &v_mont) {      // v in Montgomery form
-    int32_t w = sig2wire[sig];
-    if (w >= 0) out[w] = v_mont.from_mont();
+  ZKB_HD void put(uint32_t sig, const Fr &v_mont) {       // v in Montgomery form
+    Fr t = v_mont;
+    t.v[7] |= TAG_WRITTEN | TAG_MONT;
+    stage[sig] = t;
   }
   ZKB_HD void put_u32(uint32_t sig, uint32_t x) {
-    int32_t w = sig2wire[sig];
-    if (w >= 0) {
-      Fr v = Fr::zero();
-      v.v[0] = x;
-      out[w] = v;
-    }
+    Fr v = Fr::zero();
+    v.v[0] = x;
+    v.v[7] = TAG_WRITTEN;
+    stage[sig] = v;
   }
   ZKB_HD void fail() { status = 4; }
 };
+
+// wire value from the staged signal (canonical form), or the template's when the signal was not produced
+ZKB_HD Fr witness_gather_one(const Fr *stage, uint32_t sig, const Fr *tmpl, uint32_t wire) {
+  Fr x = stage[sig];
+  const uint32_t tag = x.v[7];
+  if (!(tag & TAG_WRITTEN)) return tmpl ? tmpl[wire] : Fr::zero();
+  x.v[7] &= ~(TAG_WRITTEN | TAG_MONT);
+  return (tag & TAG_MONT) ? x.from_mont() : x;
+}
 
 ZKB_HDN Fr fr_sbox(WitnessEnv &e, uint32_t sig, const Fr &x) {   // Sigma {out,in,in2,in4}
   Fr x2 = x.sqr(), x4 = x2.sqr(), y = x4 * x;
@@ -253,8 +270,9 @@ ZKB_HD Fr poseidon_comp(WitnessEnv &e, uint32_t base, const Fr *inputs, bool emi
 ZKB_HD uint32_t bit_of(const Fr &x, int i) { return (x.v[i >> 5] >> (i & 31)) & 1u; }
 
 // IsZero {out,in,inv}; x in Montgomery form.  Returns out (0/1).
-ZKB_HDN uint32_t is_zero_comp(WitnessEnv &e, uint32_t sig, const Fr &x) {
+ZKB_HDN uint32_t is_zero_comp(WitnessEnv &e, uint32_t sig, const Fr &x, bool emit = true) {
   uint32_t z = x.is_zero() ? 1u : 0u;
+  if (!emit) return z;
   e.put_u32(sig, z);
   e.put(sig + 1, x);
   if (z) e.put_u32(sig + 2, 0);
@@ -336,56 +354,68 @@ ZKB_HD Fr smt_hash1(WitnessEnv &e, uint32_t sig, const Fr &key, const Fr &value,
 
 // SMTVerifier(n) with enabled = 1, fnc = 0, oldKey = oldValue = isOld0 = 0 (census.circom:79-103).
 // key_n/value_n/root_n/siblings canonical.  h00 = Poseidon2(0,0), h001 = Poseidon3(0,0,1) (Montgomery).
+// chain = the part that carries the sequential hashing (hash1New, levels, checkRoot, the `value` input);
+// side = everything else.  Both recompute the cheap 0/1 bookkeeping (zero flags, levIns, state machine) privately.
 ZKB_HDN void smt_verifier(WitnessEnv &e, const VerifierLayout &V, const Fr &key_n, const Fr &value_n, const Fr &root_n,
-                         const Fr *siblings_n, const Fr &h00, const Fr &h001, bool skip_const) {
+                         const Fr *siblings_n, const Fr &h00, const Fr &h001, bool skip_const, bool chain, bool side) {
   const uint32_t n = e.L->n;
   const uint32_t b = V.base;
-  const Fr key = key_n.to_mont(), value = value_n.to_mont(), root = root_n.to_mont();
-  e.put_u32(b, 1);
-  e.put_norm(b + 1, root_n);
-  for (uint32_t i = 0; i < n; i++) e.put_norm(b + 2 + i, siblings_n[i]);
-  e.put_u32(b + n + 2, 0);   // oldKey
-  e.put_u32(b + n + 3, 0);   // oldValue
-  e.put_u32(b + n + 4, 0);   // isOld0
-  e.put_norm(b + n + 5, key_n);
-  e.put_norm(b + n + 6, value_n);
-  e.put_u32(b + n + 7, 0);   // fnc
-  // hash1Old = SMTHash1(0, 0): constant
-  Fr old1leaf = h001;
-  if (!skip_const) old1leaf = smt_hash1(e, V.hash1Old, Fr::zero(), Fr::zero(), true);
-  Fr new1leaf = smt_hash1(e, V.hash1New, key, value, true);
-  if (!skip_const) num2bits_strict_comp(e, V.n2bOld, Fr::zero());
-  num2bits_strict_comp(e, V.n2bNew, key_n);
+  const Fr key = key_n.to_mont(), root = root_n.to_mont();
+  Fr old1leaf = h001, new1leaf = Fr::zero();
+  if (side) {
+    e.put_u32(b, 1);
+    e.put_norm(b + 1, root_n);
+    for (uint32_t i = 0; i < n; i++) e.put_norm(b + 2 + i, siblings_n[i]);
+    e.put_u32(b + n + 2, 0);   // oldKey
+    e.put_u32(b + n + 3, 0);   // oldValue
+    e.put_u32(b + n + 4, 0);   // isOld0
+    e.put_norm(b + n + 5, key_n);
+    e.put_u32(b + n + 7, 0);   // fnc
+    // hash1Old = SMTHash1(0, 0), n2bOld = Num2Bits_strict(0): constant
+    if (!skip_const) {
+      smt_hash1(e, V.hash1Old, Fr::zero(), Fr::zero(), true);
+      num2bits_strict_comp(e, V.n2bOld, Fr::zero());
+    }
+    num2bits_strict_comp(e, V.n2bNew, key_n);
+  }
+  if (chain) {
+    e.put_norm(b + n + 6, value_n);
+    new1leaf = smt_hash1(e, V.hash1New, key, value_n.to_mont(), true);
+  }
   // smtLevIns {levIns[n], enabled, siblings[n], done[n-1]} + isZero[n]
   const uint32_t li = V.smtLevIns;
-  e.put_u32(li + n, 1);
+  if (side) e.put_u32(li + n, 1);
   // bitmask of zero siblings (n <= 254)
   uint32_t zmask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (uint32_t i = 0; i < n; i++) {
-    e.put_norm(li + n + 1 + i, siblings_n[i]);
-    Fr sm = siblings_n[i].to_mont();
-    uint32_t z = is_zero_comp(e, li + 3 * n + 3 * i, sm);
+    uint32_t z;
+    if (side) {
+      e.put_norm(li + n + 1 + i, siblings_n[i]);
+      z = is_zero_comp(e, li + 3 * n + 3 * i, siblings_n[i].to_mont());
+    } else {
+      z = siblings_n[i].is_zero() ? 1u : 0u;
+    }
     zmask[i >> 5] |= z << (i & 31);
   }
   auto isz = [&](uint32_t i) { return (zmask[i >> 5] >> (i & 31)) & 1u; };
-  if (!isz(n - 1)) e.fail();                                  // (isZero[n-1].out - 1) * enabled === 0
+  if (side && !isz(n - 1)) e.fail();                          // (isZero[n-1].out - 1) * enabled === 0
   // levIns / done (all 0/1); levmask bit i = levIns[i]
   uint32_t levmask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   {
     uint32_t lev = 1u - isz(n - 2);
-    e.put_u32(li + n - 1, lev);
+    if (side) e.put_u32(li + n - 1, lev);
     levmask[(n - 1) >> 5] |= lev << ((n - 1) & 31);
     uint32_t done = lev;
-    e.put_u32(li + 2 * n + 1 + (n - 2), done);
+    if (side) e.put_u32(li + 2 * n + 1 + (n - 2), done);
     for (uint32_t i = n - 2; i > 0; i--) {
       lev = (1u - done) * (1u - isz(i - 1));
-      e.put_u32(li + i, lev);
+      if (side) e.put_u32(li + i, lev);
       levmask[i >> 5] |= lev << (i & 31);
       done = lev + done;
-      e.put_u32(li + 2 * n + 1 + (i - 1), done);
+      if (side) e.put_u32(li + 2 * n + 1 + (i - 1), done);
     }
     lev = 1u - done;
-    e.put_u32(li, lev);
+    if (side) e.put_u32(li, lev);
     levmask[0] |= lev;
   }
   // state machines sm[i] (is0 = 0, fnc = 0)
@@ -399,20 +429,22 @@ ZKB_HDN void smt_verifier(WitnessEnv &e, const VerifierLayout &V, const Fr &key_
       uint32_t ptl = p_top * lev;
       uint32_t st_top = p_top - ptl, st_inew = ptl, st_iold = 0, st_i0 = 0;
       uint32_t st_na = p_na + p_inew + p_iold + p_i0;
-      e.put_u32(s + 0, st_top); e.put_u32(s + 1, st_i0); e.put_u32(s + 2, st_iold); e.put_u32(s + 3, st_inew);
-      e.put_u32(s + 4, st_na); e.put_u32(s + 5, 0); e.put_u32(s + 6, lev); e.put_u32(s + 7, 0);
-      e.put_u32(s + 8, p_top); e.put_u32(s + 9, p_i0); e.put_u32(s + 10, p_iold); e.put_u32(s + 11, p_inew);
-      e.put_u32(s + 12, p_na); e.put_u32(s + 13, ptl); e.put_u32(s + 14, 0);
+      if (side) {
+        e.put_u32(s + 0, st_top); e.put_u32(s + 1, st_i0); e.put_u32(s + 2, st_iold); e.put_u32(s + 3, st_inew);
+        e.put_u32(s + 4, st_na); e.put_u32(s + 5, 0); e.put_u32(s + 6, lev); e.put_u32(s + 7, 0);
+        e.put_u32(s + 8, p_top); e.put_u32(s + 9, p_i0); e.put_u32(s + 10, p_iold); e.put_u32(s + 11, p_inew);
+        e.put_u32(s + 12, p_na); e.put_u32(s + 13, ptl); e.put_u32(s + 14, 0);
+        if (i == n - 1 && st_na + st_iold + st_inew + st_i0 != 1) e.fail();
+      }
       topmask[i >> 5] |= st_top << (i & 31);
       inewmask[i >> 5] |= st_inew << (i & 31);
       namask[i >> 5] |= (st_na & 1u) << (i & 31);
-      if (i == n - 1 && st_na + st_iold + st_inew + st_i0 != 1) e.fail();
       p_top = st_top; p_i0 = st_i0; p_iold = st_iold; p_inew = st_inew; p_na = st_na;
     }
   }
   // levels n-1 .. 0
   Fr child = Fr::zero();
-  for (int i = (int)n - 1; i >= 0; i--) {
+  for (int i = (int)n - 1; chain && i >= 0; i--) {
     const uint32_t s = V.levels + (uint32_t)i * e.L->level_size;
     const uint32_t st_top = (topmask[i >> 5] >> (i & 31)) & 1u, st_inew = (inewmask[i >> 5] >> (i & 31)) & 1u;
     const uint32_t st_na = (namask[i >> 5] >> (i & 31)) & 1u;
@@ -449,7 +481,7 @@ ZKB_HDN void smt_verifier(WitnessEnv &e, const VerifierLayout &V, const Fr &key_
     child = rt;
   }
   // areKeyEquals = IsEqual(oldKey = 0, key) {out,in[2]} + isz
-  {
+  if (side) {
     uint32_t s = V.areKeyEquals;
     e.put_u32(s + 1, 0);
     e.put_norm(s + 2, key_n);
@@ -466,7 +498,7 @@ ZKB_HDN void smt_verifier(WitnessEnv &e, const VerifierLayout &V, const Fr &key_
     e.put_u32(k + 17, z); e.put_u32(k + 18, z); e.put_u32(k + 19, 1);           //   and1
   }
   // checkRoot = ForceEqualIfEnabled(1, levels[0].root, root)
-  {
+  if (chain) {
     uint32_t s = V.checkRoot;
     e.put_u32(s, 1);
     e.put(s + 1, child);
@@ -515,18 +547,31 @@ ZKB_HDN void census_main_task(WitnessEnv &e, const Fr *in) {
   }
 }
 
-ZKB_HD void census_tree_task(WitnessEnv &e, int which, const Fr *in, const Fr &h00, const Fr &h001, bool skip_const) {
+// which: 0 = census tree, 1 = SIK tree; chain / side: see smt_verifier
+ZKB_HD void census_tree_task(WitnessEnv &e, int which, bool chain, bool side, const Fr *in, const Fr &h00,
+                             const Fr &h001, bool skip_const) {
   const CensusLayout &L = *e.L;
   const Fr &address = in[L.address - 1];
   if (which == 0) {
     smt_verifier(e, L.census, address, in[L.availableWeight - 1], in[L.censusRoot - 1], in + (L.censusSiblings - 1),
-                 h00, h001, skip_const);
+                 h00, h001, skip_const, chain, side);
   } else {
-    Fr hin[3] = {address.to_mont(), in[L.password - 1].to_mont(), in[L.signature - 1].to_mont()};
-    Fr sik = poseidon_comp<4>(e, L.sikHash, hin, true);
-    smt_verifier(e, L.sik, address, sik.from_mont(), in[L.sikRoot - 1], in + (L.sikSiblings - 1), h00, h001,
-                 skip_const);
+    Fr sik = Fr::zero();
+    if (chain) {
+      Fr hin[3] = {address.to_mont(), in[L.password - 1].to_mont(), in[L.signature - 1].to_mont()};
+      sik = poseidon_comp<4>(e, L.sikHash, hin, true).from_mont();
+    }
+    smt_verifier(e, L.sik, address, sik, in[L.sikRoot - 1], in + (L.sikSiblings - 1), h00, h001, skip_const, chain,
+                 side);
   }
+}
+
+// task ids of the batched kernel
+static constexpr int WITNESS_TASKS = 5;
+ZKB_HD void census_witness_task(WitnessEnv &e, int task, const Fr *in, const Fr &h00, const Fr &h001, bool skip_const) {
+  if (task == 2) census_main_task(e, in);
+  else if (task < 2) census_tree_task(e, task, true, false, in, h00, h001, skip_const);
+  else census_tree_task(e, task - 3, false, true, in, h00, h001, skip_const);
 }
 
 }  // namespace zkb

@@ -52,30 +52,34 @@ __global__ void k_consts_to_mont(Fr *c, const int *form, uint32_t n) {
 __global__ void k_hash_consts(CensusLayout L, const Fr *consts, Fr *hc) {
   if (threadIdx.x || blockIdx.x) return;
   WitnessEnv e;
-  e.L = &L; e.consts = consts; e.sig2wire = nullptr; e.out = nullptr; e.status = 0;
+  e.L = &L; e.consts = consts; e.stage = nullptr; e.status = 0;
   Fr z2[2] = {Fr::zero(), Fr::zero()};
   hc[0] = poseidon_ex<3>(e, 0, z2, false);
   Fr z3[3] = {Fr::zero(), Fr::zero(), Fr::one()};
   hc[1] = poseidon_ex<4>(e, 0, z3, false);
 }
 
-// thread = (proof, task).  inputs: [n][n_inputs] canonical; wtns: [n][n_wires]
-__global__ void __launch_bounds__(32) k_witness(CensusLayout L, const Fr *consts, const int32_t *sig2wire,
-                                                 const Fr *hc, const Fr *inputs, Fr *wtns, int *status, uint32_t n,
-                                                 int skip_const) {
+// thread = (proof, task): the census witness program (census_witness.cuh) writing this proof's staging array.
+// inputs: [n][n_inputs] canonical; stage: [n][n_signals], zeroed
+__global__ void __launch_bounds__(32) k_witness(CensusLayout L, const Fr *consts, const Fr *hc, const Fr *inputs,
+                                                 Fr *stage, int *status, uint32_t n, int skip_const) {
   uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   WitnessEnv e;
   e.L = &L;
   e.consts = consts;
-  e.sig2wire = sig2wire;
-  e.out = wtns + (size_t)p * L.n_wires;
+  e.stage = stage + (size_t)p * L.n_signals;
   e.status = 0;
-  const Fr *in = inputs + (size_t)p * L.n_inputs;
-  int task = blockIdx.y;
-  if (task == 2) census_main_task(e, in);
-  else census_tree_task(e, task, in, hc[0], hc[1], skip_const != 0);
+  census_witness_task(e, blockIdx.y, inputs + (size_t)p * L.n_inputs, hc[0], hc[1], skip_const != 0);
   if (e.status) atomicMax(status + p, e.status);
+}
+
+// thread = (wire, proof): wire value from its staged signal, or from the template when the signal was not produced
+__global__ void __launch_bounds__(256) k_witness_gather(const Fr *stage, size_t n_signals, const uint32_t *wmap,
+                                                        const Fr *tmpl, Fr *wtns, uint32_t n_wires) {
+  uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_wires) return;
+  wtns[(size_t)blockIdx.y * n_wires + w] = witness_gather_one(stage + (size_t)blockIdx.y * n_signals, wmap[w], tmpl, w);
 }
 
 // batched Poseidon hash with the circuit's constants: in [n][T-1] canonical -> out [n] canonical
@@ -84,16 +88,10 @@ __global__ void k_poseidon_batch(CensusLayout L, const Fr *consts, const Fr *in,
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   WitnessEnv e;
-  e.L = &L; e.consts = consts; e.sig2wire = nullptr; e.out = nullptr; e.status = 0;
+  e.L = &L; e.consts = consts; e.stage = nullptr; e.status = 0;
   Fr x[T - 1];
   for (int j = 0; j < T - 1; j++) x[j] = in[(size_t)i * (T - 1) + j].to_mont();
   out[i] = poseidon_ex<T>(e, 0, x, false).from_mont();
-}
-
-__global__ void k_fill_template(uint4 *dst, const uint4 *tmpl, size_t per_proof_u4, uint32_t n) {
-  size_t total = per_proof_u4 * n;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = tmpl[i % per_proof_u4];
 }
 
 __device__ __forceinline__ Fr ldg_fr8(const Fr *p);
@@ -168,7 +166,7 @@ static const char *INPUT_NAMES[12] = {"electionId", "nullifier", "voteHash", "si
 struct Lane {
   cudaStream_t st = nullptr;
   cudaEvent_t done = nullptr;
-  Fr *abc = nullptr, *hs = nullptr, *dw = nullptr;
+  Fr *abc = nullptr, *hs = nullptr, *dw = nullptr, *stage = nullptr;
   MsmSort sortW, sortH;
   MsmWork<Fq> work1, workH;
   MsmWork<Fq2> work2;
@@ -176,8 +174,8 @@ struct Lane {
   XYZZ<Fq2> *g2out = nullptr;
   XYZZ<Fq> *fin_scratch = nullptr;
   void free_all() {
-    cudaFree(abc); cudaFree(hs); cudaFree(dw); cudaFree(g1out); cudaFree(g2out); cudaFree(fin_scratch);
-    abc = hs = dw = nullptr; g1out = fin_scratch = nullptr; g2out = nullptr;
+    cudaFree(abc); cudaFree(hs); cudaFree(dw); cudaFree(g1out); cudaFree(g2out); cudaFree(fin_scratch); cudaFree(stage);
+    abc = hs = dw = stage = nullptr; g1out = fin_scratch = nullptr; g2out = nullptr;
     if (sortW.counts) sortW.free_all();
     if (sortH.counts) sortH.free_all();
     if (work1.buckets) work1.free_all();
@@ -194,7 +192,7 @@ struct Circuit {
   uint32_t in_pos[12], in_size[12];
   // device constants
   Fr *consts = nullptr, *hc = nullptr, *tmpl = nullptr;
-  int32_t *sig2wire = nullptr;
+  uint32_t *wmap = nullptr;        // wire -> circom signal (the wasm's witness table)
   uint32_t *csr_buf = nullptr;
   Fr *csr_val = nullptr;
   CsrDev csrA, csrB;
@@ -285,6 +283,7 @@ static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
     CKR(cudaMalloc(&ln.abc, (size_t)chunk * 3 * c->domain * 32), "alloc abc");
     CKR(cudaMalloc(&ln.hs, (size_t)chunk * c->domain * 32), "alloc h");
     CKR(cudaMalloc(&ln.dw, (size_t)chunk * c->n_vars * 32), "alloc witness diff");
+    if (c->consts) CKR(cudaMalloc(&ln.stage, (size_t)chunk * c->L.n_signals * 32), "alloc witness staging");
     CKR(cudaMalloc(&ln.g1out, (size_t)chunk * 4 * sizeof(XYZZ<Fq>)), "alloc g1out");
     CKR(cudaMalloc(&ln.g2out, (size_t)chunk * sizeof(XYZZ<Fq2>)), "alloc g2out");
     CKR(cudaMalloc(&ln.fin_scratch, (size_t)chunk * 30 * sizeof(XYZZ<Fq>)), "alloc finalize scratch");
@@ -297,15 +296,15 @@ static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
   return ZKB_OK;
 }
 
-// witness for proofs [first, first + n) of c->inputs
-static int run_witness(Circuit *c, uint32_t first, uint32_t n, cudaStream_t st) {
+// witness for proofs [first, first + n) of c->inputs, n <= chunk, staged in lane ln
+static int run_witness(Circuit *c, Lane &ln, uint32_t first, uint32_t n, cudaStream_t st) {
   CKR(cudaMemsetAsync(c->status + first, 0, (size_t)n * 4, st), "memset status");
-  size_t per = (size_t)c->n_vars * 2;   // uint4 per proof
-  Fr *w = c->wtns + (size_t)first * c->n_vars;
-  k_fill_template<<<1184, 256, 0, st>>>(reinterpret_cast<uint4 *>(w), reinterpret_cast<const uint4 *>(c->tmpl), per, n);
-  dim3 grid((n + 31) / 32, 3);
-  k_witness<<<grid, 32, 0, st>>>(c->L, c->consts, c->sig2wire, c->hc, c->inputs + (size_t)first * c->L.n_inputs, w,
-                                 c->status + first, n, 1);
+  CKR(cudaMemsetAsync(ln.stage, 0, (size_t)n * c->L.n_signals * 32, st), "memset staging");
+  k_witness<<<dim3((n + 31) / 32, WITNESS_TASKS), 32, 0, st>>>(c->L, c->consts, c->hc,
+                                                               c->inputs + (size_t)first * c->L.n_inputs, ln.stage,
+                                                               c->status + first, n, 1);
+  k_witness_gather<<<dim3((c->n_vars + 255) / 256, n), 256, 0, st>>>(ln.stage, c->L.n_signals, c->wmap, c->tmpl,
+                                                                     c->wtns + (size_t)first * c->n_vars, c->n_vars);
   g_launches += 2;
   return cudaGetLastError() == cudaSuccess ? ZKB_OK : cuda_fail(cudaGetLastError(), "witness launch");
 }
@@ -313,7 +312,7 @@ static int run_witness(Circuit *c, uint32_t first, uint32_t n, cudaStream_t st) 
 // witness (optional) + Groth16 for proofs [first, first + m), m <= chunk, on lane ln
 static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, bool with_witness, cudaEvent_t *ev) {
   cudaStream_t st = ln.st;
-  if (with_witness) { int rc = run_witness(c, first, m, st); if (rc) return rc; }
+  if (with_witness) { int rc = run_witness(c, ln, first, m, st); if (rc) return rc; }
   if (ev) cudaEventRecord(ev[1], st);
   const Fr *w = c->wtns + (size_t)first * c->n_vars;
   dim3 g1((c->domain + 127) / 128, m);
@@ -496,22 +495,24 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
     CKR(upload(&c->consts, cbuf.data(), cbuf.size() * 4), "upload poseidon constants");
     CKR(upload(&dforms, forms.data(), forms.size() * 4), "upload forms");
     k_consts_to_mont<<<(off + 127) / 128, 128, 0, st>>>(c->consts, dforms, off);
-    std::vector<int32_t> s2w(c->L.n_signals, -1);
-    for (uint32_t i = 0; i < w.n_wires; i++) s2w[w.witness_map[i]] = (int32_t)i;
-    CKR(upload(&c->sig2wire, s2w.data(), s2w.size() * 4), "upload sig2wire");
+    CKR(upload(&c->wmap, w.witness_map.data(), w.witness_map.size() * 4), "upload witness map");
     CKR(cudaMalloc(&c->hc, 64), "alloc hc");
     k_hash_consts<<<1, 1, 0, st>>>(c->L, c->consts, c->hc);
     // template witness: the program itself on all-zero inputs, constant blocks included
     CKR(cudaMalloc(&c->tmpl, (size_t)c->n_vars * 32), "alloc template");
-    CKR(cudaMemsetAsync(c->tmpl, 0, (size_t)c->n_vars * 32, st), "memset");
-    Fr *zin = nullptr;
+    Fr *zin = nullptr, *zstage = nullptr;
     int *zst = nullptr;
     CKR(cudaMalloc(&zin, (size_t)c->L.n_inputs * 32), "alloc");
+    CKR(cudaMalloc(&zstage, (size_t)c->L.n_signals * 32), "alloc");
     CKR(cudaMalloc(&zst, 4), "alloc");
     CKR(cudaMemsetAsync(zin, 0, (size_t)c->L.n_inputs * 32, st), "memset");
+    CKR(cudaMemsetAsync(zstage, 0, (size_t)c->L.n_signals * 32, st), "memset");
     CKR(cudaMemsetAsync(zst, 0, 4, st), "memset");
-    k_witness<<<dim3(1, 3), 32, 0, st>>>(c->L, c->consts, c->sig2wire, c->hc, zin, c->tmpl, zst, 1, 0);
+    k_witness<<<dim3(1, WITNESS_TASKS), 32, 0, st>>>(c->L, c->consts, c->hc, zin, zstage, zst, 1, 0);
+    k_witness_gather<<<dim3((c->n_vars + 255) / 256, 1), 256, 0, st>>>(zstage, c->L.n_signals, c->wmap, nullptr, c->tmpl,
+                                                                       c->n_vars);
     CKR(cudaStreamSynchronize(st), "witness template");
+    cudaFree(zstage);
     cudaFree(zin); cudaFree(zst); cudaFree(dforms);
   }
 
@@ -603,7 +604,7 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
 static void destroy_circuit(Circuit *c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
-  cudaFree(c->consts); cudaFree(c->hc); cudaFree(c->tmpl); cudaFree(c->sig2wire); cudaFree(c->csr_buf);
+  cudaFree(c->consts); cudaFree(c->hc); cudaFree(c->tmpl); cudaFree(c->wmap); cudaFree(c->csr_buf);
   cudaFree(c->csr_val); cudaFree(c->fix1); cudaFree(c->fix2); cudaFree(c->d1tab); cudaFree(c->d2tab);
   cudaFree(c->tconst1); cudaFree(c->tconst2);
   cudaFree(c->tabA.tab); cudaFree(c->tabB1.tab); cudaFree(c->tabC.tab); cudaFree(c->tabH.tab); cudaFree(c->tabB2.tab);
@@ -946,7 +947,7 @@ int zkb_witness(zkb_circuit *h, const char *inputs_json, size_t inputs_len, void
   if (pack_inputs(c, inputs_json, inputs_len, c->h_inputs[0].v, err)) { set_error(err); return ZKB_ERROR; }
   cudaStream_t st = c->ctx->stream;
   CKR(cudaMemcpyAsync(c->inputs, c->h_inputs, (size_t)c->L.n_inputs * 32, cudaMemcpyHostToDevice, st), "h2d");
-  if ((rc = run_witness(c, 0, 1, st))) return rc;
+  if ((rc = run_witness(c, c->lanes[0], 0, 1, st))) return rc;
   uint8_t *o = (uint8_t *)wtns_out;
   static const uint32_t RMOD[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
                                    0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
