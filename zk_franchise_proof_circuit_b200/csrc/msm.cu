@@ -185,6 +185,10 @@ __global__ void __launch_bounds__(1024) k_order(const uint32_t *counts, uint32_t
   }
 }
 
+// kernels one MsmSort::run launches.  (A single-CTA-per-item variant with the 2^(c-1) counters in shared memory was
+// tried: on B200 the 2 x 2.1 M shared-memory atomics per H sort made it 2x slower than these L2-atomic passes.)
+int msm_sort_launches() { return 4; }
+
 cudaError_t MsmSort::alloc(uint32_t n_, uint32_t batch_, MsmCfg cfg_) {
   n = n_;
   batch = batch_;

@@ -47,6 +47,8 @@ struct MsmSort {
   cudaError_t run(const Fr *scalars, size_t scalar_stride, uint32_t nbatch, cudaStream_t st);
 };
 
+int msm_sort_launches();   // kernels one MsmSort::run launches
+
 // workspace for bucket sums + reduction of `slots` simultaneous (batch item, table) pairs
 template <class F>
 struct MsmWork {

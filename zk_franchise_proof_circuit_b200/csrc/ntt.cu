@@ -132,10 +132,15 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr *data, size_t vec_s
       int k = ((kk >> sb) << (sb + 1)) | (kk & (d - 1));
       int i0 = col ? (k * G + g) : (g * rows + k);
       int i1 = i0 + d * stride;
+      Fr u = lds_fr(sm, i0), v = lds_fr(sm, i1);
+      if (s == 0) {                                   // half distance 1: every twiddle is omega^0 = 1 (block-uniform)
+        sts_fr(sm, i0, u + v);
+        sts_fr(sm, i1, u - v);
+        continue;
+      }
       size_t j = ((size_t)(k & (d - 1)) << lo) + (col ? (low0 + g) : 0);
       size_t e = j << (logn - 1 - s);
       Fr w = ldg_fr(tw + e);
-      Fr u = lds_fr(sm, i0), v = lds_fr(sm, i1);
       if (DIF) {
         sts_fr(sm, i0, u + v);
         sts_fr(sm, i1, (u - v) * w);
