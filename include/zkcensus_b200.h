@@ -138,6 +138,30 @@ int zkb_raw_msm_g1(const void *bases, size_t n, const void *scalars, int nbatch,
 int zkb_raw_msm_g2(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
                    float *table_ms);
 
+
+/* --- device-resident raw sessions: large MSM split by point range, across GPUs (BASELINE.json configs 4-5) -------
+ * The reference has no multi-GPU code; this is the "single large-circuit MSM split by point range with per-GPU
+ * partial sums combined via P2P copy over NVLink" of BASELINE.json's north_star.  One process per GPU: every rank
+ * creates a session for its point range (synthetic bases by try-and-increment hash-to-curve and scalars are generated
+ * on the device, the window table is built once), rank 0 exports the CUDA IPC handle of its exchange buffer, the
+ * other ranks attach to it, then each step every rank calls run() (asynchronous; its last kernel writes the rank's
+ * partial sum into rank 0's memory and releases a flag) and rank 0 calls combine(). */
+typedef struct zkb_msm_session zkb_msm_session;
+int zkb_msm_session_create(int device, int logn, int rank, int nranks, uint64_t seed, int window_bits,
+                           zkb_msm_session **out);
+void zkb_msm_session_destroy(zkb_msm_session *s);
+/* info[6] = points of this rank, sub-MSM size, sub-MSMs, window bits, table build us, data generation us */
+int zkb_msm_session_info(zkb_msm_session *s, uint64_t *info);
+int zkb_msm_session_export(zkb_msm_session *s, void *handle64);
+int zkb_msm_session_attach(zkb_msm_session *s, const void *handle64);
+int zkb_msm_session_attach_local(zkb_msm_session *s, zkb_msm_session *root); /* same process, another GPU or the same */
+int zkb_msm_session_run(zkb_msm_session *s, float *ms);
+int zkb_msm_session_combine(zkb_msm_session *s, int nslots, void *out64, float *ms);
+int zkb_msm_session_madds(zkb_msm_session *s, uint64_t *madds);
+int zkb_msm_session_read(zkb_msm_session *s, void *bases_out, void *scalars_out);
+/* resident NTT timing: ms per inverse (DIF + coset scale) and per forward (DIT) transform of nvec x 2^logn values */
+int zkb_ntt_bench(int device, int logn, int nvec, int iters, float *dif_ms, float *dit_ms);
+
 #ifdef __cplusplus
 }
 #endif

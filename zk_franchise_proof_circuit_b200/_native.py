@@ -32,6 +32,19 @@ def lib():
         L.zkb_raw_coset_ntt.argtypes = [vp, i32, i32]
         L.zkb_raw_msm_g1.argtypes = [vp, sz, vp, i32, vp, fp, fp]
         L.zkb_raw_msm_g2.argtypes = [vp, sz, vp, i32, vp, fp, fp]
+        u64p, pp = ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_void_p)
+        L.zkb_msm_session_create.argtypes = [i32, i32, i32, i32, ctypes.c_uint64, i32, pp]
+        L.zkb_msm_session_destroy.argtypes = [vp]
+        L.zkb_msm_session_destroy.restype = None
+        L.zkb_msm_session_info.argtypes = [vp, u64p]
+        L.zkb_msm_session_export.argtypes = [vp, vp]
+        L.zkb_msm_session_attach.argtypes = [vp, vp]
+        L.zkb_msm_session_attach_local.argtypes = [vp, vp]
+        L.zkb_msm_session_run.argtypes = [vp, fp]
+        L.zkb_msm_session_combine.argtypes = [vp, i32, vp, fp]
+        L.zkb_msm_session_madds.argtypes = [vp, u64p]
+        L.zkb_msm_session_read.argtypes = [vp, vp, vp]
+        L.zkb_ntt_bench.argtypes = [i32, i32, i32, i32, fp, fp]
         _lib = L
     return _lib
 

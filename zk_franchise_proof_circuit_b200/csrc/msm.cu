@@ -44,6 +44,8 @@ template <class F>
 __global__ void k_table(Affine<F> *tab, const Affine<F> *bases, uint32_t n, int c, int windows) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
+  tab += (size_t)blockIdx.y * windows * n;      // sub-range blockIdx.y: its own [windows][n] block
+  bases += (size_t)blockIdx.y * n;
   Affine<F> p = ldg_pod(bases + k);
   XYZZ<F> acc = XYZZ<F>::from_affine(p);
   for (int j = 0; j < windows; j++) {
@@ -56,15 +58,16 @@ __global__ void k_table(Affine<F> *tab, const Affine<F> *bases, uint32_t n, int 
 }
 
 template <class F>
-cudaError_t msm_build_table(MsmTable<F> &t, const Affine<F> *bases, uint32_t n, MsmCfg cfg, cudaStream_t st) {
+cudaError_t msm_build_table(MsmTable<F> &t, const Affine<F> *bases, uint32_t n, MsmCfg cfg, cudaStream_t st,
+                            uint32_t subs) {
   t.n = n;
   t.cfg = cfg;
-  CK(cudaMalloc(&t.tab, (size_t)n * cfg.windows * sizeof(Affine<F>)));
-  k_table<F><<<(n + 63) / 64, 64, 0, st>>>(t.tab, bases, n, cfg.c, cfg.windows);
+  CK(cudaMalloc(&t.tab, (size_t)subs * n * cfg.windows * sizeof(Affine<F>)));
+  k_table<F><<<dim3((n + 63) / 64, subs), 64, 0, st>>>(t.tab, bases, n, cfg.c, cfg.windows);
   return cudaGetLastError();
 }
-template cudaError_t msm_build_table<Fq>(MsmTable<Fq> &, const Affine<Fq> *, uint32_t, MsmCfg, cudaStream_t);
-template cudaError_t msm_build_table<Fq2>(MsmTable<Fq2> &, const Affine<Fq2> *, uint32_t, MsmCfg, cudaStream_t);
+template cudaError_t msm_build_table<Fq>(MsmTable<Fq> &, const Affine<Fq> *, uint32_t, MsmCfg, cudaStream_t, uint32_t);
+template cudaError_t msm_build_table<Fq2>(MsmTable<Fq2> &, const Affine<Fq2> *, uint32_t, MsmCfg, cudaStream_t, uint32_t);
 
 // ---------------------------------------------------------------------------------------------
 // digits + counting sort
@@ -237,13 +240,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_accumulate(TablePtrs<F> tabs,
                                                         uint32_t nbuckets, const uint32_t *__restrict__ offsets,
                                                         const uint32_t *__restrict__ entries,
                                                         const uint32_t *__restrict__ order,
-                                                        const uint32_t *__restrict__ n_long, XYZZ<F> *buckets) {
+                                                        const uint32_t *__restrict__ n_long, XYZZ<F> *buckets,
+                                                        size_t tab_batch_stride) {
   uint32_t t = blockIdx.y, b = blockIdx.z;
   const uint32_t pos = blockIdx.x * THREADS + threadIdx.x;
   if ((pos | 31u) < n_long[b]) return;     // this whole warp's buckets belong to k_accumulate_long
   const bool mine = pos >= n_long[b];
   const uint32_t bucket = order[(size_t)b * nbuckets + pos];
-  const Affine<F> *tab = t == 0 ? tabs.tab[0] : (t == 1 ? tabs.tab[1] : (t == 2 ? tabs.tab[2] : tabs.tab[3]));
+  const Affine<F> *tab = (t == 0 ? tabs.tab[0] : (t == 1 ? tabs.tab[1] : (t == 2 ? tabs.tab[2] : tabs.tab[3]))) +
+                         (size_t)b * tab_batch_stride;
   const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
   const uint32_t *ent = entries + (size_t)b * n * windows;
   const uint32_t beg = off[bucket], len = mine ? off[bucket + 1] - beg : 0u;
@@ -290,10 +295,12 @@ __global__ void __launch_bounds__(32) k_accumulate_long(TablePtrs<F> tabs, int n
                                                         uint32_t nbuckets, const uint32_t *__restrict__ offsets,
                                                         const uint32_t *__restrict__ entries,
                                                         const uint32_t *__restrict__ order,
-                                                        const uint32_t *__restrict__ n_long, XYZZ<F> *buckets) {
+                                                        const uint32_t *__restrict__ n_long, XYZZ<F> *buckets,
+                                                        size_t tab_batch_stride) {
   const uint32_t t = blockIdx.y, b = blockIdx.z, lane = threadIdx.x;
   if (blockIdx.x >= n_long[b]) return;
-  const Affine<F> *tab = t == 0 ? tabs.tab[0] : (t == 1 ? tabs.tab[1] : (t == 2 ? tabs.tab[2] : tabs.tab[3]));
+  const Affine<F> *tab = (t == 0 ? tabs.tab[0] : (t == 1 ? tabs.tab[1] : (t == 2 ? tabs.tab[2] : tabs.tab[3]))) +
+                         (size_t)b * tab_batch_stride;
   const uint32_t bucket = order[(size_t)b * nbuckets + blockIdx.x];
   const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
   const uint32_t *ent = entries + (size_t)b * n * windows;
@@ -440,7 +447,7 @@ template <> struct AccCfg<Fq2> { static constexpr int THREADS = 64; static const
 
 template <class F>
 cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
-                           uint32_t slot0, cudaStream_t st) {
+                           uint32_t slot0, cudaStream_t st, size_t tab_batch_stride) {
   if (ntab < 1 || ntab > 4 || slot0 + nbatch * (uint32_t)ntab > work.slots) return cudaErrorInvalidValue;
   TablePtrs<F> tp;
   for (int i = 0; i < 4; i++) tp.tab[i] = i < ntab ? tables[i].tab : nullptr;
@@ -452,7 +459,7 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
   dim3 grid(nb / TH, ntab, nbatch);
   XYZZ<F> *dst = work.buckets + (size_t)slot0 * nb;
   static const int variant = getenv("ZKB_ACC_VARIANT") ? atoi(getenv("ZKB_ACC_VARIANT")) : 0;
-#define ZKB_ACC(MINB, INL) k_accumulate<F, TH, MINB, INL><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order, sort.n_long, dst)
+#define ZKB_ACC(MINB, INL) k_accumulate<F, TH, MINB, INL><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order, sort.n_long, dst, tab_batch_stride)
   if constexpr (sizeof(F) == 32) {
     switch (variant) {
       case 1: ZKB_ACC(4, false); break;
@@ -472,7 +479,7 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
 #undef ZKB_ACC
   dim3 glong(MAX_LONG, ntab, nbatch);
   k_accumulate_long<F><<<glong, 32, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order,
-                                             sort.n_long, dst);
+                                             sort.n_long, dst, tab_batch_stride);
   return cudaGetLastError();
 }
 
@@ -499,7 +506,7 @@ cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F
 template <class F>
 cudaError_t msm_run(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
                     XYZZ<F> *out, cudaStream_t st) {
-  cudaError_t e = msm_accumulate<F>(sort, tables, ntab, nbatch, work, 0, st);
+  cudaError_t e = msm_accumulate<F>(sort, tables, ntab, nbatch, work, 0, st, 0);
   if (e != cudaSuccess) return e;
   return msm_reduce<F>(work, 0, nbatch * (uint32_t)ntab, out, st);
 }
@@ -541,8 +548,8 @@ cudaError_t msm_count_madds(const MsmSort &sort, const MsmTable<F> &table, uint3
 }
 template cudaError_t msm_count_madds<Fq>(const MsmSort &, const MsmTable<Fq> &, uint32_t, unsigned long long *, cudaStream_t);
 template cudaError_t msm_count_madds<Fq2>(const MsmSort &, const MsmTable<Fq2> &, uint32_t, unsigned long long *, cudaStream_t);
-template cudaError_t msm_accumulate<Fq>(const MsmSort &, const MsmTable<Fq> *, int, uint32_t, MsmWork<Fq> &, uint32_t, cudaStream_t);
-template cudaError_t msm_accumulate<Fq2>(const MsmSort &, const MsmTable<Fq2> *, int, uint32_t, MsmWork<Fq2> &, uint32_t, cudaStream_t);
+template cudaError_t msm_accumulate<Fq>(const MsmSort &, const MsmTable<Fq> *, int, uint32_t, MsmWork<Fq> &, uint32_t, cudaStream_t, size_t);
+template cudaError_t msm_accumulate<Fq2>(const MsmSort &, const MsmTable<Fq2> *, int, uint32_t, MsmWork<Fq2> &, uint32_t, cudaStream_t, size_t);
 template cudaError_t msm_reduce<Fq>(MsmWork<Fq> &, uint32_t, uint32_t, XYZZ<Fq> *, cudaStream_t);
 template cudaError_t msm_reduce<Fq2>(MsmWork<Fq2> &, uint32_t, uint32_t, XYZZ<Fq2> *, cudaStream_t);
 template cudaError_t msm_run<Fq>(const MsmSort &, const MsmTable<Fq> *, int, uint32_t, MsmWork<Fq> &, XYZZ<Fq> *,

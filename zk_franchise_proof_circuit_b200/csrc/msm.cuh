@@ -61,14 +61,18 @@ struct MsmWork {
   void free_all();
 };
 
-// build the window table from n affine bases (Montgomery form, zkey layout; (0,0) = infinity)
+// build the window table from n affine bases (Montgomery form, zkey layout; (0,0) = infinity).  subs > 1: `bases`
+// holds subs consecutive ranges of n points and the table is subs consecutive [windows][n] blocks (a large MSM split
+// by point range into sub-MSMs that run as batch items, see tab_batch_stride below).
 template <class F>
-cudaError_t msm_build_table(MsmTable<F> &t, const Affine<F> *bases, uint32_t n, MsmCfg cfg, cudaStream_t st);
+cudaError_t msm_build_table(MsmTable<F> &t, const Affine<F> *bases, uint32_t n, MsmCfg cfg, cudaStream_t st,
+                            uint32_t subs = 1);
 
 // bucket sums of (batch item b, table t) -> work.buckets[slot0 + b*ntab + t].  Tables, sort and work must share cfg.
 template <class F>
+// tab_batch_stride: batch item b reads its bases at table + b * tab_batch_stride (0: every item shares the table).
 cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
-                           uint32_t slot0, cudaStream_t st);
+                           uint32_t slot0, cudaStream_t st, size_t tab_batch_stride = 0);
 // out[i] = sum_b (b+1) * buckets[slot0 + i][b], i < nslots
 template <class F>
 cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F> *out, cudaStream_t st);

@@ -65,3 +65,69 @@ def msm_g1(bases, scalars, timing=False):
 
 def msm_g2(bases, scalars, timing=False):
     return _msm(_native.lib().zkb_raw_msm_g2, 128, bases, scalars, timing)
+
+
+class MsmSession:
+    """One rank's share of a 2^logn-point synthetic G1 MSM split by point range (include/zkcensus_b200.h,
+    zkb_msm_session_*).  Ranks > 0 push their partial sum into rank 0's exchange buffer over NVLink; rank 0 combines."""
+
+    def __init__(self, logn, rank=0, nranks=1, device=0, seed=1, window=16):
+        self.h = ctypes.c_void_p()
+        self.rank, self.nranks = rank, nranks
+        _native.check(_native.lib().zkb_msm_session_create(device, logn, rank, nranks, seed, window, ctypes.byref(self.h)))
+        info = (ctypes.c_uint64 * 6)()
+        _native.check(_native.lib().zkb_msm_session_info(self.h, info))
+        self.points, self.sub_size, self.subs, self.window = int(info[0]), int(info[1]), int(info[2]), int(info[3])
+        self.table_ms, self.gen_ms = info[4] / 1e3, info[5] / 1e3
+
+    def export_handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        _native.check(_native.lib().zkb_msm_session_export(self.h, buf))
+        return buf.raw
+
+    def attach(self, handle: bytes):
+        _native.check(_native.lib().zkb_msm_session_attach(self.h, ctypes.create_string_buffer(handle, 64)))
+
+    def attach_local(self, root: "MsmSession"):
+        _native.check(_native.lib().zkb_msm_session_attach_local(self.h, root.h))
+
+    def run(self, wait=False):
+        ms = ctypes.c_float()
+        _native.check(_native.lib().zkb_msm_session_run(self.h, ctypes.byref(ms) if wait else None))
+        return ms.value if wait else None
+
+    def combine(self, nslots=None):
+        """rank 0: (affine canonical point bytes, device ms from the start of this rank's run())."""
+        out = ctypes.create_string_buffer(64)
+        ms = ctypes.c_float()
+        _native.check(_native.lib().zkb_msm_session_combine(self.h, nslots or self.nranks, out, ctypes.byref(ms)))
+        return out.raw, ms.value
+
+    def madds(self) -> int:
+        v = ctypes.c_uint64()
+        _native.check(_native.lib().zkb_msm_session_madds(self.h, ctypes.byref(v)))
+        return int(v.value)
+
+    def read(self):
+        b = np.zeros((self.points, 64), dtype=np.uint8)
+        s = np.zeros((self.points, 32), dtype=np.uint8)
+        _native.check(_native.lib().zkb_msm_session_read(self.h, b.ctypes.data, s.ctypes.data))
+        return b, s
+
+    def close(self):
+        if self.h:
+            _native.lib().zkb_msm_session_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ntt_bench(logn, nvec=1, iters=5, device=0):
+    """(ms per inverse DIF transform incl. coset scale, ms per forward DIT transform), data resident."""
+    a, b = ctypes.c_float(), ctypes.c_float()
+    _native.check(_native.lib().zkb_ntt_bench(device, logn, nvec, iters, ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
