@@ -159,6 +159,23 @@ int zkb_msm_session_run(zkb_msm_session *s, float *ms);
 int zkb_msm_session_combine(zkb_msm_session *s, int nslots, void *out64, float *ms);
 int zkb_msm_session_madds(zkb_msm_session *s, uint64_t *madds);
 int zkb_msm_session_read(zkb_msm_session *s, void *bases_out, void *scalars_out);
+/* 4-step NTT of 2^logn (>= 2^24) values over nranks GPUs, one session per rank: rank g owns N2/G columns of the
+ * N1 x N2 input, runs the length-N1 column transforms, then READS its N1/G positions of every rank's columns through
+ * CUDA IPC mappings (the all-to-all transpose and the omega_N^(n2 k1) twiddles are fused into that load), then runs
+ * the length-N2 row transforms.  Output rows, concatenated over ranks, are the transform in bit-reversed order
+ * (exactly what the single-GPU decimation-in-frequency plan produces).  Between two transforms the caller places a
+ * host barrier (the column buffers are reused). */
+typedef struct zkb_ntt_dist zkb_ntt_dist;
+int zkb_ntt_dist_create(int device, int logn, int rank, int nranks, uint64_t seed, zkb_ntt_dist **out);
+void zkb_ntt_dist_destroy(zkb_ntt_dist *s);
+int zkb_ntt_dist_export(zkb_ntt_dist *s, void *handle64);
+int zkb_ntt_dist_attach(zkb_ntt_dist *s, int peer_rank, const void *handle64);
+int zkb_ntt_dist_attach_local(zkb_ntt_dist *s, int peer_rank, zkb_ntt_dist *peer);
+int zkb_ntt_dist_fill(zkb_ntt_dist *s);
+int zkb_ntt_dist_run(zkb_ntt_dist *s);
+int zkb_ntt_dist_sync(zkb_ntt_dist *s, float *ms4); /* total, columns, wait + exchange, rows */
+int zkb_ntt_dist_read(zkb_ntt_dist *s, int which, void *out);
+int zkb_raw_ntt_dif_forward(void *data, int logn); /* single GPU, natural in, bit-reversed out (parity aid) */
 /* resident NTT timing: ms per inverse (DIF + coset scale) and per forward (DIT) transform of nvec x 2^logn values */
 int zkb_ntt_bench(int device, int logn, int nvec, int iters, float *dif_ms, float *dit_ms);
 

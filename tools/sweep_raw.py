@@ -27,6 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--msm", default="16,18,20,22,24")
     ap.add_argument("--ntt", default="16,18,20,22,24")
+    ap.add_argument("--ntt-dist", default="", help="sizes (log2, >= 24) for the 4-step NTT split over all ranks")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -110,6 +111,35 @@ def main():
               "algorithmic_gbs_per_gpu": 2 * 32 * n / per / 1e9,
               "frac_of_hbm_peak": (2 * 32 * n / per / 1e9) / peaks.get("hbm_gbs", 6464.6),
               "scaling": "weak (independent vectors per GPU)"})
+    for logn in [int(x) for x in args.ntt_dist.split(",") if x]:
+        s = raw.NttDist(logn, rank, world, device=local)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, s.export_handle())
+            for g in range(world):
+                if g != rank:
+                    s.attach(g, handles[g])
+        rows = []
+        for it in range(args.steps + 1):
+            s.fill()
+            barrier()
+            s.run()
+            ms = s.sync()
+            barrier()
+            if it:
+                rows.append([reduce_max(x) for x in ms])
+        rows.sort()
+        tot, colms, exms, rowms = rows[len(rows) // 2]
+        n = 1 << logn
+        mm = n / 2 * logn + 2 * n                      # butterflies + 2 modmul per element for the fused twiddle
+        emit({"kind": "ntt_fr_4step", "logn": logn, "n_gpus": world, "ms": tot, "columns_ms": colms,
+              "wait_plus_p2p_exchange_ms": exms, "rows_ms": rowms, "gmodmul_per_s": mm / (tot * 1e-3) / 1e9,
+              "frac_of_imad_peak": mm / (tot * 1e-3) / (peak * world),
+              "exchange_bytes_per_gpu": (n // world) * 32 * (world - 1) // world,
+              "exchange": "fused into the transposing load of the row pass: P2P reads of peer buffers (CUDA IPC), "
+                          "no NCCL" if world > 1 else "local transpose", "scaling": "strong"})
+        s.close()
+        barrier()
     if rank == 0 and args.out:
         with open(os.path.join(ROOT, args.out), "w") as f:
             for d in lines:

@@ -45,6 +45,17 @@ def lib():
         L.zkb_msm_session_madds.argtypes = [vp, u64p]
         L.zkb_msm_session_read.argtypes = [vp, vp, vp]
         L.zkb_ntt_bench.argtypes = [i32, i32, i32, i32, fp, fp]
+        L.zkb_ntt_dist_create.argtypes = [i32, i32, i32, i32, ctypes.c_uint64, pp]
+        L.zkb_ntt_dist_destroy.argtypes = [vp]
+        L.zkb_ntt_dist_destroy.restype = None
+        L.zkb_ntt_dist_export.argtypes = [vp, vp]
+        L.zkb_ntt_dist_attach.argtypes = [vp, i32, vp]
+        L.zkb_ntt_dist_attach_local.argtypes = [vp, i32, vp]
+        L.zkb_ntt_dist_fill.argtypes = [vp]
+        L.zkb_ntt_dist_run.argtypes = [vp]
+        L.zkb_ntt_dist_sync.argtypes = [vp, fp]
+        L.zkb_ntt_dist_read.argtypes = [vp, i32, vp]
+        L.zkb_raw_ntt_dif_forward.argtypes = [vp, i32]
         _lib = L
     return _lib
 

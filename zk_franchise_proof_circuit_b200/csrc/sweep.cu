@@ -169,6 +169,117 @@ struct MsmSession {
   float table_ms = 0, gen_ms = 0;
 };
 
+
+// ---- 4-step NTT across GPUs ----------------------------------------------------------------------------
+// N = N1 * N2, x[n1 * N2 + n2].  Rank g owns the columns n2 in [g N2/G, (g+1) N2/G), each stored contiguously:
+// B_g[c][n1].  (1) forward DIF of length N1 on every column: B_g[c][p] = Y[n2][k1 = bitrev(p)].  (2) release flag.
+// (3) rank g' takes positions p in [g' N1/G, (g'+1) N1/G) of EVERY rank's B (32 x 32 tiles read through the IPC
+// mappings, multiplied by omega_N^(n2 k1), written transposed): C_g'[p_local][n2].  (4) forward DIF of length N2 on
+// every row: C_g'[p_local][q] = X[bitrev_N1(p) + N1 * bitrev_N2(q)].
+struct NttCtl { uint32_t ready; uint32_t pad[63]; };   // head of the exported allocation (256 B), then B
+
+__global__ void k_set_flag(uint32_t *flag, uint32_t epoch) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+struct PeerPtrs { const uint8_t *base[MAX_RANKS]; };
+__global__ void k_wait_flags(PeerPtrs peers, int n, uint32_t epoch, int *status) {
+  if (threadIdx.x || blockIdx.x) return;
+  const long long t0 = clock64();
+  for (int g = 0; g < n; g++) {
+    const uint32_t *flag = &reinterpret_cast<const NttCtl *>(peers.base[g])->ready;
+    uint32_t f;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory");
+      if (f != epoch && clock64() - t0 > SPIN_LIMIT_CYCLES) { *status = 1 + g; return; }
+    } while (f != epoch);
+  }
+}
+
+__device__ __forceinline__ Fr ld_fr_volatile(const Fr *p) {   // peer data: bypass L1 (no stale lines across epochs)
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = __ldcg(q), b = __ldcg(q + 1);
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// grid (N2 / 32, (N1/G) / 32); block 32 x 8.  tile: 32 columns n2 x 32 positions p.
+__global__ void __launch_bounds__(256) k_gather_transpose(PeerPtrs peers, Fr *C, int l1, int l2, uint32_t cols_per_rank,
+                                                          uint32_t p0, const Fr *__restrict__ tw_lo,
+                                                          const Fr *__restrict__ tw_hi, int status_ok_only,
+                                                          const int *status) {
+  __shared__ uint32_t tile[8][32][33];   // limb-planar, padded
+  if (status_ok_only && *status) return;
+  const uint32_t N1 = 1u << l1, N2 = 1u << l2;
+  const uint32_t n2_0 = blockIdx.x * 32, pl_0 = blockIdx.y * 32;
+  const uint32_t tx = threadIdx.x, ty = threadIdx.y;
+  const uint64_t nmask = ((uint64_t)N1 << l2) - 1;
+  for (uint32_t r = ty; r < 32; r += 8) {              // row r of the tile = column n2_0 + r, lanes = 32 consecutive p
+    const uint32_t n2 = n2_0 + r, g = n2 / cols_per_rank, c = n2 % cols_per_rank;
+    const Fr *B = reinterpret_cast<const Fr *>(peers.base[g] + sizeof(NttCtl));
+    const uint32_t p = p0 + pl_0 + tx;
+    Fr v = ld_fr_volatile(B + (size_t)c * N1 + p);
+    const uint32_t k1 = __brev(p) >> (32 - l1);
+    const uint64_t e = ((uint64_t)n2 * k1) & nmask;
+    Fr w = tw_lo[e & 8191] * tw_hi[e >> 13];
+    v = v * w;
+#pragma unroll
+    for (int l = 0; l < 8; l++) tile[l][r][tx] = v.v[l];
+  }
+  __syncthreads();
+  for (uint32_t r = ty; r < 32; r += 8) {              // row r = position pl_0 + r, lanes = 32 consecutive n2
+    Fr v;
+#pragma unroll
+    for (int l = 0; l < 8; l++) v.v[l] = tile[l][tx][r];
+    uint4 *q = reinterpret_cast<uint4 *>(C + (size_t)(pl_0 + r) * N2 + n2_0 + tx);
+    q[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    q[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+  }
+  (void)N2;
+}
+
+// tw[e] = base^(e << shift), e < count (Montgomery form); pw[k] = omega_N^(2^k)
+__global__ void k_pow_table(Fr *out, const Fr *pw, uint32_t count, int shift) {
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  Fr acc = Fr::one();
+  uint64_t x = (uint64_t)e << shift;
+  for (int k = 0; x; k++, x >>= 1)
+    if (x & 1) acc = acc * pw[k];
+  out[e] = acc;
+}
+__global__ void k_root_pw(Fr *pw, int logn) {        // pw[k] = omega_{2^logn}^(2^k), omega_{2^28} = 5^((r-1)/2^28)
+  if (threadIdx.x || blockIdx.x) return;
+  const uint32_t W28[8] = {0x80d13d9cu, 0x636e7355u, 0x2445ffd6u, 0xa22bf374u, 0x1eb203d8u, 0x56452ac0u, 0x2963f9e7u, 0x1860ef94u};
+  Fr g;
+  for (int i = 0; i < 8; i++) g.v[i] = W28[i];
+  for (int i = 28; i > logn; i--) g = g.sqr();
+  for (int k = 0; k < 32; k++) { pw[k] = g; g = g.sqr(); }
+}
+// B_g[c][n1] = to_mont(hash(n1 * N2 + first_col + c))
+__global__ void k_fill_columns(Fr *B, int l1, int l2, uint32_t first_col, uint32_t cols, uint64_t seed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ((size_t)cols << l1)) return;
+  uint32_t c = (uint32_t)(i >> l1), n1 = (uint32_t)(i & ((1u << l1) - 1));
+  uint64_t idx = ((uint64_t)n1 << l2) + first_col + c;
+  B[i] = hash_field<Fr>(seed ^ 0x5ca1ab1eull, idx, 0, 0x1fffffffu).to_mont();
+}
+
+struct NttDist {
+  int device = 0, rank = 0, nranks = 1, logn = 0, l1 = 0, l2 = 0;
+  uint64_t seed = 0;
+  cudaStream_t st = nullptr;
+  uint8_t *alloc = nullptr;          // [NttCtl][B]
+  Fr *B = nullptr, *C = nullptr, *tw_lo = nullptr, *tw_hi = nullptr;
+  NttPlan plan1, plan2;
+  PeerPtrs peers;
+  bool ipc[MAX_RANKS];
+  uint32_t epoch = 0;
+  int *status = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+};
 }  // namespace zkb
 
 using namespace zkb;
@@ -384,6 +495,173 @@ int zkb_ntt_bench(int device, int logn, int nvec, int iters, float *dif_ms, floa
   *dif_ms = a / iters;
   *dit_ms = b / iters;
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  cudaFree(d);
+  plan.destroy();
+  return ZKB_OK;
+}
+
+
+// ---- 4-step NTT over `nranks` GPUs (one session per rank; see NttDist above) -----------------------------------
+struct zkb_ntt_dist;
+int zkb_ntt_dist_create(int device, int logn, int rank, int nranks, uint64_t seed, zkb_ntt_dist **out) {
+  if (require_device()) return ZKB_ERROR;
+  if (logn < 24 || logn > 30 || nranks < 1 || nranks > MAX_RANKS || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) {
+    set_error("ntt dist: logn in [24,30], nranks a power of two <= 16");
+    return ZKB_ERROR;
+  }
+  CKR(cudaSetDevice(device), "set device");
+  NttDist *s = new NttDist();
+  s->device = device; s->rank = rank; s->nranks = nranks; s->logn = logn; s->seed = seed;
+  s->l2 = logn / 2; s->l1 = logn - s->l2;
+  const size_t per = ((size_t)1 << logn) / nranks;
+  CKR(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking), "stream");
+  cudaEventCreate(&s->e0); cudaEventCreate(&s->e1); cudaEventCreate(&s->e2); cudaEventCreate(&s->e3);
+  CKR(cudaMalloc(&s->alloc, sizeof(NttCtl) + per * 32), "alloc B");
+  CKR(cudaMemsetAsync(s->alloc, 0, sizeof(NttCtl), s->st), "memset");
+  s->B = reinterpret_cast<Fr *>(s->alloc + sizeof(NttCtl));
+  CKR(cudaMalloc(&s->C, per * 32), "alloc C");
+  CKR(cudaMalloc(&s->status, 4), "alloc");
+  CKR(cudaMemsetAsync(s->status, 0, 4, s->st), "memset");
+  CKR(s->plan1.init(s->l1, s->st), "ntt plan 1");
+  CKR(s->plan2.init(s->l2, s->st), "ntt plan 2");
+  Fr *pw = nullptr;
+  CKR(cudaMalloc(&pw, 32 * 32), "alloc");
+  CKR(cudaMalloc(&s->tw_lo, 8192 * 32), "alloc");
+  const uint32_t hi = (uint32_t)(((size_t)1 << logn) >> 13);
+  CKR(cudaMalloc(&s->tw_hi, (size_t)hi * 32), "alloc");
+  k_root_pw<<<1, 1, 0, s->st>>>(pw, logn);
+  k_pow_table<<<8192 / 256, 256, 0, s->st>>>(s->tw_lo, pw, 8192, 0);
+  k_pow_table<<<(hi + 255) / 256, 256, 0, s->st>>>(s->tw_hi, pw, hi, 13);
+  CKR(cudaStreamSynchronize(s->st), "ntt dist setup");
+  cudaFree(pw);
+  for (int g = 0; g < MAX_RANKS; g++) { s->peers.base[g] = nullptr; s->ipc[g] = false; }
+  s->peers.base[rank] = s->alloc;
+  *out = reinterpret_cast<zkb_ntt_dist *>(s);
+  return ZKB_OK;
+}
+void zkb_ntt_dist_destroy(zkb_ntt_dist *h) {
+  NttDist *s = reinterpret_cast<NttDist *>(h);
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->st);
+  for (int g = 0; g < MAX_RANKS; g++)
+    if (s->ipc[g]) cudaIpcCloseMemHandle(const_cast<uint8_t *>(s->peers.base[g]));
+  cudaFree(s->alloc); cudaFree(s->C); cudaFree(s->status); cudaFree(s->tw_lo); cudaFree(s->tw_hi);
+  s->plan1.destroy(); s->plan2.destroy();
+  cudaEventDestroy(s->e0); cudaEventDestroy(s->e1); cudaEventDestroy(s->e2); cudaEventDestroy(s->e3);
+  cudaStreamDestroy(s->st);
+  delete s;
+}
+int zkb_ntt_dist_export(zkb_ntt_dist *h, void *handle64) {
+  NttDist *s = reinterpret_cast<NttDist *>(h);
+  CKR(cudaSetDevice(s->device), "set device");
+  cudaIpcMemHandle_t mh;
+  CKR(cudaIpcGetMemHandle(&mh, s->alloc), "ipc export");
+  memcpy(handle64, &mh, 64);
+  return ZKB_OK;
+}
+int zkb_ntt_dist_attach(zkb_ntt_dist *h, int peer_rank, const void *handle64) {
+  NttDist *s = reinterpret_cast<NttDist *>(h);
+  CKR(cudaSetDevice(s->device), "set device");
+  if (peer_rank < 0 || peer_rank >= s->nranks || peer_rank == s->rank) { set_error("ntt dist: bad peer rank"); return ZKB_ERROR; }
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, handle64, 64);
+  void *p = nullptr;
+  CKR(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess), "ipc open (peer access)");
+  s->peers.base[peer_rank] = reinterpret_cast<const uint8_t *>(p);
+  s->ipc[peer_rank] = true;
+  return ZKB_OK;
+}
+int zkb_ntt_dist_attach_local(zkb_ntt_dist *h, int peer_rank, zkb_ntt_dist *peer) {
+  NttDist *s = reinterpret_cast<NttDist *>(h), *o = reinterpret_cast<NttDist *>(peer);
+  CKR(cudaSetDevice(s->device), "set device");
+  if (s->device != o->device) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, s->device, o->device);
+    if (!can) { set_error("no peer access between the two GPUs"); return ZKB_ERROR; }
+    cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "enable peer access");
+    cudaGetLastError();
+  }
+  s->peers.base[peer_rank] = o->alloc;
+  return ZKB_OK;
+}
+// (re)generate this rank's columns of the synthetic input
+int zkb_ntt_dist_fill(zkb_ntt_dist *h) {
+  NttDist *s = reinterpret_cast<NttDist *>(h);
+  CKR(cudaSetDevice(s->device), "set device");
+  const uint32_t cols = (1u << s->l2) / s->nranks;
+  const size_t per = (size_t)cols << s->l1;
+  k_fill_columns<<<(unsigned)((per + 255) / 256), 256, 0, s->st>>>(s->B, s->l1, s->l2, s->rank * cols, cols, s->seed);
+  CKR(cudaStreamSynchronize(s->st), "fill");
+  return ZKB_OK;
+}
+// queue one transform (asynchronous).  All ranks must have called fill() (and be past a host barrier) before.
+int zkb_ntt_dist_run(zkb_ntt_dist *h) {
+  NttDist *s = reinterpret_cast<NttDist *>(h);
+  CKR(cudaSetDevice(s->device), "set device");
+  for (int g = 0; g < s->nranks; g++)
+    if (!s->peers.base[g]) { set_error("ntt dist: peer " + std::to_string(g) + " not attached"); return ZKB_ERROR; }
+  const uint32_t N1 = 1u << s->l1, N2 = 1u << s->l2, cols = N2 / s->nranks, rows = N1 / s->nranks;
+  s->epoch++;
+  cudaEventRecord(s->e0, s->st);
+  CKR(s->plan1.dif(s->B, (int)cols, N1, false, false, s->st), "column transforms");
+  k_set_flag<<<1, 1, 0, s->st>>>(&reinterpret_cast<NttCtl *>(s->alloc)->ready, s->epoch);
+  cudaEventRecord(s->e1, s->st);
+  k_wait_flags<<<1, 32, 0, s->st>>>(s->peers, s->nranks, s->epoch, s->status);
+  k_gather_transpose<<<dim3(N2 / 32, rows / 32), dim3(32, 8), 0, s->st>>>(s->peers, s->C, s->l1, s->l2, cols,
+                                                                             s->rank * rows, s->tw_lo, s->tw_hi, 1, s->status);
+  cudaEventRecord(s->e2, s->st);
+  CKR(s->plan2.dif(s->C, (int)rows, N2, false, false, s->st), "row transforms");
+  cudaEventRecord(s->e3, s->st);
+  CKR(cudaGetLastError(), "ntt dist launch");
+  return ZKB_OK;
+}
+// wait for the queued transform; ms[4] = total, column transforms, wait + exchange (P2P gather), row transforms
+int zkb_ntt_dist_sync(zkb_ntt_dist *h, float *ms) {
+  NttDist *s = reinterpret_cast<NttDist *>(h);
+  CKR(cudaSetDevice(s->device), "set device");
+  int st = -1;
+  CKR(cudaMemcpyAsync(&st, s->status, 4, cudaMemcpyDeviceToHost, s->st), "d2h");
+  CKR(cudaStreamSynchronize(s->st), "ntt dist run");
+  if (st != 0) { set_error("ntt dist: timed out waiting for rank " + std::to_string(st - 1)); return ZKB_ERROR; }
+  if (ms) {
+    cudaEventElapsedTime(ms + 0, s->e0, s->e3);
+    cudaEventElapsedTime(ms + 1, s->e0, s->e1);
+    cudaEventElapsedTime(ms + 2, s->e1, s->e2);
+    cudaEventElapsedTime(ms + 3, s->e2, s->e3);
+  }
+  return ZKB_OK;
+}
+// which = 0: this rank's input columns B_g[c][n1] (only valid right after fill()); 1: its output rows
+// C_g[p_local][q] = X[bitrev_N1(rank * N1/G + p_local) + N1 * bitrev_N2(q)].  Canonical form, N/G x 32 bytes.
+int zkb_ntt_dist_read(zkb_ntt_dist *h, int which, void *out) {
+  NttDist *s = reinterpret_cast<NttDist *>(h);
+  CKR(cudaSetDevice(s->device), "set device");
+  const size_t per = ((size_t)1 << s->logn) / s->nranks;
+  Fr *tmp = nullptr;
+  CKR(cudaMalloc(&tmp, per * 32), "alloc");
+  CKR(cudaMemcpyAsync(tmp, which ? s->C : s->B, per * 32, cudaMemcpyDeviceToDevice, s->st), "copy");
+  CKR(fr_from_mont(tmp, per, s->st), "from_mont");
+  CKR(cudaMemcpyAsync(out, tmp, per * 32, cudaMemcpyDeviceToHost, s->st), "d2h");
+  CKR(cudaStreamSynchronize(s->st), "read");
+  cudaFree(tmp);
+  return ZKB_OK;
+}
+// parity aid: forward transform of one resident vector by the single-GPU plan (natural in, BIT-REVERSED out):
+// data = N x 32 B canonical on the host, in place
+int zkb_raw_ntt_dif_forward(void *data, int logn) {
+  if (require_device()) return ZKB_ERROR;
+  NttPlan plan;
+  CKR(plan.init(logn, 0), "ntt plan");
+  size_t n = (size_t)1 << logn;
+  Fr *d = nullptr;
+  CKR(cudaMalloc(&d, n * 32), "alloc");
+  CKR(cudaMemcpy(d, data, n * 32, cudaMemcpyHostToDevice), "h2d");
+  CKR(fr_to_mont(d, n, 0), "to_mont");
+  CKR(plan.dif(d, 1, n, false, false, 0), "dif");
+  CKR(fr_from_mont(d, n, 0), "from_mont");
+  CKR(cudaMemcpy(data, d, n * 32, cudaMemcpyDeviceToHost), "d2h");
   cudaFree(d);
   plan.destroy();
   return ZKB_OK;

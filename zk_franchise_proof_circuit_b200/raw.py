@@ -131,3 +131,60 @@ def ntt_bench(logn, nvec=1, iters=5, device=0):
     a, b = ctypes.c_float(), ctypes.c_float()
     _native.check(_native.lib().zkb_ntt_bench(device, logn, nvec, iters, ctypes.byref(a), ctypes.byref(b)))
     return a.value, b.value
+
+
+class NttDist:
+    """One rank of the 4-step multi-GPU NTT (include/zkcensus_b200.h, zkb_ntt_dist_*)."""
+
+    def __init__(self, logn, rank=0, nranks=1, device=0, seed=1):
+        self.h = ctypes.c_void_p()
+        self.logn, self.rank, self.nranks = logn, rank, nranks
+        self.per = (1 << logn) // nranks
+        _native.check(_native.lib().zkb_ntt_dist_create(device, logn, rank, nranks, seed, ctypes.byref(self.h)))
+
+    def export_handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        _native.check(_native.lib().zkb_ntt_dist_export(self.h, buf))
+        return buf.raw
+
+    def attach(self, peer_rank, handle: bytes):
+        _native.check(_native.lib().zkb_ntt_dist_attach(self.h, peer_rank, ctypes.create_string_buffer(handle, 64)))
+
+    def attach_local(self, peer_rank, peer: "NttDist"):
+        _native.check(_native.lib().zkb_ntt_dist_attach_local(self.h, peer_rank, peer.h))
+
+    def fill(self):
+        _native.check(_native.lib().zkb_ntt_dist_fill(self.h))
+
+    def run(self):
+        _native.check(_native.lib().zkb_ntt_dist_run(self.h))
+
+    def sync(self):
+        """(total, column transforms, wait + P2P exchange, row transforms) in ms, device time."""
+        ms = (ctypes.c_float * 4)()
+        _native.check(_native.lib().zkb_ntt_dist_sync(self.h, ms))
+        return tuple(float(x) for x in ms)
+
+    def read(self, which):
+        out = np.zeros((self.per, 32), dtype=np.uint8)
+        _native.check(_native.lib().zkb_ntt_dist_read(self.h, which, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.h:
+            _native.lib().zkb_ntt_dist_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ntt_dif_forward(values: np.ndarray):
+    """Single-GPU forward transform, natural order in, bit-reversed order out (the decimation-in-frequency plan)."""
+    v = np.ascontiguousarray(values, dtype=np.uint8).copy()
+    logn = v.shape[0].bit_length() - 1
+    _native.check(_native.lib().zkb_raw_ntt_dif_forward(v.ctypes.data, logn))
+    return v
