@@ -81,6 +81,10 @@ int zkb_witness(zkb_circuit *c, const char *inputs_json, size_t inputs_len, void
 int zkb_prove_wtns(zkb_circuit *c, const void *wtns, size_t wtns_size, char *proof_buf, size_t *proof_size,
                    char *public_buf, size_t *public_size);
 
+/* same, plus the device stage times of the pass (8 floats as zkb_batch_prove_resident; measurement aid) */
+int zkb_prove_wtns_stages(zkb_circuit *c, const void *wtns, size_t wtns_size, char *proof_buf, size_t *proof_size,
+                          char *public_buf, size_t *public_size, float *stage_ms);
+
 /* rapidsnark prover.h, same symbol and signature, so go-rapidsnark's cgo wrapper links unchanged
  * (go.mod:30 github.com/iden3/go-rapidsnark/prover v0.0.9).  Returns 0 / 1 / 2. */
 int groth16_prover(const void *zkey_buffer, unsigned long zkey_size, const void *wtns_buffer, unsigned long wtns_size,

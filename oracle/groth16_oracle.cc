@@ -622,6 +622,136 @@ int orc_setup(const char *r1cs_path, const char *zkey_path, const char *vkey_pat
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Synthetic Poseidon-shaped chain circuit (BASELINE.json configs[3]): x_{k+1} = P(x_k, k), public output x_L.
+// P is a Poseidon-shaped permutation on t = 3 state elements (0, x, k): 8 full + 57 partial rounds, S-box x^5,
+// a fixed invertible 3 x 3 mix matrix, round constants from splitmix64 (SYNTHETIC constants: this circuit only has
+// to have the reference circuit's constraint shape, it is not circomlib's Poseidon).  Every state element after a
+// round's mix is its own wire (one linear row each), every S-box is 3 rows: 438 rows per link, <= 4 terms per row.
+// wires: 0 = one, 1 = x_L (public output), 2 = x_0 (private input), then the link wires.
+// ---------------------------------------------------------------------------------------------
+static void chain_build(uint32_t links, uint64_t x0_seed, R1CS &r1, std::vector<Fr> &w) {
+  const int T = 3, RF = 8, RP = 57, ROUNDS = RF + RP;
+  uint64_t cs = 0xC4A1D;
+  std::vector<Fr> C((size_t)ROUNDS * T);
+  for (auto &c : C) c = rand_fr(cs);
+  Fr M[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) M[i][j] = Fr::from_u64((uint64_t)(i == j ? 2 : 1) + (uint64_t)(i * 3 + j == 5 ? 1 : 0));   // det != 0
+  r1 = R1CS();
+  w.clear();
+  w.push_back(Fr::one());
+  w.push_back(Fr::zero());                 // x_L, patched at the end
+  uint64_t xs = x0_seed;
+  w.push_back(rand_fr(xs));                // x_0
+  auto new_wire = [&](const Fr &v) { w.push_back(v); return (uint32_t)(w.size() - 1); };
+  auto row = [&](std::vector<Term> a, std::vector<Term> b, std::vector<Term> c) {
+    r1.A.push_back(std::move(a)); r1.B.push_back(std::move(b)); r1.C.push_back(std::move(c));
+  };
+  const Fr one = Fr::one();
+  uint32_t x = 2;
+  for (uint32_t k = 0; k < links; k++) {
+    // state wires; s[0] = 0 and s[2] = k enter as constants on wire 0
+    bool is_wire[3] = {false, true, false};
+    uint32_t sw[3] = {0, x, 0};
+    Fr sc[3] = {Fr::zero(), Fr::zero(), Fr::from_u64(k)};     // constant part when !is_wire
+    Fr sv[3] = {Fr::zero(), w[x], Fr::from_u64(k)};
+    for (int r = 0; r < ROUNDS; r++) {
+      const bool full = r < RF / 2 || r >= RF / 2 + RP;
+      // ark + sbox: in_i = s_i + C ; out = in^5 for the S-boxed elements
+      Fr tv[3];
+      std::vector<Term> tl[3];        // linear form of the element after ark / sbox
+      for (int i = 0; i < T; i++) {
+        Fr cst = C[(size_t)r * T + i] + (is_wire[i] ? Fr::zero() : sc[i]);
+        Fr in = sv[i] + C[(size_t)r * T + i];
+        std::vector<Term> lin;
+        if (is_wire[i]) lin.push_back({sw[i], one});
+        lin.push_back({0, cst});
+        if (full || i == 0) {
+          Fr v2 = in * in, v4 = v2 * v2, v5 = v4 * in;
+          uint32_t w2 = new_wire(v2), w4 = new_wire(v4), w5 = new_wire(v5);
+          row(lin, lin, {{w2, one}});
+          row({{w2, one}}, {{w2, one}}, {{w4, one}});
+          row({{w4, one}}, lin, {{w5, one}});
+          tv[i] = v5;
+          tl[i] = {{w5, one}};
+        } else {
+          tv[i] = in;
+          tl[i] = lin;
+        }
+      }
+      // mix: s'_i = sum_j M[i][j] t_j, each a new wire:  (sum_j M[i][j] t_j) * 1 = s'_i
+      for (int i = 0; i < T; i++) {
+        Fr v = Fr::zero();
+        std::vector<Term> a;
+        Fr c0 = Fr::zero();
+        for (int j = 0; j < T; j++) {
+          v = v + M[i][j] * tv[j];
+          for (const Term &t : tl[j]) {
+            if (t.wire == 0) c0 = c0 + M[i][j] * t.coef;
+            else a.push_back({t.wire, M[i][j] * t.coef});
+          }
+        }
+        a.push_back({0, c0});
+        uint32_t nw = new_wire(v);
+        row(a, {{0, one}}, {{nw, one}});
+        sw[i] = nw; sv[i] = v; is_wire[i] = true;
+      }
+    }
+    x = sw[0];
+  }
+  // public output: x_L * 1 = out
+  w[1] = w[x];
+  row({{x, one}}, {{0, one}}, {{1, one}});
+  r1.nWires = (uint32_t)w.size();
+  r1.nPubOut = 1; r1.nPubIn = 0; r1.nPrvIn = 1;
+  r1.nConstraints = (uint32_t)r1.A.size();
+}
+
+static bool write_file(const char *path, const void *data, size_t n) {
+  FILE *f = fopen(path, "wb");
+  if (!f) return false;
+  bool ok = fwrite(data, 1, n, f) == n;
+  fclose(f);
+  return ok;
+}
+
+// Builds the chain circuit, runs the dev setup and writes proving_key (.zkey), verification key (json) and the
+// witness (.wtns, iden3 format).  info[3] = nWires, nConstraints, domain size.  check != 0: also verifies that the
+// witness satisfies every row.
+int orc_chain_artifacts(uint32_t links, uint64_t seed, const char *zkey_path, const char *vkey_path,
+                        const char *wtns_path, uint32_t *info, int check) {
+  oracle_init();
+  R1CS r1;
+  std::vector<Fr> w;
+  chain_build(links, seed ^ 0x1234, r1, w);
+  if (check) {
+    auto dot = [&](const std::vector<Term> &l) { Fr a = Fr::zero(); for (const Term &t : l) a = a + t.coef * w[t.wire]; return a; };
+    for (uint32_t i = 0; i < r1.nConstraints; i++)
+      if (!(dot(r1.A[i]) * dot(r1.B[i]) == dot(r1.C[i]))) return 10;
+  }
+  std::vector<uint8_t> zk;
+  std::string vk;
+  if (!setup(r1, seed, zk, vk)) return 3;
+  if (!write_file(zkey_path, zk.data(), zk.size())) return 4;
+  if (!write_file(vkey_path, vk.data(), vk.size())) return 5;
+  // .wtns: magic, version 2, 2 sections: (1) n8, prime, nWitness; (2) values
+  std::vector<uint8_t> o;
+  o.insert(o.end(), {'w', 't', 'n', 's'});
+  put_u32(o, 2); put_u32(o, 2);
+  put_u32(o, 1); put_u64(o, 40);
+  put_u32(o, 32); o.insert(o.end(), (uint8_t *)R_MOD, (uint8_t *)R_MOD + 32); put_u32(o, (uint32_t)w.size());
+  put_u32(o, 2); put_u64(o, (uint64_t)w.size() * 32);
+  size_t k = o.size();
+  o.resize(k + w.size() * 32);
+  for (size_t i = 0; i < w.size(); i++) w[i].to_bytes(o.data() + k + i * 32);
+  if (!write_file(wtns_path, o.data(), o.size())) return 6;
+  uint32_t rows = r1.nConstraints + 2, dom = 1;
+  while (dom < rows) dom <<= 1;
+  info[0] = r1.nWires; info[1] = r1.nConstraints; info[2] = dom;
+  return 0;
+}
+
 // info[0..3] = nVars, nPublic, domainSize, nCoefs
 int orc_zkey_info(const uint8_t *zkey, size_t len, uint32_t *info) {
   oracle_init();

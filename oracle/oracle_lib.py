@@ -33,6 +33,7 @@ def lib():
         L.orc_g1_mul_gen.argtypes = [vp, vp]
         L.orc_check_closed_form.argtypes = [ctypes.c_char_p, u64, vp, vp, vp, vp]
         L.orc_set_threads.argtypes = [i32]
+        L.orc_chain_artifacts.argtypes = [ctypes.c_uint32, u64, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, vp, i32]
         _lib = L
     return _lib
 
@@ -107,6 +108,19 @@ def alphabeta12(vk: dict):
     lib().orc_alphabeta12(_buf(g1_bin(vk["vk_alpha_1"])), _buf(g2_bin(vk["vk_beta_2"])), out)
     v = [str(from_le(bytes(out)[i:i + 32])) for i in range(0, 384, 32)]
     return [[[v[(i * 3 + j) * 2], v[(i * 3 + j) * 2 + 1]] for j in range(3)] for i in range(2)]
+
+
+def chain_artifacts(links: int, seed: int, out_dir: str, check=True):
+    """Synthetic Poseidon-shaped chain circuit (BASELINE.json configs[3]) with `links` permutations: writes
+    proving_key.zkey, verification_key.json, witness.wtns into out_dir; returns (nWires, nConstraints, domain)."""
+    os.makedirs(out_dir, exist_ok=True)
+    info = np.zeros(3, dtype=np.uint32)
+    rc = lib().orc_chain_artifacts(links, seed, os.path.join(out_dir, "proving_key.zkey").encode(),
+                                   os.path.join(out_dir, "verification_key.json").encode(),
+                                   os.path.join(out_dir, "witness.wtns").encode(), info.ctypes.data, 1 if check else 0)
+    if rc:
+        raise RuntimeError(f"orc_chain_artifacts failed ({rc})")
+    return tuple(int(x) for x in info)
 
 
 class ZKeyRef:

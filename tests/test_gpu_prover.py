@@ -242,3 +242,30 @@ def test_gpu_verifier_reference_fixture_and_own_proofs(circuit):
     assert prover.verify_batch(vk, pubs[:1], proofs[:1]) == [0]          # wrong key
     for p, q in zip(proofs[:4], pubs[:4]):
         assert O.verify(H.dev_vkey(), json.loads(q), json.loads(p))
+
+
+def test_generic_circuit_chain_bit_exact(tmp_path):
+    """A non-census key: the synthetic Poseidon-shaped chain circuit (BASELINE configs[3], 40 links = 17.5 k rows),
+    loaded without a wasm, proved from its .wtns; A/B/C == the CPU oracle with pinned r,s, and the proof verifies
+    under the matching vkey on the GPU and on the CPU."""
+    from zk_franchise_proof_circuit_b200 import prover
+    n_wires, n_cons, domain = O.chain_artifacts(40, 7, str(tmp_path))
+    assert n_cons == 40 * 438 + 1 and domain == 1 << 15
+    zkey = open(tmp_path / "proving_key.zkey", "rb").read()
+    wtns = open(tmp_path / "witness.wtns", "rb").read()
+    vkey = open(tmp_path / "verification_key.json", "rb").read()
+    c = prover.load(zkey, None)
+    assert c.n_vars == n_wires
+    c.set_blinding(H.R_FIXED, H.S_FIXED)
+    try:
+        pj, sj = c.prove_wtns(wtns)
+    finally:
+        c.set_blinding(None, None)
+    w = H.wtns_payload(wtns, n_wires)
+    exp = O.ZKeyRef(zkey).prove(w, H.R_FIXED, H.S_FIXED)
+    proof, pub = json.loads(pj), json.loads(sj)
+    assert O.proof_bin(proof) == exp
+    assert pub == [str(int.from_bytes(w[1].tobytes(), "little"))]
+    assert O.verify(json.loads(vkey), pub, proof)
+    prover.verify(vkey, sj, pj)
+    c.close()

@@ -255,6 +255,15 @@ static uint32_t env_u32(const char *name, uint32_t dflt) {
   return x > 0 ? (uint32_t)x : dflt;
 }
 
+// proofs per NTT/MSM chunk: 128 for census-sized keys (2^17 rows), fewer for larger ones so that a chunk's working
+// set (45 MB per proof at 2^17) stays bounded; a 2^22-row circuit runs one proof per chunk
+static uint32_t default_chunk(const Circuit *c) {
+  uint32_t fit = (uint32_t)(((size_t)1 << 24) / (c->domain ? c->domain : 1));
+  if (fit < 1) fit = 1;
+  if (fit > 128) fit = 128;
+  return env_u32("ZKB_CHUNK", fit);
+}
+
 static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
   if (c->cap >= cap && c->chunk >= chunk) return ZKB_OK;
   // (re)allocate everything; sizes are small next to the 180 GB of HBM
@@ -737,7 +746,7 @@ int zkb_batch_set_inputs(zkb_circuit *h, int n, const void *inputs) {
   if (!c->consts) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
   std::lock_guard<std::mutex> g(c->mu);
   CKR(cudaSetDevice(c->ctx->device), "set device");
-  uint32_t chunk = env_u32("ZKB_CHUNK", 128);
+  uint32_t chunk = default_chunk(c);
   int rc = ensure_workspace(c, (uint32_t)n, chunk);
   if (rc) return rc;
   CKR(cudaMemcpyAsync(c->inputs, inputs, (size_t)n * c->L.n_inputs * 32, cudaMemcpyHostToDevice, c->ctx->stream), "h2d inputs");
@@ -886,7 +895,7 @@ int zkb_fullprove_batch(zkb_circuit *h, int n, const char *const *inputs_json, c
   if (n <= 0) return ZKB_OK;
   std::lock_guard<std::mutex> g(c->mu);
   CKR(cudaSetDevice(c->ctx->device), "set device");
-  uint32_t chunk = env_u32("ZKB_CHUNK", 128), group = env_u32("ZKB_GROUP", 1024);
+  uint32_t chunk = default_chunk(c), group = env_u32("ZKB_GROUP", 1024);
   uint32_t cap = (uint32_t)n < group ? (uint32_t)n : group;
   int rc = ensure_workspace(c, cap > c->cap ? cap : c->cap, chunk);
   if (rc) return rc;
@@ -957,7 +966,7 @@ int zkb_witness(zkb_circuit *h, const char *inputs_json, size_t inputs_len, void
   CKR(cudaSetDevice(c->ctx->device), "set device");
   size_t need = 4 + 4 + 4 + 12 + (4 + 32 + 4) + 12 + (size_t)c->n_vars * 32;
   if (!wtns_out || *wtns_len < need) { *wtns_len = need; return ZKB_SHORT_BUFFER; }
-  int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : env_u32("ZKB_CHUNK", 128));
+  int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : default_chunk(c));
   if (rc) return rc;
   std::string err;
   memset(c->h_inputs, 0, (size_t)c->L.n_inputs * 32);
@@ -984,8 +993,15 @@ int zkb_witness(zkb_circuit *h, const char *inputs_json, size_t inputs_len, void
 }
 
 // Groth16 from a caller-supplied witness (.wtns bytes): what go-rapidsnark's Groth16ProverRaw does.
+int zkb_prove_wtns_stages(zkb_circuit *h, const void *wtns, size_t wtns_size, char *proof_buf, size_t *proof_size,
+                          char *public_buf, size_t *public_size, float *stage_ms);
 int zkb_prove_wtns(zkb_circuit *h, const void *wtns, size_t wtns_size, char *proof_buf, size_t *proof_size,
                    char *public_buf, size_t *public_size) {
+  return zkb_prove_wtns_stages(h, wtns, wtns_size, proof_buf, proof_size, public_buf, public_size, nullptr);
+}
+// same, with the device stage times of the pass (8 floats as zkb_batch_prove_resident; the witness slot is 0)
+int zkb_prove_wtns_stages(zkb_circuit *h, const void *wtns, size_t wtns_size, char *proof_buf, size_t *proof_size,
+                          char *public_buf, size_t *public_size, float *stage_ms) {
   Circuit *c = h->c;
   const uint8_t *b = (const uint8_t *)wtns;
   if (wtns_size < 12 || memcmp(b, "wtns", 4) != 0) { set_error("wtns: bad magic"); return ZKB_ERROR; }
@@ -1009,10 +1025,10 @@ int zkb_prove_wtns(zkb_circuit *h, const void *wtns, size_t wtns_size, char *pro
   if (nw != c->n_vars) { set_error("wtns: witness length does not match the zkey"); return ZKB_INVALID_WITNESS_LENGTH; }
   std::lock_guard<std::mutex> g(c->mu);
   CKR(cudaSetDevice(c->ctx->device), "set device");
-  int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : env_u32("ZKB_CHUNK", 128));
+  int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : default_chunk(c));
   if (rc) return rc;
   CKR(cudaMemcpyAsync(c->wtns, data, (size_t)nw * 32, cudaMemcpyHostToDevice, c->ctx->stream), "h2d witness");
-  if ((rc = prove_group(c, 1, false, nullptr))) return rc;
+  if ((rc = prove_group(c, 1, false, stage_ms))) return rc;
   std::string pj = proof_to_json(c->h_out, false), sj = publics_to_json(c->h_out + 256, c->n_public);
   int r1 = copy_out(pj, proof_buf, proof_size), r2 = copy_out(sj, public_buf, public_size);
   return (r1 || r2) ? ZKB_SHORT_BUFFER : ZKB_OK;

@@ -53,6 +53,7 @@ def _lib():
                                     _vp, _sz]
         L.zkb_witness.argtypes = [_vp, ctypes.c_char_p, _sz, _vp, ctypes.POINTER(_sz)]
         L.zkb_prove_wtns.argtypes = [_vp, _vp, _sz, _vp, ctypes.POINTER(_sz), _vp, ctypes.POINTER(_sz)]
+        L.zkb_prove_wtns_stages.argtypes = [_vp, _vp, _sz, _vp, ctypes.POINTER(_sz), _vp, ctypes.POINTER(_sz), _vp]
         L.groth16_prover.argtypes = [_vp, ctypes.c_ulong, _vp, ctypes.c_ulong, _vp, ctypes.POINTER(ctypes.c_ulong),
                                      _vp, ctypes.POINTER(ctypes.c_ulong), _vp, ctypes.c_ulong]
         _bound = True
@@ -146,12 +147,16 @@ class Circuit:
         _native.check(_lib().zkb_witness(self.h, doc, len(doc), buf, ctypes.byref(n)))
         return buf.raw[:n.value]
 
-    def prove_wtns(self, wtns: bytes):
+    def prove_wtns(self, wtns: bytes, stages=False):
+        """Groth16 from a .wtns (go-rapidsnark Groth16ProverRaw).  stages=True also returns the 8 device stage times."""
         pbuf, qbuf = ctypes.create_string_buffer(1024), ctypes.create_string_buffer(2048)
         pn, qn = ctypes.c_size_t(1024), ctypes.c_size_t(2048)
         wb = (ctypes.c_char * len(wtns)).from_buffer_copy(wtns)
-        _native.check(_lib().zkb_prove_wtns(self.h, wb, len(wtns), pbuf, ctypes.byref(pn), qbuf, ctypes.byref(qn)))
-        return pbuf.raw[:pn.value], qbuf.raw[:qn.value]
+        st = np.zeros(8, dtype=np.float32)
+        _native.check(_lib().zkb_prove_wtns_stages(self.h, wb, len(wtns), pbuf, ctypes.byref(pn), qbuf, ctypes.byref(qn),
+                                                   st.ctypes.data if stages else None))
+        out = (pbuf.raw[:pn.value], qbuf.raw[:qn.value])
+        return out + (st,) if stages else out
 
     def poseidon(self, rows):
         """Batched Poseidon on the GPU: rows = list of equal-length tuples of ints (arity 2..4) -> list of ints."""
