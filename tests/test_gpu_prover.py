@@ -244,13 +244,15 @@ def test_gpu_verifier_reference_fixture_and_own_proofs(circuit):
         assert O.verify(H.dev_vkey(), json.loads(q), json.loads(p))
 
 
-def test_generic_circuit_chain_bit_exact(tmp_path):
-    """A non-census key: the synthetic Poseidon-shaped chain circuit (BASELINE configs[3], 40 links = 17.5 k rows),
-    loaded without a wasm, proved from its .wtns; A/B/C == the CPU oracle with pinned r,s, and the proof verifies
-    under the matching vkey on the GPU and on the CPU."""
+@pytest.mark.parametrize("links", [40, 600])
+def test_generic_circuit_chain_bit_exact(tmp_path, links):
+    """A non-census key: the synthetic Poseidon-shaped chain circuit (BASELINE configs[3]), loaded without a wasm,
+    proved from its .wtns; A/B/C == the CPU oracle with pinned r,s, and the proof verifies under the matching vkey
+    on the GPU and on the CPU.  40 links = 17.5 k rows (one point range per MSM); 600 links = 262,803 wires, domain
+    2^19: the witness MSMs run as 3 point ranges (the last one padded) and the H MSM as 4."""
     from zk_franchise_proof_circuit_b200 import prover
-    n_wires, n_cons, domain = O.chain_artifacts(40, 7, str(tmp_path))
-    assert n_cons == 40 * 438 + 1 and domain == 1 << 15
+    n_wires, n_cons, domain = O.chain_artifacts(links, 7, str(tmp_path))
+    assert n_cons == links * 438 + 1 and domain == (1 << 15 if links == 40 else 1 << 19)
     zkey = open(tmp_path / "proving_key.zkey", "rb").read()
     wtns = open(tmp_path / "witness.wtns", "rb").read()
     vkey = open(tmp_path / "verification_key.json", "rb").read()

@@ -241,14 +241,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_accumulate(TablePtrs<F> tabs,
                                                         const uint32_t *__restrict__ entries,
                                                         const uint32_t *__restrict__ order,
                                                         const uint32_t *__restrict__ n_long, XYZZ<F> *buckets,
-                                                        size_t tab_batch_stride) {
+                                                        size_t tab_batch_stride, uint32_t tab_mod) {
   uint32_t t = blockIdx.y, b = blockIdx.z;
   const uint32_t pos = blockIdx.x * THREADS + threadIdx.x;
   if ((pos | 31u) < n_long[b]) return;     // this whole warp's buckets belong to k_accumulate_long
   const bool mine = pos >= n_long[b];
   const uint32_t bucket = order[(size_t)b * nbuckets + pos];
   const Affine<F> *tab = (t == 0 ? tabs.tab[0] : (t == 1 ? tabs.tab[1] : (t == 2 ? tabs.tab[2] : tabs.tab[3]))) +
-                         (size_t)b * tab_batch_stride;
+                         (size_t)(b % tab_mod) * tab_batch_stride;
   const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
   const uint32_t *ent = entries + (size_t)b * n * windows;
   const uint32_t beg = off[bucket], len = mine ? off[bucket + 1] - beg : 0u;
@@ -296,11 +296,11 @@ __global__ void __launch_bounds__(32) k_accumulate_long(TablePtrs<F> tabs, int n
                                                         const uint32_t *__restrict__ entries,
                                                         const uint32_t *__restrict__ order,
                                                         const uint32_t *__restrict__ n_long, XYZZ<F> *buckets,
-                                                        size_t tab_batch_stride) {
+                                                        size_t tab_batch_stride, uint32_t tab_mod) {
   const uint32_t t = blockIdx.y, b = blockIdx.z, lane = threadIdx.x;
   if (blockIdx.x >= n_long[b]) return;
   const Affine<F> *tab = (t == 0 ? tabs.tab[0] : (t == 1 ? tabs.tab[1] : (t == 2 ? tabs.tab[2] : tabs.tab[3]))) +
-                         (size_t)b * tab_batch_stride;
+                         (size_t)(b % tab_mod) * tab_batch_stride;
   const uint32_t bucket = order[(size_t)b * nbuckets + blockIdx.x];
   const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
   const uint32_t *ent = entries + (size_t)b * n * windows;
@@ -447,7 +447,8 @@ template <> struct AccCfg<Fq2> { static constexpr int THREADS = 64; static const
 
 template <class F>
 cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
-                           uint32_t slot0, cudaStream_t st, size_t tab_batch_stride) {
+                           uint32_t slot0, cudaStream_t st, size_t tab_batch_stride, uint32_t tab_mod) {
+  if (tab_mod == 0) tab_mod = nbatch;
   if (ntab < 1 || ntab > 4 || slot0 + nbatch * (uint32_t)ntab > work.slots) return cudaErrorInvalidValue;
   TablePtrs<F> tp;
   for (int i = 0; i < 4; i++) tp.tab[i] = i < ntab ? tables[i].tab : nullptr;
@@ -459,7 +460,7 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
   dim3 grid(nb / TH, ntab, nbatch);
   XYZZ<F> *dst = work.buckets + (size_t)slot0 * nb;
   static const int variant = getenv("ZKB_ACC_VARIANT") ? atoi(getenv("ZKB_ACC_VARIANT")) : 0;
-#define ZKB_ACC(MINB, INL) k_accumulate<F, TH, MINB, INL><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order, sort.n_long, dst, tab_batch_stride)
+#define ZKB_ACC(MINB, INL) k_accumulate<F, TH, MINB, INL><<<grid, TH, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order, sort.n_long, dst, tab_batch_stride, tab_mod)
   if constexpr (sizeof(F) == 32) {
     switch (variant) {
       case 1: ZKB_ACC(4, false); break;
@@ -479,7 +480,7 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
 #undef ZKB_ACC
   dim3 glong(MAX_LONG, ntab, nbatch);
   k_accumulate_long<F><<<glong, 32, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order,
-                                             sort.n_long, dst, tab_batch_stride);
+                                             sort.n_long, dst, tab_batch_stride, tab_mod);
   return cudaGetLastError();
 }
 
@@ -503,10 +504,29 @@ cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F
   return cudaGetLastError();
 }
 
+// out[p * ntab + t] = sum over sub-ranges s of in[(p * subs + s) * ntab + t]   (one thread per output; subs is small)
+template <class F>
+__global__ void k_fold_subs(const XYZZ<F> *in, XYZZ<F> *out, uint32_t subs, uint32_t ntab, uint32_t total) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const uint32_t p = i / ntab, t = i % ntab;
+  XYZZ<F> acc = XYZZ<F>::infinity();
+  for (uint32_t s = 0; s < subs; s++) xyzz_add_ni(&acc, in + ((size_t)(p * subs + s) * ntab + t));
+  stg_pod(out + i, acc);
+}
+template <class F>
+cudaError_t msm_fold_subs(const XYZZ<F> *in, XYZZ<F> *out, uint32_t nproofs, uint32_t subs, uint32_t ntab, cudaStream_t st) {
+  const uint32_t total = nproofs * ntab;
+  k_fold_subs<F><<<(total + 31) / 32, 32, 0, st>>>(in, out, subs, ntab, total);
+  return cudaGetLastError();
+}
+template cudaError_t msm_fold_subs<Fq>(const XYZZ<Fq> *, XYZZ<Fq> *, uint32_t, uint32_t, uint32_t, cudaStream_t);
+template cudaError_t msm_fold_subs<Fq2>(const XYZZ<Fq2> *, XYZZ<Fq2> *, uint32_t, uint32_t, uint32_t, cudaStream_t);
+
 template <class F>
 cudaError_t msm_run(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
                     XYZZ<F> *out, cudaStream_t st) {
-  cudaError_t e = msm_accumulate<F>(sort, tables, ntab, nbatch, work, 0, st, 0);
+  cudaError_t e = msm_accumulate<F>(sort, tables, ntab, nbatch, work, 0, st, 0, 0);
   if (e != cudaSuccess) return e;
   return msm_reduce<F>(work, 0, nbatch * (uint32_t)ntab, out, st);
 }
@@ -548,8 +568,8 @@ cudaError_t msm_count_madds(const MsmSort &sort, const MsmTable<F> &table, uint3
 }
 template cudaError_t msm_count_madds<Fq>(const MsmSort &, const MsmTable<Fq> &, uint32_t, unsigned long long *, cudaStream_t);
 template cudaError_t msm_count_madds<Fq2>(const MsmSort &, const MsmTable<Fq2> &, uint32_t, unsigned long long *, cudaStream_t);
-template cudaError_t msm_accumulate<Fq>(const MsmSort &, const MsmTable<Fq> *, int, uint32_t, MsmWork<Fq> &, uint32_t, cudaStream_t, size_t);
-template cudaError_t msm_accumulate<Fq2>(const MsmSort &, const MsmTable<Fq2> *, int, uint32_t, MsmWork<Fq2> &, uint32_t, cudaStream_t, size_t);
+template cudaError_t msm_accumulate<Fq>(const MsmSort &, const MsmTable<Fq> *, int, uint32_t, MsmWork<Fq> &, uint32_t, cudaStream_t, size_t, uint32_t);
+template cudaError_t msm_accumulate<Fq2>(const MsmSort &, const MsmTable<Fq2> *, int, uint32_t, MsmWork<Fq2> &, uint32_t, cudaStream_t, size_t, uint32_t);
 template cudaError_t msm_reduce<Fq>(MsmWork<Fq> &, uint32_t, uint32_t, XYZZ<Fq> *, cudaStream_t);
 template cudaError_t msm_reduce<Fq2>(MsmWork<Fq2> &, uint32_t, uint32_t, XYZZ<Fq2> *, cudaStream_t);
 template cudaError_t msm_run<Fq>(const MsmSort &, const MsmTable<Fq> *, int, uint32_t, MsmWork<Fq> &, XYZZ<Fq> *,

@@ -70,9 +70,14 @@ cudaError_t msm_build_table(MsmTable<F> &t, const Affine<F> *bases, uint32_t n, 
 
 // bucket sums of (batch item b, table t) -> work.buckets[slot0 + b*ntab + t].  Tables, sort and work must share cfg.
 template <class F>
-// tab_batch_stride: batch item b reads its bases at table + b * tab_batch_stride (0: every item shares the table).
+// tab_batch_stride: batch item b reads its bases at table + (b % tab_mod) * tab_batch_stride (0: every item shares
+// the table; tab_mod = 0 means nbatch).  With a key split into `subs` point ranges, batch item p * subs + s is range
+// s of proof p and tab_mod = subs.
 cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int ntab, uint32_t nbatch, MsmWork<F> &work,
-                           uint32_t slot0, cudaStream_t st, size_t tab_batch_stride = 0);
+                           uint32_t slot0, cudaStream_t st, size_t tab_batch_stride = 0, uint32_t tab_mod = 0);
+// out[p * ntab + t] = sum_s in[(p * subs + s) * ntab + t]
+template <class F>
+cudaError_t msm_fold_subs(const XYZZ<F> *in, XYZZ<F> *out, uint32_t nproofs, uint32_t subs, uint32_t ntab, cudaStream_t st);
 // out[i] = sum_b (b+1) * buckets[slot0 + i][b], i < nslots
 template <class F>
 cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F> *out, cudaStream_t st);

@@ -102,11 +102,11 @@ __device__ __forceinline__ void stg_fr8(Fr *p, const Fr &x);
 // Poseidon2(0,0) blocks below the leaf level, the oldKey = 0 sub-circuits), so d is zero there and the four
 // witness MSMs only see the wires that differ:  sum_i w_i P_i = sum_i tmpl_i P_i + sum_i d_i P_i, with the first
 // sum computed once per key.  Decided per wire on the data, exact for any tree depth.
-__global__ void k_witness_diff(const Fr *wtns, size_t wtns_stride, const Fr *tmpl, Fr *d, uint32_t n) {
+__global__ void k_witness_diff(const Fr *wtns, size_t wtns_stride, const Fr *tmpl, Fr *d, size_t d_stride, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fr w = ldg_fr8(wtns + (size_t)blockIdx.y * wtns_stride + i);
-  stg_fr8(d + (size_t)blockIdx.y * n + i, tmpl ? w - ldg_fr8(tmpl + i) : w);
+  stg_fr8(d + (size_t)blockIdx.y * d_stride + i, tmpl ? w - ldg_fr8(tmpl + i) : w);
 }
 
 __device__ __forceinline__ Fr ldg_fr8(const Fr *p) {
@@ -175,12 +175,13 @@ struct Lane {
   MsmSort sortW, sortH;
   MsmWork<Fq> work1, workH;
   MsmWork<Fq2> work2;
-  XYZZ<Fq> *g1out = nullptr;
-  XYZZ<Fq2> *g2out = nullptr;
+  XYZZ<Fq> *g1out = nullptr, *g1raw = nullptr;   // g1raw / g2raw: per point-range sums before the fold (large keys)
+  XYZZ<Fq2> *g2out = nullptr, *g2raw = nullptr;
   XYZZ<Fq> *fin_scratch = nullptr;
   void free_all() {
     cudaFree(abc); cudaFree(hs); cudaFree(dw); cudaFree(g1out); cudaFree(g2out); cudaFree(fin_scratch); cudaFree(stage);
-    abc = hs = dw = stage = nullptr; g1out = fin_scratch = nullptr; g2out = nullptr;
+    cudaFree(g1raw); cudaFree(g2raw);
+    abc = hs = dw = stage = nullptr; g1out = fin_scratch = g1raw = nullptr; g2out = g2raw = nullptr;
     if (sortW.counts) sortW.free_all();
     if (sortH.counts) sortH.free_all();
     if (work1.buckets) work1.free_all();
@@ -220,6 +221,9 @@ struct Circuit {
   XYZZ<Fq> *tconst1 = nullptr;     // sum_i tmpl_i * {A_i, B1_i, C_i}
   XYZZ<Fq2> *tconst2 = nullptr;    // sum_i tmpl_i * B2_i
   int *status = nullptr;
+  // Large keys: every MSM is cut by point range into sub-MSMs of 2^17 points that run as extra batch items (a single
+  // 4 M-point MSM would otherwise be 32,768 threads with 2,048 sequential adds each); 1 range for census-sized keys.
+  uint32_t subW = 1, subH = 1, nsubW = 0, nsubH = 0, n_pad = 0;
   MsmCfg cfgW, cfgH;              // window sizes: witness MSMs (sparse after the template difference), H MSM (dense)
   uint8_t *out = nullptr;          // device results
   uint8_t *h_out = nullptr;        // pinned
@@ -296,16 +300,21 @@ static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
     }
     CKR(cudaMalloc(&ln.abc, (size_t)chunk * 3 * c->domain * 32), "alloc abc");
     CKR(cudaMalloc(&ln.hs, (size_t)chunk * c->domain * 32), "alloc h");
-    CKR(cudaMalloc(&ln.dw, (size_t)chunk * c->n_vars * 32), "alloc witness diff");
+    CKR(cudaMalloc(&ln.dw, (size_t)chunk * c->n_pad * 32), "alloc witness diff");
+    CKR(cudaMemset(ln.dw, 0, (size_t)chunk * c->n_pad * 32), "clear witness diff");   // the padding stays zero
     if (c->consts) CKR(cudaMalloc(&ln.stage, (size_t)chunk * c->L.n_signals * 32), "alloc witness staging");
     CKR(cudaMalloc(&ln.g1out, (size_t)chunk * 4 * sizeof(XYZZ<Fq>)), "alloc g1out");
     CKR(cudaMalloc(&ln.g2out, (size_t)chunk * sizeof(XYZZ<Fq2>)), "alloc g2out");
     CKR(cudaMalloc(&ln.fin_scratch, (size_t)chunk * 30 * sizeof(XYZZ<Fq>)), "alloc finalize scratch");
-    CKR(ln.sortW.alloc(c->n_vars, chunk, c->cfgW), "alloc sortW");
-    CKR(ln.sortH.alloc(c->domain, chunk, c->cfgH), "alloc sortH");
-    CKR(ln.work1.alloc(chunk * 3, c->cfgW), "alloc msm work g1");
-    CKR(ln.workH.alloc(chunk, c->cfgH), "alloc msm work g1 (H)");
-    CKR(ln.work2.alloc(chunk, c->cfgW), "alloc msm work g2");
+    CKR(ln.sortW.alloc(c->nsubW, chunk * c->subW, c->cfgW), "alloc sortW");
+    CKR(ln.sortH.alloc(c->nsubH, chunk * c->subH, c->cfgH), "alloc sortH");
+    CKR(ln.work1.alloc(chunk * c->subW * 3, c->cfgW), "alloc msm work g1");
+    CKR(ln.workH.alloc(chunk * c->subH, c->cfgH), "alloc msm work g1 (H)");
+    CKR(ln.work2.alloc(chunk * c->subW, c->cfgW), "alloc msm work g2");
+    if (c->subW > 1 || c->subH > 1) {
+      CKR(cudaMalloc(&ln.g1raw, (size_t)chunk * (3 * c->subW + c->subH) * sizeof(XYZZ<Fq>)), "alloc g1 range sums");
+      CKR(cudaMalloc(&ln.g2raw, (size_t)chunk * c->subW * sizeof(XYZZ<Fq2>)), "alloc g2 range sums");
+    }
   }
   return ZKB_OK;
 }
@@ -338,21 +347,36 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
   dim3 g2((c->domain + 255) / 256, m);
   k_join<<<g2, 256, 0, st>>>(ln.abc, ln.hs, c->domain);
   if (ev) cudaEventRecord(ev[3], st);
-  k_witness_diff<<<dim3((c->n_vars + 255) / 256, m), 256, 0, st>>>(w, c->n_vars, c->tconst1 ? c->tmpl : nullptr, ln.dw, c->n_vars);
+  k_witness_diff<<<dim3((c->n_vars + 255) / 256, m), 256, 0, st>>>(w, c->n_vars, c->tconst1 ? c->tmpl : nullptr, ln.dw, c->n_pad, c->n_vars);
   g_launches += 1;
-  CKR(ln.sortW.run(ln.dw, c->n_vars, m, st), "sort witness digits");
-  CKR(ln.sortH.run(ln.hs, c->domain, m, st), "sort h digits");
+  // batch item p * sub + s = point range s of proof p (sub = 1: one item per proof)
+  const uint32_t sW = c->subW, sH = c->subH;
+  const size_t strW = sW > 1 ? (size_t)c->cfgW.windows * c->nsubW : 0, strH = sH > 1 ? (size_t)c->cfgH.windows * c->nsubH : 0;
+  CKR(ln.sortW.run(ln.dw, c->nsubW, m * sW, st), "sort witness digits");
+  CKR(ln.sortH.run(ln.hs, c->nsubH, m * sH, st), "sort h digits");
   if (ev) cudaEventRecord(ev[4], st);
   // bucket sums: G1 over the witness difference (A, B1, C share one sort), H over h, G2 (B2) over the witness difference
   MsmTable<Fq> tabs[3] = {c->tabA, c->tabB1, c->tabC};
-  CKR(msm_accumulate<Fq>(ln.sortW, tabs, 3, m, ln.work1, 0, st), "msm accumulate g1 (A,B1,C)");
-  CKR(msm_accumulate<Fq>(ln.sortH, &c->tabH, 1, m, ln.workH, 0, st), "msm accumulate g1 (H)");
+  CKR(msm_accumulate<Fq>(ln.sortW, tabs, 3, m * sW, ln.work1, 0, st, strW, sW), "msm accumulate g1 (A,B1,C)");
+  CKR(msm_accumulate<Fq>(ln.sortH, &c->tabH, 1, m * sH, ln.workH, 0, st, strH, sH), "msm accumulate g1 (H)");
   if (ev) cudaEventRecord(ev[5], st);
-  CKR(msm_accumulate<Fq2>(ln.sortW, &c->tabB2, 1, m, ln.work2, 0, st), "msm accumulate g2 (B2)");
+  CKR(msm_accumulate<Fq2>(ln.sortW, &c->tabB2, 1, m * sW, ln.work2, 0, st, strW, sW), "msm accumulate g2 (B2)");
   if (ev) cudaEventRecord(ev[6], st);
-  CKR(msm_reduce<Fq>(ln.work1, 0, 3 * m, ln.g1out, st), "msm reduce g1");
-  CKR(msm_reduce<Fq>(ln.workH, 0, m, ln.g1out + (size_t)3 * c->chunk, st), "msm reduce g1 (H)");
-  CKR(msm_reduce<Fq2>(ln.work2, 0, m, ln.g2out, st), "msm reduce g2");
+  XYZZ<Fq> *outW = sW > 1 ? ln.g1raw : ln.g1out;
+  XYZZ<Fq> *outH = sH > 1 ? ln.g1raw + (size_t)3 * c->chunk * sW : ln.g1out + (size_t)3 * c->chunk;
+  XYZZ<Fq2> *out2 = sW > 1 ? ln.g2raw : ln.g2out;
+  CKR(msm_reduce<Fq>(ln.work1, 0, 3 * m * sW, outW, st), "msm reduce g1");
+  CKR(msm_reduce<Fq>(ln.workH, 0, m * sH, outH, st), "msm reduce g1 (H)");
+  CKR(msm_reduce<Fq2>(ln.work2, 0, m * sW, out2, st), "msm reduce g2");
+  if (sW > 1) {
+    CKR(msm_fold_subs<Fq>(outW, ln.g1out, m, sW, 3, st), "fold g1 ranges");
+    CKR(msm_fold_subs<Fq2>(out2, ln.g2out, m, sW, 1, st), "fold g2 ranges");
+    g_launches += 2;
+  }
+  if (sH > 1) {
+    CKR(msm_fold_subs<Fq>(outH, ln.g1out + (size_t)3 * c->chunk, m, sH, 1, st), "fold g1 (H) ranges");
+    g_launches += 1;
+  }
   if (ev) cudaEventRecord(ev[7], st);
   g_launches += 2 * msm_sort_launches() + 4 + 2 + 6;   // 2 sorts, (2 + 1) x 2 accumulate, 3 x 2 reduce
   FinalizeParams P;
@@ -568,23 +592,39 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
     Affine<Fq2> *d2 = nullptr;
     c->cfgW = msm_cfg((int)env_u32("ZKB_C_WITNESS", c->tmpl ? 13 : 16));
     c->cfgH = msm_cfg((int)env_u32("ZKB_C_H", 16));
-    auto build1 = [&](MsmTable<Fq> &t, const uint8_t *src, uint32_t n, uint32_t pad_front, MsmCfg cfg) -> int {
+    // point ranges (see Circuit::subW): 2^17 points each once a key has more than 2^18; the last range is padded
+    // with points at infinity
+    const uint32_t SUB = 1u << 17;
+    c->nsubW = (z.n_vars > 2 * SUB && !c->tmpl) ? SUB : z.n_vars;
+    c->subW = (z.n_vars + c->nsubW - 1) / c->nsubW;
+    c->n_pad = c->subW * c->nsubW;
+    c->nsubH = z.domain > 2 * SUB ? SUB : z.domain;
+    c->subH = z.domain / c->nsubH;
+    // n points after pad_front leading infinities, padded at the back to subs * n_sub
+    auto build1 = [&](MsmTable<Fq> &t, const uint8_t *src, uint32_t n, uint32_t pad_front, MsmCfg cfg, uint32_t n_sub,
+                      uint32_t subs) -> int {
       std::vector<uint8_t> tmp;
       const uint8_t *p = src;
-      if (pad_front) { tmp.assign((size_t)(n + pad_front) * 64, 0); memcpy(tmp.data() + (size_t)pad_front * 64, src, (size_t)n * 64); p = tmp.data(); }
-      CKR(upload(&d1, p, (size_t)(n + pad_front) * 64), "upload bases");
-      CKR(msm_build_table<Fq>(t, d1, n + pad_front, cfg, st), "build table");
+      const size_t total = (size_t)n_sub * subs;
+      if (pad_front || total != n) { tmp.assign(total * 64, 0); memcpy(tmp.data() + (size_t)pad_front * 64, src, (size_t)n * 64); p = tmp.data(); }
+      CKR(upload(&d1, p, total * 64), "upload bases");
+      CKR(msm_build_table<Fq>(t, d1, n_sub, cfg, st, subs), "build table");
       CKR(cudaStreamSynchronize(st), "build table");
       cudaFree(d1);
       return ZKB_OK;
     };
     int rc;
-    if ((rc = build1(c->tabA, z.a, z.n_vars, 0, c->cfgW))) return rc;
-    if ((rc = build1(c->tabB1, z.b1, z.n_vars, 0, c->cfgW))) return rc;
-    if ((rc = build1(c->tabC, z.c, z.n_vars - z.n_public - 1, z.n_public + 1, c->cfgW))) return rc;
-    if ((rc = build1(c->tabH, z.h, z.domain, 0, c->cfgH))) return rc;
-    CKR(upload(&d2, z.b2, (size_t)z.n_vars * 128), "upload bases");
-    CKR(msm_build_table<Fq2>(c->tabB2, d2, z.n_vars, c->cfgW, st), "build table");
+    if ((rc = build1(c->tabA, z.a, z.n_vars, 0, c->cfgW, c->nsubW, c->subW))) return rc;
+    if ((rc = build1(c->tabB1, z.b1, z.n_vars, 0, c->cfgW, c->nsubW, c->subW))) return rc;
+    if ((rc = build1(c->tabC, z.c, z.n_vars - z.n_public - 1, z.n_public + 1, c->cfgW, c->nsubW, c->subW))) return rc;
+    if ((rc = build1(c->tabH, z.h, z.domain, 0, c->cfgH, c->nsubH, c->subH))) return rc;
+    {
+      std::vector<uint8_t> tmp;
+      const uint8_t *p = z.b2;
+      if (c->n_pad != z.n_vars) { tmp.assign((size_t)c->n_pad * 128, 0); memcpy(tmp.data(), z.b2, (size_t)z.n_vars * 128); p = tmp.data(); }
+      CKR(upload(&d2, p, (size_t)c->n_pad * 128), "upload bases");
+    }
+    CKR(msm_build_table<Fq2>(c->tabB2, d2, c->nsubW, c->cfgW, st, c->subW), "build table");
     CKR(cudaStreamSynchronize(st), "build table");
     cudaFree(d2);
   }
@@ -804,6 +844,7 @@ int zkb_work_counters(zkb_circuit *h, uint64_t *out) {
   cudaStream_t st = c->ctx->stream;
   uint32_t m = c->last_chunk_m;
   if (!m) { set_error("no chunk processed yet"); return ZKB_ERROR; }
+  if (c->subW > 1 || c->subH > 1) { set_error("work counters are implemented for single-range keys only"); return ZKB_ERROR; }
   unsigned long long t[5] = {0, 0, 0, 0, 0};
   Lane &ln = c->lanes[c->last_lane];
   CKR(msm_count_madds<Fq>(ln.sortW, c->tabA, m, &t[0], st), "count");
