@@ -81,9 +81,21 @@ int zkb_witness(zkb_circuit *c, const char *inputs_json, size_t inputs_len, void
 int zkb_prove_wtns(zkb_circuit *c, const void *wtns, size_t wtns_size, char *proof_buf, size_t *proof_size,
                    char *public_buf, size_t *public_size);
 
-/* same, plus the device stage times of the pass (8 floats as zkb_batch_prove_resident; measurement aid) */
+/* same, plus the device stage times of the pass (8 floats as zkb_batch_prove_resident; measurement aid).
+ * wtns == NULL: prove again from the witness the previous call left on the device (device-resident timing). */
 int zkb_prove_wtns_stages(zkb_circuit *c, const void *wtns, size_t wtns_size, char *proof_buf, size_t *proof_size,
                           char *public_buf, size_t *public_size, float *stage_ms);
+
+/* A proving key sharded over nranks GPUs (BASELINE.json configs[3]: one large proof, MSMs split by point range):
+ * rank `rank` keeps the window tables of its 2^17-point ranges only, every rank is given the same .wtns and computes
+ * the H scalars itself (the three coset transforms are ~6 ms at 2^22), ranks > 0 write their five partial sums into
+ * rank 0's exchange buffer over NVLink (zkb_shard_export on rank 0 -> zkb_shard_attach on the others), rank 0 adds
+ * them and assembles the proof.  zkb_prove_wtns(_stages) is the call on every rank; ranks > 0 return empty strings.
+ * The caller places a barrier between two proofs (a slot holds one epoch's partial sums). */
+int zkb_load_circuit_shard(zkb_ctx *ctx, const void *zkey, size_t zkey_len, int rank, int nranks, zkb_circuit **out);
+int zkb_shard_export(zkb_circuit *c, void *handle64);
+int zkb_shard_attach(zkb_circuit *c, const void *handle64);
+int zkb_shard_attach_local(zkb_circuit *c, zkb_circuit *root);
 
 /* rapidsnark prover.h, same symbol and signature, so go-rapidsnark's cgo wrapper links unchanged
  * (go.mod:30 github.com/iden3/go-rapidsnark/prover v0.0.9).  Returns 0 / 1 / 2. */

@@ -271,3 +271,50 @@ def test_generic_circuit_chain_bit_exact(tmp_path, links):
     assert O.verify(json.loads(vkey), pub, proof)
     prover.verify(vkey, sj, pj)
     c.close()
+
+
+def _sharded_proof(zkey, wtns, nranks, devices):
+    from zk_franchise_proof_circuit_b200 import prover
+    cs = [prover.load_shard(zkey, r, nranks, device=devices[r % len(devices)]) for r in range(nranks)]
+    for c in cs[1:]:
+        c.shard_attach_local(cs[0])
+    cs[0].set_blinding(H.R_FIXED, H.S_FIXED)
+    for c in cs[1:]:                       # single thread: the peers publish first, then rank 0 combines
+        assert c.prove_wtns(wtns) == (b"", b"")
+    pj, sj = cs[0].prove_wtns(wtns)
+    # second proof: next epoch
+    for c in cs[1:]:
+        c.prove_wtns(wtns)
+    assert cs[0].prove_wtns(wtns) == (pj, sj)
+    for c in cs:
+        c.close()
+    return pj, sj
+
+
+def test_sharded_key_matches_oracle(tmp_path):
+    """262,803-wire chain circuit sharded over 2 and 3 ranks (contexts of one GPU): rank 0's proof == the CPU oracle
+    with pinned r,s (the same bytes as the unsharded path), and it verifies."""
+    from zk_franchise_proof_circuit_b200 import prover
+    n_wires, _, _ = O.chain_artifacts(600, 7, str(tmp_path), check=False)
+    zkey = open(tmp_path / "proving_key.zkey", "rb").read()
+    wtns = open(tmp_path / "witness.wtns", "rb").read()
+    vkey = open(tmp_path / "verification_key.json", "rb").read()
+    exp = O.ZKeyRef(zkey).prove(H.wtns_payload(wtns, n_wires), H.R_FIXED, H.S_FIXED)
+    for nranks in (2, 3):
+        pj, sj = _sharded_proof(zkey, wtns, nranks, [0])
+        assert O.proof_bin(json.loads(pj)) == exp
+        prover.verify(vkey, sj, pj)
+    with pytest.raises(Exception):
+        prover.load_shard(zkey, 0, 8)       # 3 witness ranges cannot feed 8 ranks
+
+
+def test_sharded_key_two_gpus(tmp_path):
+    from zk_franchise_proof_circuit_b200 import prover, _native
+    if _native.lib().zkb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n_wires, _, _ = O.chain_artifacts(600, 7, str(tmp_path), check=False)
+    zkey = open(tmp_path / "proving_key.zkey", "rb").read()
+    wtns = open(tmp_path / "witness.wtns", "rb").read()
+    exp = O.ZKeyRef(zkey).prove(H.wtns_payload(wtns, n_wires), H.R_FIXED, H.S_FIXED)
+    pj, sj = _sharded_proof(zkey, wtns, 2, [0, 1])
+    assert O.proof_bin(json.loads(pj)) == exp

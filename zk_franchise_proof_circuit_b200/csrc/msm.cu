@@ -494,10 +494,12 @@ cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F
   k_reduce1<F, RT><<<g1, RT, 0, st>>>(work.buckets + (size_t)slot0 * nb, work.part_r + (size_t)slot0 * parts,
                                       work.part_s + (size_t)slot0 * parts, nb);
   const uint32_t nthr = parts < 256 ? parts : 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};            // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     cudaFuncSetAttribute(k_reduce2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * (int)sizeof(XYZZ<F>));
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   k_reduce2<F><<<nslots, nthr, nthr * sizeof(XYZZ<F>), st>>>(work.part_r + (size_t)slot0 * parts,
                                                               work.part_s + (size_t)slot0 * parts, out, parts);

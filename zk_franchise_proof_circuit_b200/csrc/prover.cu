@@ -19,7 +19,8 @@
 #include <vector>
 #include <map>
 #include <mutex>
-#include <random>
+#include <sys/random.h>
+#include <cerrno>
 #include <memory>
 #include <atomic>
 #include <algorithm>
@@ -152,6 +153,51 @@ __global__ void __launch_bounds__(256) k_join(const Fr *abc, Fr *h, uint32_t dom
   stg_fr8(h + (size_t)blockIdx.y * domain + i, (a * b - c).from_mont());
 }
 
+// ---- key sharded over GPUs (one large proof, MSMs split by point range) ---------------------------
+// Every rank sums its own point ranges; rank r > 0 then writes its five partial sums into slot r of rank 0's exchange
+// buffer (a CUDA IPC / peer mapping: the stores travel over NVLink) and releases the epoch flag; rank 0 waits for the
+// flags, adds the partial sums to its own and goes on to the proof assembly.  No NCCL, no host round trip.
+static constexpr int SHARD_MAX_RANKS = 16;
+struct alignas(256) ShardSlot {
+  XYZZ<Fq> g1[4];      // pi_a', pi_b1', pi_c', pi_h partial sums
+  XYZZ<Fq2> g2;        // pi_b' partial sum
+  uint32_t flag;
+};
+__global__ void k_shard_publish(ShardSlot *slot, const XYZZ<Fq> *g1, const XYZZ<Fq> *g1h, const XYZZ<Fq2> *g2, uint32_t epoch) {
+  const uint32_t t = threadIdx.x;                       // 256 threads: 4 x 32 + 64 words
+  uint32_t *dst = reinterpret_cast<uint32_t *>(slot);
+  if (t < 96) dst[t] = reinterpret_cast<const uint32_t *>(g1)[t];
+  else if (t < 128) dst[t] = reinterpret_cast<const uint32_t *>(g1h)[t - 96];
+  else if (t < 192) dst[t] = reinterpret_cast<const uint32_t *>(g2)[t - 128];
+  __threadfence_system();
+  __syncthreads();
+  if (t == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&slot->flag), "r"(epoch) : "memory");
+}
+__global__ void k_shard_combine(ShardSlot *slots, int nranks, uint32_t epoch, XYZZ<Fq> *g1, XYZZ<Fq> *g1h, XYZZ<Fq2> *g2,
+                                int *status) {
+  const uint32_t t = threadIdx.x;                       // 5 threads: one per partial sum
+  __shared__ int bad;
+  if (t == 0) {
+    bad = 0;
+    const long long t0 = clock64();
+    for (int r = 1; r < nranks && !bad; r++) {
+      uint32_t f;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&slots[r].flag) : "memory");
+        if (f != epoch && clock64() - t0 > 8000000000LL) { bad = r; break; }
+      } while (f != epoch);
+    }
+    if (bad) atomicMax(status, 7);                      // ZKB shard timeout marker
+  }
+  __syncthreads();
+  if (bad || t >= 5) return;
+  for (int r = 1; r < nranks; r++) {
+    if (t < 3) { XYZZ<Fq> p = slots[r].g1[t]; xyzz_add_ni(g1 + t, &p); }
+    else if (t == 3) { XYZZ<Fq> p = slots[r].g1[3]; xyzz_add_ni(g1h, &p); }
+    else { XYZZ<Fq2> p = slots[r].g2; xyzz_add_ni(g2, &p); }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host objects
 // ---------------------------------------------------------------------------------------------
@@ -165,6 +211,31 @@ struct Ctx {
 static const char *INPUT_NAMES[12] = {"electionId", "nullifier", "voteHash", "sikRoot", "censusRoot", "voteWeight",
                                       "availableWeight", "address", "password", "signature", "censusSiblings",
                                       "sikSiblings"};
+
+// Blinding scalars r, s come from the kernel CSPRNG (getrandom(2)), buffered; uniform in [0, r) by rejection.
+// (snarkjs uses crypto.getRandomValues, rapidsnark libsodium's randombytes_buf: both are OS-CSPRNG backed.)
+struct OsRandom {
+  uint8_t buf[4096];
+  size_t pos = sizeof(buf);
+  bool fill(void *dst, size_t n) {
+    uint8_t *d = (uint8_t *)dst;
+    while (n) {
+      if (pos == sizeof(buf)) {
+        size_t got = 0;
+        while (got < sizeof(buf)) {
+          ssize_t k = getrandom(buf + got, sizeof(buf) - got, 0);
+          if (k < 0) { if (errno == EINTR) continue; return false; }
+          got += (size_t)k;
+        }
+        pos = 0;
+      }
+      size_t take = sizeof(buf) - pos < n ? sizeof(buf) - pos : n;
+      memcpy(d, buf + pos, take);
+      pos += take; d += take; n -= take;
+    }
+    return true;
+  }
+};
 
 // Per-chunk working set.  Chunks alternate between lanes (each with its own stream), so the latency-bound kernels
 // of one chunk (witness, bucket reduction, proof assembly, scans) overlap the IMAD-bound accumulation of the other.
@@ -224,6 +295,13 @@ struct Circuit {
   // Large keys: every MSM is cut by point range into sub-MSMs of 2^17 points that run as extra batch items (a single
   // 4 M-point MSM would otherwise be 32,768 threads with 2,048 sequential adds each); 1 range for census-sized keys.
   uint32_t subW = 1, subH = 1, nsubW = 0, nsubH = 0, n_pad = 0;
+  // sharded key: this rank owns ranges [loW, loW + cntW) of the witness MSMs and [loH, loH + cntH) of the H MSM
+  uint32_t loW = 0, cntW = 1, loH = 0, cntH = 1;
+  int shard_rank = 0, shard_n = 1;
+  ShardSlot *xbuf = nullptr;       // rank 0: SHARD_MAX_RANKS slots (exported)
+  ShardSlot *root_x = nullptr;     // where this rank publishes
+  bool root_is_ipc = false;
+  uint32_t epoch = 0;
   MsmCfg cfgW, cfgH;              // window sizes: witness MSMs (sparse after the template difference), H MSM (dense)
   uint8_t *out = nullptr;          // device results
   uint8_t *h_out = nullptr;        // pinned
@@ -233,20 +311,20 @@ struct Circuit {
   std::mutex mu;
   uint32_t last_chunk_m = 0;
   int last_lane = 0;
-  std::mt19937_64 rng;
+  OsRandom rng;
   // stage timing of the last device pass (ms)
   float t_witness = 0, t_abc = 0, t_ntt = 0, t_msm = 0, t_fin = 0;
   size_t out_stride() const { return 256 + 32 * (size_t)n_public; }
 };
 
-static void random_fr(std::mt19937_64 &g, uint32_t out[8]) {
+static bool random_fr(OsRandom &g, uint32_t out[8]) {
   static const uint32_t RMOD[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
                                    0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
   for (;;) {
-    for (int i = 0; i < 8; i += 2) { uint64_t x = g(); out[i] = (uint32_t)x; out[i + 1] = (uint32_t)(x >> 32); }
+    if (!g.fill(out, 32)) return false;
     out[7] &= 0x3fffffffu;
     for (int i = 7; i >= 0; i--) {
-      if (out[i] < RMOD[i]) return;
+      if (out[i] < RMOD[i]) return true;
       if (out[i] > RMOD[i]) break;
     }
   }
@@ -350,10 +428,13 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
   k_witness_diff<<<dim3((c->n_vars + 255) / 256, m), 256, 0, st>>>(w, c->n_vars, c->tconst1 ? c->tmpl : nullptr, ln.dw, c->n_pad, c->n_vars);
   g_launches += 1;
   // batch item p * sub + s = point range s of proof p (sub = 1: one item per proof)
-  const uint32_t sW = c->subW, sH = c->subH;
-  const size_t strW = sW > 1 ? (size_t)c->cfgW.windows * c->nsubW : 0, strH = sH > 1 ? (size_t)c->cfgH.windows * c->nsubH : 0;
-  CKR(ln.sortW.run(ln.dw, c->nsubW, m * sW, st), "sort witness digits");
-  CKR(ln.sortH.run(ln.hs, c->nsubH, m * sH, st), "sort h digits");
+  // (a sharded key proves one proof at a time and only sorts / sums its own ranges [lo, lo + cnt))
+  const uint32_t sW = c->cntW, sH = c->cntH;
+  const bool splitW = c->subW > 1, splitH = c->subH > 1;
+  const size_t strW = splitW ? (size_t)c->cfgW.windows * c->nsubW : 0, strH = splitH ? (size_t)c->cfgH.windows * c->nsubH : 0;
+  if (c->shard_n > 1 && m != 1) { set_error("a sharded key proves one witness per call"); return ZKB_ERROR; }
+  CKR(ln.sortW.run(ln.dw + (size_t)c->loW * c->nsubW, c->nsubW, m * sW, st), "sort witness digits");
+  CKR(ln.sortH.run(ln.hs + (size_t)c->loH * c->nsubH, c->nsubH, m * sH, st), "sort h digits");
   if (ev) cudaEventRecord(ev[4], st);
   // bucket sums: G1 over the witness difference (A, B1, C share one sort), H over h, G2 (B2) over the witness difference
   MsmTable<Fq> tabs[3] = {c->tabA, c->tabB1, c->tabC};
@@ -362,20 +443,32 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
   if (ev) cudaEventRecord(ev[5], st);
   CKR(msm_accumulate<Fq2>(ln.sortW, &c->tabB2, 1, m * sW, ln.work2, 0, st, strW, sW), "msm accumulate g2 (B2)");
   if (ev) cudaEventRecord(ev[6], st);
-  XYZZ<Fq> *outW = sW > 1 ? ln.g1raw : ln.g1out;
-  XYZZ<Fq> *outH = sH > 1 ? ln.g1raw + (size_t)3 * c->chunk * sW : ln.g1out + (size_t)3 * c->chunk;
-  XYZZ<Fq2> *out2 = sW > 1 ? ln.g2raw : ln.g2out;
+  XYZZ<Fq> *outW = splitW ? ln.g1raw : ln.g1out;
+  XYZZ<Fq> *outH = splitH ? ln.g1raw + (size_t)3 * c->chunk * c->subW : ln.g1out + (size_t)3 * c->chunk;
+  XYZZ<Fq2> *out2 = splitW ? ln.g2raw : ln.g2out;
   CKR(msm_reduce<Fq>(ln.work1, 0, 3 * m * sW, outW, st), "msm reduce g1");
   CKR(msm_reduce<Fq>(ln.workH, 0, m * sH, outH, st), "msm reduce g1 (H)");
   CKR(msm_reduce<Fq2>(ln.work2, 0, m * sW, out2, st), "msm reduce g2");
-  if (sW > 1) {
+  if (splitW) {
     CKR(msm_fold_subs<Fq>(outW, ln.g1out, m, sW, 3, st), "fold g1 ranges");
     CKR(msm_fold_subs<Fq2>(out2, ln.g2out, m, sW, 1, st), "fold g2 ranges");
     g_launches += 2;
   }
-  if (sH > 1) {
+  if (splitH) {
     CKR(msm_fold_subs<Fq>(outH, ln.g1out + (size_t)3 * c->chunk, m, sH, 1, st), "fold g1 (H) ranges");
     g_launches += 1;
+  }
+  if (c->shard_n > 1) {
+    c->epoch++;
+    g_launches += 1;
+    if (c->shard_rank != 0) {
+      k_shard_publish<<<1, 256, 0, st>>>(c->root_x + c->shard_rank, ln.g1out, ln.g1out + (size_t)3 * c->chunk, ln.g2out, c->epoch);
+      if (ev) { cudaEventRecord(ev[7], st); cudaEventRecord(ev[8], st); }
+      CKR(cudaGetLastError(), "shard publish");
+      return ZKB_OK;                                     // rank 0 assembles the proof
+    }
+    k_shard_combine<<<1, 32, 0, st>>>(c->xbuf, c->shard_n, c->epoch, ln.g1out, ln.g1out + (size_t)3 * c->chunk, ln.g2out,
+                                      c->status + first);
   }
   if (ev) cudaEventRecord(ev[7], st);
   g_launches += 2 * msm_sort_launches() + 4 + 2 + 6;   // 2 sorts, (2 + 1) x 2 accumulate, 3 x 2 reduce
@@ -447,12 +540,13 @@ static int prove_resident(Circuit *c, uint32_t n, bool with_witness, float *stag
   return ZKB_OK;
 }
 
-static void fill_blinding(Circuit *c, uint32_t n) {
+static bool fill_blinding(Circuit *c, uint32_t n) {
   for (uint32_t i = 0; i < n; i++) {
     uint32_t *r = c->h_rs[2 * i].v, *s = c->h_rs[2 * i + 1].v;
     if (c->fixed_rs) { memcpy(r, c->fr, 32); memcpy(s, c->fs, 32); }
-    else { random_fr(c->rng, r); random_fr(c->rng, s); }
+    else if (!random_fr(c->rng, r) || !random_fr(c->rng, s)) { set_error("getrandom failed: no blinding scalars"); return false; }
   }
+  return true;
 }
 
 // inputs.json -> canonical values in main-signal order (n_inputs x 8 u32)
@@ -480,7 +574,7 @@ static cudaError_t upload(T **dptr, const void *src, size_t bytes) {
 }
 
 static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const uint8_t *wasm, size_t wasm_len,
-                        Circuit **out) {
+                        Circuit **out, int shard_rank = 0, int shard_n = 1) {
   CKR(cudaSetDevice(ctx->device), "set device");
   std::string err;
   ZkeyView z;
@@ -488,8 +582,6 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
   std::unique_ptr<Circuit> c(new Circuit());
   c->ctx = ctx;
   c->n_vars = z.n_vars; c->n_public = z.n_public; c->domain = z.domain; c->power = z.power;
-  std::random_device rd;
-  c->rng.seed(((uint64_t)rd() << 32) ^ rd());
   cudaStream_t st = ctx->stream;
   memset(&c->L, 0, sizeof c->L);
 
@@ -600,31 +692,50 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
     c->n_pad = c->subW * c->nsubW;
     c->nsubH = z.domain > 2 * SUB ? SUB : z.domain;
     c->subH = z.domain / c->nsubH;
+    c->loW = c->loH = 0;
+    c->cntW = c->subW;
+    c->cntH = c->subH;
+    c->shard_rank = shard_rank;
+    c->shard_n = shard_n;
+    if (shard_n > 1) {
+      if (c->subW < (uint32_t)shard_n || c->subH < (uint32_t)shard_n) {
+        set_error("key too small to shard: every rank needs at least one 2^17-point range of each MSM");
+        return ZKB_ERROR;
+      }
+      c->loW = (uint32_t)((uint64_t)c->subW * shard_rank / shard_n);
+      c->cntW = (uint32_t)((uint64_t)c->subW * (shard_rank + 1) / shard_n) - c->loW;
+      c->loH = (uint32_t)((uint64_t)c->subH * shard_rank / shard_n);
+      c->cntH = (uint32_t)((uint64_t)c->subH * (shard_rank + 1) / shard_n) - c->loH;
+      CKR(cudaMalloc(&c->xbuf, SHARD_MAX_RANKS * sizeof(ShardSlot)), "alloc shard exchange");
+      CKR(cudaMemsetAsync(c->xbuf, 0, SHARD_MAX_RANKS * sizeof(ShardSlot), st), "memset");
+      c->root_x = c->xbuf;
+    }
     // n points after pad_front leading infinities, padded at the back to subs * n_sub
+    // only ranges [lo, lo + cnt) are uploaded and expanded (all of them unless the key is sharded)
     auto build1 = [&](MsmTable<Fq> &t, const uint8_t *src, uint32_t n, uint32_t pad_front, MsmCfg cfg, uint32_t n_sub,
-                      uint32_t subs) -> int {
+                      uint32_t subs, uint32_t lo, uint32_t cnt) -> int {
       std::vector<uint8_t> tmp;
       const uint8_t *p = src;
       const size_t total = (size_t)n_sub * subs;
       if (pad_front || total != n) { tmp.assign(total * 64, 0); memcpy(tmp.data() + (size_t)pad_front * 64, src, (size_t)n * 64); p = tmp.data(); }
-      CKR(upload(&d1, p, total * 64), "upload bases");
-      CKR(msm_build_table<Fq>(t, d1, n_sub, cfg, st, subs), "build table");
+      CKR(upload(&d1, p + (size_t)lo * n_sub * 64, (size_t)cnt * n_sub * 64), "upload bases");
+      CKR(msm_build_table<Fq>(t, d1, n_sub, cfg, st, cnt), "build table");
       CKR(cudaStreamSynchronize(st), "build table");
       cudaFree(d1);
       return ZKB_OK;
     };
     int rc;
-    if ((rc = build1(c->tabA, z.a, z.n_vars, 0, c->cfgW, c->nsubW, c->subW))) return rc;
-    if ((rc = build1(c->tabB1, z.b1, z.n_vars, 0, c->cfgW, c->nsubW, c->subW))) return rc;
-    if ((rc = build1(c->tabC, z.c, z.n_vars - z.n_public - 1, z.n_public + 1, c->cfgW, c->nsubW, c->subW))) return rc;
-    if ((rc = build1(c->tabH, z.h, z.domain, 0, c->cfgH, c->nsubH, c->subH))) return rc;
+    if ((rc = build1(c->tabA, z.a, z.n_vars, 0, c->cfgW, c->nsubW, c->subW, c->loW, c->cntW))) return rc;
+    if ((rc = build1(c->tabB1, z.b1, z.n_vars, 0, c->cfgW, c->nsubW, c->subW, c->loW, c->cntW))) return rc;
+    if ((rc = build1(c->tabC, z.c, z.n_vars - z.n_public - 1, z.n_public + 1, c->cfgW, c->nsubW, c->subW, c->loW, c->cntW))) return rc;
+    if ((rc = build1(c->tabH, z.h, z.domain, 0, c->cfgH, c->nsubH, c->subH, c->loH, c->cntH))) return rc;
     {
       std::vector<uint8_t> tmp;
       const uint8_t *p = z.b2;
       if (c->n_pad != z.n_vars) { tmp.assign((size_t)c->n_pad * 128, 0); memcpy(tmp.data(), z.b2, (size_t)z.n_vars * 128); p = tmp.data(); }
-      CKR(upload(&d2, p, (size_t)c->n_pad * 128), "upload bases");
+      CKR(upload(&d2, p + (size_t)c->loW * c->nsubW * 128, (size_t)c->cntW * c->nsubW * 128), "upload bases");
     }
-    CKR(msm_build_table<Fq2>(c->tabB2, d2, c->nsubW, c->cfgW, st, c->subW), "build table");
+    CKR(msm_build_table<Fq2>(c->tabB2, d2, c->nsubW, c->cfgW, st, c->cntW), "build table");
     CKR(cudaStreamSynchronize(st), "build table");
     cudaFree(d2);
   }
@@ -673,6 +784,8 @@ static void destroy_circuit(Circuit *c) {
   cudaFree(c->consts); cudaFree(c->hc); cudaFree(c->tmpl); cudaFree(c->wmap); cudaFree(c->csr_buf); cudaFree(c->row_order);
   cudaFree(c->csr_val); cudaFree(c->fix1); cudaFree(c->fix2); cudaFree(c->d1tab); cudaFree(c->d2tab);
   cudaFree(c->tconst1); cudaFree(c->tconst2);
+  if (c->root_is_ipc) cudaIpcCloseMemHandle(c->root_x);
+  cudaFree(c->xbuf);
   cudaFree(c->tabA.tab); cudaFree(c->tabB1.tab); cudaFree(c->tabC.tab); cudaFree(c->tabH.tab); cudaFree(c->tabB2.tab);
   c->ntt.destroy();
   cudaFree(c->inputs); cudaFree(c->wtns); cudaFree(c->rs); cudaFree(c->status); cudaFree(c->out);
@@ -700,7 +813,7 @@ static int prove_group(Circuit *c, uint32_t n, bool with_witness, float *stage_m
   cudaStream_t st = c->ctx->stream;
   if (with_witness)
     CKR(cudaMemcpyAsync(c->inputs, c->h_inputs, (size_t)n * c->L.n_inputs * 32, cudaMemcpyHostToDevice, st), "h2d inputs");
-  fill_blinding(c, n);
+  if (!fill_blinding(c, n)) return ZKB_ERROR;
   CKR(cudaMemcpyAsync(c->rs, c->h_rs, (size_t)n * 64, cudaMemcpyHostToDevice, st), "h2d rs");
   int rc = prove_resident(c, n, with_witness, stage_ms);
   if (rc) return rc;
@@ -753,6 +866,57 @@ int zkb_load_circuit(zkb_ctx *ctx, const void *zkey, size_t zkey_len, const void
   return ZKB_OK;
 }
 
+// A proving key sharded over `nranks` GPUs (one context / process per GPU): rank `rank` keeps the fixed-base tables of
+// its point ranges only.  No witness generator (prove from a .wtns); every rank is given the same witness.
+int zkb_load_circuit_shard(zkb_ctx *ctx, const void *zkey, size_t zkey_len, int rank, int nranks, zkb_circuit **out) {
+  if (!ctx || !zkey || !out) { set_error("null argument"); return ZKB_ERROR; }
+  if (nranks < 1 || nranks > SHARD_MAX_RANKS || rank < 0 || rank >= nranks) { set_error("bad shard rank"); return ZKB_ERROR; }
+  Circuit *c = nullptr;
+  int rc = load_circuit(&ctx->c, (const uint8_t *)zkey, zkey_len, nullptr, 0, &c, rank, nranks);
+  if (rc) return rc;
+  *out = new zkb_circuit{c};
+  return ZKB_OK;
+}
+// rank 0: the 64-byte CUDA IPC handle of its exchange buffer
+int zkb_shard_export(zkb_circuit *h, void *handle64) {
+  Circuit *c = h->c;
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  if (!c->xbuf) { set_error("not a sharded key"); return ZKB_ERROR; }
+  cudaIpcMemHandle_t mh;
+  CKR(cudaIpcGetMemHandle(&mh, c->xbuf), "ipc export");
+  memcpy(handle64, &mh, 64);
+  return ZKB_OK;
+}
+// ranks > 0: map rank 0's exchange buffer (their partial sums are written there over NVLink)
+int zkb_shard_attach(zkb_circuit *h, const void *handle64) {
+  Circuit *c = h->c;
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  if (!c->xbuf) { set_error("not a sharded key"); return ZKB_ERROR; }
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, handle64, 64);
+  void *p = nullptr;
+  CKR(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess), "ipc open (peer access to rank 0)");
+  c->root_x = reinterpret_cast<ShardSlot *>(p);
+  c->root_is_ipc = true;
+  return ZKB_OK;
+}
+// same process (several contexts): publish straight into the root circuit's buffer
+int zkb_shard_attach_local(zkb_circuit *h, zkb_circuit *root) {
+  Circuit *c = h->c, *r = root->c;
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  if (!c->xbuf || !r->xbuf) { set_error("not a sharded key"); return ZKB_ERROR; }
+  if (c->ctx->device != r->ctx->device) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, c->ctx->device, r->ctx->device);
+    if (!can) { set_error("no peer access between the two GPUs"); return ZKB_ERROR; }
+    cudaError_t e = cudaDeviceEnablePeerAccess(r->ctx->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "enable peer access");
+    cudaGetLastError();
+  }
+  c->root_x = r->xbuf;
+  return ZKB_OK;
+}
+
 void zkb_circuit_destroy(zkb_circuit *h) {
   if (!h) return;
   destroy_circuit(h->c);
@@ -790,7 +954,7 @@ int zkb_batch_set_inputs(zkb_circuit *h, int n, const void *inputs) {
   int rc = ensure_workspace(c, (uint32_t)n, chunk);
   if (rc) return rc;
   CKR(cudaMemcpyAsync(c->inputs, inputs, (size_t)n * c->L.n_inputs * 32, cudaMemcpyHostToDevice, c->ctx->stream), "h2d inputs");
-  fill_blinding(c, n);
+  if (!fill_blinding(c, n)) return ZKB_ERROR;
   CKR(cudaMemcpyAsync(c->rs, c->h_rs, (size_t)n * 64, cudaMemcpyHostToDevice, c->ctx->stream), "h2d rs");
   CKR(cudaStreamSynchronize(c->ctx->stream), "sync");
   return ZKB_OK;
@@ -1045,6 +1209,24 @@ int zkb_prove_wtns_stages(zkb_circuit *h, const void *wtns, size_t wtns_size, ch
                           char *public_buf, size_t *public_size, float *stage_ms) {
   Circuit *c = h->c;
   const uint8_t *b = (const uint8_t *)wtns;
+  const bool resident = wtns == nullptr;   // NULL: prove again from the witness already on the device (measurement aid)
+  if (resident) {
+    if (!c->wtns) { set_error("no witness resident on the device yet"); return ZKB_ERROR; }
+    std::lock_guard<std::mutex> g(c->mu);
+    CKR(cudaSetDevice(c->ctx->device), "set device");
+    if (c->shard_n > 1) CKR(cudaMemsetAsync(c->status, 0, 4, c->ctx->stream), "memset status");
+    int rc = prove_group(c, 1, false, stage_ms);
+    if (rc) return rc;
+    if (c->shard_n > 1) {
+      int stt = 0;
+      CKR(cudaMemcpy(&stt, c->status, 4, cudaMemcpyDeviceToHost), "d2h status");
+      if (stt == 7) { set_error("sharded prove: timed out waiting for a peer's partial sums"); return ZKB_ERROR; }
+      if (c->shard_rank != 0) { if (proof_size) *proof_size = 0; if (public_size) *public_size = 0; return ZKB_OK; }
+    }
+    std::string pj = proof_to_json(c->h_out, false), sj = publics_to_json(c->h_out + 256, c->n_public);
+    int r1 = copy_out(pj, proof_buf, proof_size), r2 = copy_out(sj, public_buf, public_size);
+    return (r1 || r2) ? ZKB_SHORT_BUFFER : ZKB_OK;
+  }
   if (wtns_size < 12 || memcmp(b, "wtns", 4) != 0) { set_error("wtns: bad magic"); return ZKB_ERROR; }
   uint32_t nsec;
   memcpy(&nsec, b + 8, 4);
@@ -1069,7 +1251,20 @@ int zkb_prove_wtns_stages(zkb_circuit *h, const void *wtns, size_t wtns_size, ch
   int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : default_chunk(c));
   if (rc) return rc;
   CKR(cudaMemcpyAsync(c->wtns, data, (size_t)nw * 32, cudaMemcpyHostToDevice, c->ctx->stream), "h2d witness");
+  if (c->shard_n > 1) CKR(cudaMemsetAsync(c->status, 0, 4, c->ctx->stream), "memset status");
   if ((rc = prove_group(c, 1, false, stage_ms))) return rc;
+  if (c->shard_n > 1) {
+    int stt = 0;
+    CKR(cudaMemcpy(&stt, c->status, 4, cudaMemcpyDeviceToHost), "d2h status");
+    if (stt == 7) { set_error("sharded prove: timed out waiting for a peer's partial sums"); return ZKB_ERROR; }
+    if (c->shard_rank != 0) {                            // only rank 0 assembles and returns the proof
+      if (proof_size) *proof_size = 0;
+      if (public_size) *public_size = 0;
+      if (proof_buf) proof_buf[0] = 0;
+      if (public_buf) public_buf[0] = 0;
+      return ZKB_OK;
+    }
+  }
   std::string pj = proof_to_json(c->h_out, false), sj = publics_to_json(c->h_out + 256, c->n_public);
   int r1 = copy_out(pj, proof_buf, proof_size), r2 = copy_out(sj, public_buf, public_size);
   return (r1 || r2) ? ZKB_SHORT_BUFFER : ZKB_OK;

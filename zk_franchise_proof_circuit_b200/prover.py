@@ -35,6 +35,10 @@ def _lib():
         L.zkb_ctx_stream.argtypes = [_vp]
         L.zkb_ctx_stream.restype = _vp
         L.zkb_load_circuit.argtypes = [_vp, _vp, _sz, _vp, _sz, ctypes.POINTER(_vp)]
+        L.zkb_load_circuit_shard.argtypes = [_vp, _vp, _sz, _i32, _i32, ctypes.POINTER(_vp)]
+        L.zkb_shard_export.argtypes = [_vp, _vp]
+        L.zkb_shard_attach.argtypes = [_vp, _vp]
+        L.zkb_shard_attach_local.argtypes = [_vp, _vp]
         L.zkb_circuit_destroy.argtypes = [_vp]
         L.zkb_circuit_info.argtypes = [_vp, _vp]
         L.zkb_set_blinding.argtypes = [_vp, _vp, _vp]
@@ -87,17 +91,34 @@ class Context:
 class Circuit:
     """A proving key + witness calculator loaded onto the GPU (zkb_load_circuit)."""
 
-    def __init__(self, ctx: Context, zkey: bytes, wasm: bytes = None):
+    def __init__(self, ctx: Context, zkey: bytes, wasm: bytes = None, shard=None):
+        """shard = (rank, nranks): keep only this rank's point ranges of the key (zkb_load_circuit_shard)."""
         self.ctx = ctx
         self.h = _vp()
+        self.shard = shard
         zb = (ctypes.c_char * len(zkey)).from_buffer_copy(zkey)
         wb = (ctypes.c_char * len(wasm)).from_buffer_copy(wasm) if wasm else None
-        _native.check(_lib().zkb_load_circuit(ctx.h, ctypes.addressof(zb), len(zkey),
-                                              ctypes.addressof(wb) if wasm else None, len(wasm) if wasm else 0,
-                                              ctypes.byref(self.h)))
+        if shard:
+            _native.check(_lib().zkb_load_circuit_shard(ctx.h, ctypes.addressof(zb), len(zkey), shard[0], shard[1],
+                                                        ctypes.byref(self.h)))
+        else:
+            _native.check(_lib().zkb_load_circuit(ctx.h, ctypes.addressof(zb), len(zkey),
+                                                  ctypes.addressof(wb) if wasm else None, len(wasm) if wasm else 0,
+                                                  ctypes.byref(self.h)))
         info = np.zeros(8, dtype=np.uint32)
         _lib().zkb_circuit_info(self.h, info.ctypes.data)
         self.n_vars, self.n_public, self.domain, self.n_inputs, self.n_levels1 = (int(x) for x in info[:5])
+
+    def shard_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        _native.check(_lib().zkb_shard_export(self.h, buf))
+        return buf.raw
+
+    def shard_attach(self, handle: bytes):
+        _native.check(_lib().zkb_shard_attach(self.h, ctypes.create_string_buffer(handle, 64)))
+
+    def shard_attach_local(self, root: "Circuit"):
+        _native.check(_lib().zkb_shard_attach_local(self.h, root.h))
 
     def close(self):
         if self.h:
@@ -148,12 +169,14 @@ class Circuit:
         return buf.raw[:n.value]
 
     def prove_wtns(self, wtns: bytes, stages=False):
-        """Groth16 from a .wtns (go-rapidsnark Groth16ProverRaw).  stages=True also returns the 8 device stage times."""
+        """Groth16 from a .wtns (go-rapidsnark Groth16ProverRaw).  stages=True also returns the 8 device stage times.
+        wtns=None proves again from the witness already resident on the device."""
         pbuf, qbuf = ctypes.create_string_buffer(1024), ctypes.create_string_buffer(2048)
         pn, qn = ctypes.c_size_t(1024), ctypes.c_size_t(2048)
-        wb = (ctypes.c_char * len(wtns)).from_buffer_copy(wtns)
+        wb = (ctypes.c_char * len(wtns)).from_buffer_copy(wtns) if wtns is not None else None
         st = np.zeros(8, dtype=np.float32)
-        _native.check(_lib().zkb_prove_wtns_stages(self.h, wb, len(wtns), pbuf, ctypes.byref(pn), qbuf, ctypes.byref(qn),
+        _native.check(_lib().zkb_prove_wtns_stages(self.h, wb, len(wtns) if wtns is not None else 0, pbuf,
+                                                   ctypes.byref(pn), qbuf, ctypes.byref(qn),
                                                    st.ctypes.data if stages else None))
         out = (pbuf.raw[:pn.value], qbuf.raw[:qn.value])
         return out + (st,) if stages else out
@@ -266,6 +289,11 @@ def load(zkey: bytes, wasm: bytes = None, device=None) -> Circuit:
     if key not in _circuits:
         _circuits[key] = Circuit(_context(device), zkey, wasm)
     return _circuits[key]
+
+
+def load_shard(zkey: bytes, rank: int, nranks: int, device=None) -> Circuit:
+    """One rank's share of a key sharded by point range over nranks GPUs (not cached)."""
+    return Circuit(_context(device), zkey, None, shard=(rank, nranks))
 
 
 def prove(zkey: bytes, wasm: bytes, inputs: bytes) -> Proof:
