@@ -242,6 +242,9 @@ struct OsRandom {
 struct Lane {
   cudaStream_t st = nullptr;
   cudaEvent_t done = nullptr;
+  // small batches (latency): the witness-side MSMs run on two side streams beside the H pipeline
+  cudaStream_t sW = nullptr, s2 = nullptr;
+  cudaEvent_t e_fork = nullptr, e_sortW = nullptr, e_W = nullptr, e_2 = nullptr;
   Fr *abc = nullptr, *hs = nullptr, *dw = nullptr, *stage = nullptr;
   MsmSort sortW, sortH;
   MsmWork<Fq> work1, workH;
@@ -375,6 +378,10 @@ static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
     if (!ln.st) {
       CKR(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking), "lane stream");
       CKR(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming), "lane event");
+      CKR(cudaStreamCreateWithFlags(&ln.sW, cudaStreamNonBlocking), "lane side stream");
+      CKR(cudaStreamCreateWithFlags(&ln.s2, cudaStreamNonBlocking), "lane side stream");
+      for (cudaEvent_t *e : {&ln.e_fork, &ln.e_sortW, &ln.e_W, &ln.e_2})
+        CKR(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "lane event");
     }
     CKR(cudaMalloc(&ln.abc, (size_t)chunk * 3 * c->domain * 32), "alloc abc");
     CKR(cudaMalloc(&ln.hs, (size_t)chunk * c->domain * 32), "alloc h");
@@ -416,47 +423,79 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
   if (with_witness) { int rc = run_witness(c, ln, first, m, st); if (rc) return rc; }
   if (ev) cudaEventRecord(ev[1], st);
   const Fr *w = c->wtns + (size_t)first * c->n_vars;
-  dim3 g1((c->domain + 127) / 128, m);
-  k_build_abc<<<g1, 128, 0, st>>>(c->csrA, c->csrB, c->row_order, w, c->n_vars, ln.abc, c->domain);
-  g_launches += 1 + 4 + 1;   // build_abc, 2 DIF + 2 DIT passes, join
-  if (ev) cudaEventRecord(ev[2], st);
-  CKR(c->ntt.dif(ln.abc, 3 * m, c->domain, true, true, st), "ntt dif");
-  CKR(c->ntt.dit(ln.abc, 3 * m, c->domain, false, st), "ntt dit");
-  dim3 g2((c->domain + 255) / 256, m);
-  k_join<<<g2, 256, 0, st>>>(ln.abc, ln.hs, c->domain);
-  if (ev) cudaEventRecord(ev[3], st);
-  k_witness_diff<<<dim3((c->n_vars + 255) / 256, m), 256, 0, st>>>(w, c->n_vars, c->tconst1 ? c->tmpl : nullptr, ln.dw, c->n_pad, c->n_vars);
-  g_launches += 1;
   // batch item p * sub + s = point range s of proof p (sub = 1: one item per proof)
   // (a sharded key proves one proof at a time and only sorts / sums its own ranges [lo, lo + cnt))
   const uint32_t sW = c->cntW, sH = c->cntH;
   const bool splitW = c->subW > 1, splitH = c->subH > 1;
   const size_t strW = splitW ? (size_t)c->cfgW.windows * c->nsubW : 0, strH = splitH ? (size_t)c->cfgH.windows * c->nsubH : 0;
   if (c->shard_n > 1 && m != 1) { set_error("a sharded key proves one witness per call"); return ZKB_ERROR; }
-  CKR(ln.sortW.run(ln.dw + (size_t)c->loW * c->nsubW, c->nsubW, m * sW, st), "sort witness digits");
-  CKR(ln.sortH.run(ln.hs + (size_t)c->loH * c->nsubH, c->nsubH, m * sH, st), "sort h digits");
-  if (ev) cudaEventRecord(ev[4], st);
-  // bucket sums: G1 over the witness difference (A, B1, C share one sort), H over h, G2 (B2) over the witness difference
   MsmTable<Fq> tabs[3] = {c->tabA, c->tabB1, c->tabC};
-  CKR(msm_accumulate<Fq>(ln.sortW, tabs, 3, m * sW, ln.work1, 0, st, strW, sW), "msm accumulate g1 (A,B1,C)");
-  CKR(msm_accumulate<Fq>(ln.sortH, &c->tabH, 1, m * sH, ln.workH, 0, st, strH, sH), "msm accumulate g1 (H)");
-  if (ev) cudaEventRecord(ev[5], st);
-  CKR(msm_accumulate<Fq2>(ln.sortW, &c->tabB2, 1, m * sW, ln.work2, 0, st, strW, sW), "msm accumulate g2 (B2)");
-  if (ev) cudaEventRecord(ev[6], st);
   XYZZ<Fq> *outW = splitW ? ln.g1raw : ln.g1out;
   XYZZ<Fq> *outH = splitH ? ln.g1raw + (size_t)3 * c->chunk * c->subW : ln.g1out + (size_t)3 * c->chunk;
   XYZZ<Fq2> *out2 = splitW ? ln.g2raw : ln.g2out;
-  CKR(msm_reduce<Fq>(ln.work1, 0, 3 * m * sW, outW, st), "msm reduce g1");
-  CKR(msm_reduce<Fq>(ln.workH, 0, m * sH, outH, st), "msm reduce g1 (H)");
-  CKR(msm_reduce<Fq2>(ln.work2, 0, m * sW, out2, st), "msm reduce g2");
-  if (splitW) {
-    CKR(msm_fold_subs<Fq>(outW, ln.g1out, m, sW, 3, st), "fold g1 ranges");
-    CKR(msm_fold_subs<Fq2>(out2, ln.g2out, m, sW, 1, st), "fold g2 ranges");
-    g_launches += 2;
-  }
-  if (splitH) {
-    CKR(msm_fold_subs<Fq>(outH, ln.g1out + (size_t)3 * c->chunk, m, sH, 1, st), "fold g1 (H) ranges");
+  dim3 g1((c->domain + 127) / 128, m);
+  dim3 g2((c->domain + 255) / 256, m);
+  static const uint32_t fork_max = env_u32("ZKB_FORK_MAX", 32);
+  if (!ev && m <= fork_max) {
+    // Latency shape: after the witness, three independent pipelines.  st: A/B/C vectors -> coset transforms -> h ->
+    // H MSM.  sW: witness difference -> digit sort -> A, B1, C sums.  s2: (after that sort) the G2 sum.
+    cudaEventRecord(ln.e_fork, st);
+    cudaStreamWaitEvent(ln.sW, ln.e_fork, 0);
+    cudaStreamWaitEvent(ln.s2, ln.e_fork, 0);
+    k_witness_diff<<<dim3((c->n_vars + 255) / 256, m), 256, 0, ln.sW>>>(w, c->n_vars, c->tconst1 ? c->tmpl : nullptr, ln.dw, c->n_pad, c->n_vars);
+    CKR(ln.sortW.run(ln.dw + (size_t)c->loW * c->nsubW, c->nsubW, m * sW, ln.sW), "sort witness digits");
+    cudaEventRecord(ln.e_sortW, ln.sW);
+    cudaStreamWaitEvent(ln.s2, ln.e_sortW, 0);
+    CKR(msm_accumulate<Fq2>(ln.sortW, &c->tabB2, 1, m * sW, ln.work2, 0, ln.s2, strW, sW), "msm accumulate g2 (B2)");
+    CKR(msm_reduce<Fq2>(ln.work2, 0, m * sW, out2, ln.s2), "msm reduce g2");
+    if (splitW) CKR(msm_fold_subs<Fq2>(out2, ln.g2out, m, sW, 1, ln.s2), "fold g2 ranges");
+    cudaEventRecord(ln.e_2, ln.s2);
+    CKR(msm_accumulate<Fq>(ln.sortW, tabs, 3, m * sW, ln.work1, 0, ln.sW, strW, sW), "msm accumulate g1 (A,B1,C)");
+    CKR(msm_reduce<Fq>(ln.work1, 0, 3 * m * sW, outW, ln.sW), "msm reduce g1");
+    if (splitW) CKR(msm_fold_subs<Fq>(outW, ln.g1out, m, sW, 3, ln.sW), "fold g1 ranges");
+    cudaEventRecord(ln.e_W, ln.sW);
+    k_build_abc<<<g1, 128, 0, st>>>(c->csrA, c->csrB, c->row_order, w, c->n_vars, ln.abc, c->domain);
+    CKR(c->ntt.dif(ln.abc, 3 * m, c->domain, true, true, st), "ntt dif");
+    CKR(c->ntt.dit(ln.abc, 3 * m, c->domain, false, st), "ntt dit");
+    k_join<<<g2, 256, 0, st>>>(ln.abc, ln.hs, c->domain);
+    CKR(ln.sortH.run(ln.hs + (size_t)c->loH * c->nsubH, c->nsubH, m * sH, st), "sort h digits");
+    CKR(msm_accumulate<Fq>(ln.sortH, &c->tabH, 1, m * sH, ln.workH, 0, st, strH, sH), "msm accumulate g1 (H)");
+    CKR(msm_reduce<Fq>(ln.workH, 0, m * sH, outH, st), "msm reduce g1 (H)");
+    if (splitH) CKR(msm_fold_subs<Fq>(outH, ln.g1out + (size_t)3 * c->chunk, m, sH, 1, st), "fold g1 (H) ranges");
+    cudaStreamWaitEvent(st, ln.e_W, 0);
+    cudaStreamWaitEvent(st, ln.e_2, 0);
+    g_launches += 1 + 4 + 1 + 1 + (splitW ? 2 : 0) + (splitH ? 1 : 0);
+  } else {
+    k_build_abc<<<g1, 128, 0, st>>>(c->csrA, c->csrB, c->row_order, w, c->n_vars, ln.abc, c->domain);
+    g_launches += 1 + 4 + 1;   // build_abc, 2 DIF + 2 DIT passes, join
+    if (ev) cudaEventRecord(ev[2], st);
+    CKR(c->ntt.dif(ln.abc, 3 * m, c->domain, true, true, st), "ntt dif");
+    CKR(c->ntt.dit(ln.abc, 3 * m, c->domain, false, st), "ntt dit");
+    k_join<<<g2, 256, 0, st>>>(ln.abc, ln.hs, c->domain);
+    if (ev) cudaEventRecord(ev[3], st);
+    k_witness_diff<<<dim3((c->n_vars + 255) / 256, m), 256, 0, st>>>(w, c->n_vars, c->tconst1 ? c->tmpl : nullptr, ln.dw, c->n_pad, c->n_vars);
     g_launches += 1;
+    CKR(ln.sortW.run(ln.dw + (size_t)c->loW * c->nsubW, c->nsubW, m * sW, st), "sort witness digits");
+    CKR(ln.sortH.run(ln.hs + (size_t)c->loH * c->nsubH, c->nsubH, m * sH, st), "sort h digits");
+    if (ev) cudaEventRecord(ev[4], st);
+    // bucket sums: G1 over the witness difference (A, B1, C share one sort), H over h, G2 (B2) over the witness difference
+    CKR(msm_accumulate<Fq>(ln.sortW, tabs, 3, m * sW, ln.work1, 0, st, strW, sW), "msm accumulate g1 (A,B1,C)");
+    CKR(msm_accumulate<Fq>(ln.sortH, &c->tabH, 1, m * sH, ln.workH, 0, st, strH, sH), "msm accumulate g1 (H)");
+    if (ev) cudaEventRecord(ev[5], st);
+    CKR(msm_accumulate<Fq2>(ln.sortW, &c->tabB2, 1, m * sW, ln.work2, 0, st, strW, sW), "msm accumulate g2 (B2)");
+    if (ev) cudaEventRecord(ev[6], st);
+    CKR(msm_reduce<Fq>(ln.work1, 0, 3 * m * sW, outW, st), "msm reduce g1");
+    CKR(msm_reduce<Fq>(ln.workH, 0, m * sH, outH, st), "msm reduce g1 (H)");
+    CKR(msm_reduce<Fq2>(ln.work2, 0, m * sW, out2, st), "msm reduce g2");
+    if (splitW) {
+      CKR(msm_fold_subs<Fq>(outW, ln.g1out, m, sW, 3, st), "fold g1 ranges");
+      CKR(msm_fold_subs<Fq2>(out2, ln.g2out, m, sW, 1, st), "fold g2 ranges");
+      g_launches += 2;
+    }
+    if (splitH) {
+      CKR(msm_fold_subs<Fq>(outH, ln.g1out + (size_t)3 * c->chunk, m, sH, 1, st), "fold g1 (H) ranges");
+      g_launches += 1;
+    }
   }
   if (c->shard_n > 1) {
     c->epoch++;
@@ -795,7 +834,11 @@ static void destroy_circuit(Circuit *c) {
   if (c->h_status) cudaFreeHost(c->h_status);
   for (int i = 0; i < MAX_LANES; i++) {
     c->lanes[i].free_all();
-    if (c->lanes[i].st) { cudaStreamDestroy(c->lanes[i].st); cudaEventDestroy(c->lanes[i].done); }
+    if (c->lanes[i].st) {
+      Lane &ln = c->lanes[i];
+      cudaStreamDestroy(ln.st); cudaStreamDestroy(ln.sW); cudaStreamDestroy(ln.s2);
+      for (cudaEvent_t e : {ln.done, ln.e_fork, ln.e_sortW, ln.e_W, ln.e_2}) cudaEventDestroy(e);
+    }
   }
   delete c;
 }
