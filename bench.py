@@ -255,14 +255,21 @@ def run_ours(args, rank, world, local_rank):
     madds_g1 = work["g1_madds_per_proof"] * batch
     acc_g1_s = stages[4] * 1e-3
     achieved = madds_g1 * MODMUL_PER_MADD_G1 / acc_g1_s if acc_g1_s > 0 else 0.0
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (tools/ncu_summary.py --raw)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes")
     roofline = {"bound": "imad", "kernel": "k_accumulate<Fq> (G1 bucket accumulation, XYZZ mixed adds)",
                 "achieved": achieved / 1e9, "peak": peak_modmul / 1e9, "unit": "Gmodmul/s",
-                "frac": achieved / peak_modmul if peak_modmul else None, "traffic": None,
+                "frac": achieved / peak_modmul if peak_modmul else None, "traffic": traffic,
                 "peak_source": "measured in this run: zkb_bench_modmul (dependent 254-bit Montgomery products, "
                                "137 IMAD.WIDE each); MEASURED_PEAKS.json has no integer-pipe figure",
                 "share_of_step": float(stages[4] / stages.sum()) if stages.sum() else None,
                 "measured_in": "instrumented serial pass (1 lane) over the same K steps, CUDA events on the launching "
                                "stream; the timed loop overlaps chunks on 2 streams",
+                "traffic_note": "dram__bytes_read+write of the largest k_accumulate<Fq> launch (H MSM of one 128-proof chunk: "
+                                "128 x 2.1 M gathered 64-byte table points = 17.2 GB algorithmic) from profiles/r01_traffic.json",
                 "hbm_gbs_measured": measured_peaks().get("hbm_gbs")}
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
     cpu = None

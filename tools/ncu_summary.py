@@ -58,6 +58,43 @@ def full_summary(rep):
                 print(f"  {k:85s} {d[k]:>16s} {units[hdr.index(k)]}")
 
 
+def raw_summary(path, traffic_json=None):
+    """`ncu -i rep --page raw --csv` export (made on the GPU box when the .ncu-rep is too large to bring back):
+    the same metric digest, plus - with traffic_json - the DRAM traffic per launch of the dominant kernel
+    (the largest k_accumulate<Fq> launch) for bench.py's roofline.traffic."""
+    import json
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    print(f"# ncu --set full capture, raw page export {path}")
+    best = None
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        print("kernel:", d.get("Kernel Name", "?")[:110], "grid", d.get("launch__grid_size"))
+        for k in KEYS:
+            if k in d:
+                print(f"  {k:85s} {d[k]:>16s} {units[hdr.index(k)]}")
+        if "k_accumulate<Fp<FqParams>" in d.get("Kernel Name", "") or "k_accumulate<zkb::Fp<zkb::FqParams>" in d.get("Kernel Name", ""):
+            g = int(float(d["launch__grid_size"]))
+            if best is None or g > best[0]:
+                best = (g, d)
+    if traffic_json and best:
+        d = best[1]
+
+        def to_bytes(key):
+            v, u = float(d[key]), units[hdr.index(key)].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}[u]
+        out = {"kernel": "k_accumulate<Fq> (H MSM launch of one 128-proof chunk)", "grid_blocks": best[0],
+               "dram_bytes_read": to_bytes("dram__bytes_read.sum"), "dram_bytes_write": to_bytes("dram__bytes_write.sum"),
+               "duration_ms_under_ncu": float(d["gpu__time_duration.sum"]), "source": path}
+        out["dram_bytes"] = out["dram_bytes_read"] + out["dram_bytes_write"]
+        json.dump(out, open(traffic_json, "w"), indent=1)
+        print("# traffic ->", traffic_json, out)
+
+
 if __name__ == "__main__":
-    for a in sys.argv[1:]:
-        (full_summary if a.endswith(".ncu-rep") else launch_summary)(a)
+    args = sys.argv[1:]
+    if args and args[0] == "--raw":
+        raw_summary(args[1], args[2] if len(args) > 2 else None)
+    else:
+        for a in args:
+            (full_summary if a.endswith(".ncu-rep") else launch_summary)(a)

@@ -145,11 +145,15 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t *counts, uint32_t 
 // order[b][i] = bucket ids of batch item b sorted by descending size (counting sort on the size, sizes >= 1023
 // share the first bin).  The accumulate kernel walks buckets in this order, so the 32 lanes of a warp get lists of
 // (nearly) equal length and the longest lists start first.
-static constexpr uint32_t LONG_BUCKET = 128;   // lists longer than this are summed by a whole warp
-static constexpr uint32_t MAX_LONG = 256;      // at most this many per batch item (the rest stay with one thread)
+// Lists longer than `long_bucket` are summed by a whole warp, at most `max_long` of them per batch item (the rest
+// stay with one thread).  Throughput shape (many batch items): 128 / 256 - only the pathological lists.  Latency
+// shape (fewer than 2^18 buckets in the launch): 24 / 2048 - a warp costs 5 extra full additions for its shuffle fold but the longest serial
+// chain drops from 128 mixed adds to ~1.
+static constexpr uint32_t LONG_BUCKET = 128, MAX_LONG = 256;
+static constexpr uint32_t LONG_BUCKET_LAT = 24, MAX_LONG_LAT = 2048;
 
 __global__ void __launch_bounds__(1024) k_order(const uint32_t *counts, uint32_t *order, uint32_t *n_long,
-                                                uint32_t buckets) {
+                                                uint32_t buckets, uint32_t long_bucket, uint32_t max_long) {
   __shared__ uint32_t hist[1024];
   const uint32_t b = blockIdx.x, t = threadIdx.x;
   const uint32_t *c = counts + (size_t)b * buckets;
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(1024) k_order(const uint32_t *counts, uint32_t
   __syncthreads();
   hist[t] = wt[t >> 5] + x - v;
   __syncthreads();
-  if (t == 1023u - LONG_BUCKET) n_long[b] = min(hist[t], MAX_LONG);   // buckets in bins before t: size > LONG_BUCKET
+  if (t == 1023u - long_bucket) n_long[b] = min(hist[t], max_long);   // buckets in bins before t: size > long_bucket
   __syncthreads();
   uint32_t *o = order + (size_t)b * buckets;
   for (uint32_t i = t; i < buckets; i += 1024) {
@@ -215,7 +219,10 @@ cudaError_t MsmSort::run(const Fr *scalars, size_t scalar_stride, uint32_t nbatc
   dim3 grid((n + 255) / 256, nbatch);
   k_digits<false><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cfg.c, cfg.windows, cfg.buckets, counts, nullptr);
   k_scan<<<nbatch, 1024, 0, st>>>(counts, offsets, cursor, cfg.buckets);
-  k_order<<<nbatch, 1024, 0, st>>>(counts, order, n_long, cfg.buckets);
+  const bool lat = (uint64_t)nbatch * cfg.buckets < 262144;   // fewer bucket threads than ~1 wave of the GPU
+  max_long = lat ? MAX_LONG_LAT : MAX_LONG;
+  if (max_long > cfg.buckets / 2) max_long = cfg.buckets / 2;
+  k_order<<<nbatch, 1024, 0, st>>>(counts, order, n_long, cfg.buckets, lat ? LONG_BUCKET_LAT : LONG_BUCKET, max_long);
   k_digits<true><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cfg.c, cfg.windows, cfg.buckets, cursor, entries);
   return cudaGetLastError();
 }
@@ -478,7 +485,7 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
     }
   }
 #undef ZKB_ACC
-  dim3 glong(MAX_LONG, ntab, nbatch);
+  dim3 glong(sort.max_long, ntab, nbatch);
   k_accumulate_long<F><<<glong, 32, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order,
                                              sort.n_long, dst, tab_batch_stride, tab_mod);
   return cudaGetLastError();

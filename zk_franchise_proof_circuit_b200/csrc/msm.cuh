@@ -41,6 +41,7 @@ struct MsmSort {
   uint32_t *entries = nullptr;  // [batch][n * windows]
   uint32_t *order = nullptr;    // [batch][buckets]      bucket ids by descending size
   uint32_t *n_long = nullptr;   // [batch]               how many leading buckets of `order` a whole warp sums
+  uint32_t max_long = 256;      // upper bound of n_long for the last run (grid of the warp-per-bucket kernel)
   cudaError_t alloc(uint32_t n, uint32_t batch, MsmCfg cfg);
   void free_all();
   // scalars: [batch] vectors of n canonical 256-bit values, `scalar_stride` elements apart
