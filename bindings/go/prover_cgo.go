@@ -1,0 +1,79 @@
+// cgo binding of libzkcensus_b200 for go.vocdoni.io/dvote/crypto/zk/prover: replaces the body of prover.Prove
+// (called at zk_census_test.go:89 of vocdoni/zk-franchise-proof-circuit).  Proof, ParseProof and (*Proof).Bytes stay
+// as they are in that package.  NOT compiled in this repository's image (no Go toolchain); the same C entry points
+// are exercised through ctypes in tests/test_gpu_prover.py.  See INTEGRATION.md section 1.
+package prover
+
+/*
+#cgo LDFLAGS: -L${SRCDIR}/lib -lzkcensus_b200 -lcudart
+#include <stdlib.h>
+#include "zkcensus_b200.h"
+*/
+import "C"
+
+import (
+	"crypto/sha256"
+	"fmt"
+	"sync"
+	"unsafe"
+)
+
+var (
+	mu       sync.Mutex
+	ctx      *C.zkb_ctx
+	circuits = map[[32]byte]*C.zkb_circuit{} // keyed by sha256(zkey)||sha256(wasm)
+)
+
+func circuitFor(zkey, wasm []byte) (*C.zkb_circuit, error) {
+	mu.Lock()
+	defer mu.Unlock()
+	if ctx == nil {
+		if rc := C.zkb_ctx_create(0, &ctx); rc != 0 {
+			return nil, fmt.Errorf("zkb_ctx_create: %s", C.GoString(C.zkb_last_error()))
+		}
+	}
+	h := sha256.Sum256(append(append([]byte{}, sha256sum(zkey)...), sha256sum(wasm)...))
+	if c, ok := circuits[h]; ok {
+		return c, nil
+	}
+	var c *C.zkb_circuit
+	rc := C.zkb_load_circuit(ctx, unsafe.Pointer(&zkey[0]), C.size_t(len(zkey)),
+		unsafe.Pointer(&wasm[0]), C.size_t(len(wasm)), &c)
+	if rc != 0 {
+		return nil, fmt.Errorf("zkb_load_circuit (%d): %s", rc, C.GoString(C.zkb_last_error()))
+	}
+	circuits[h] = c
+	return c, nil
+}
+
+// Prove keeps the signature used at zk_census_test.go:89.
+func Prove(zkey, wasm, inputs []byte) (*Proof, error) {
+	c, err := circuitFor(zkey, wasm)
+	if err != nil {
+		return nil, err
+	}
+	proofBuf := make([]byte, 1024)
+	pubBuf := make([]byte, 2048)
+	errBuf := make([]byte, 256)
+	pn, qn := C.size_t(len(proofBuf)), C.size_t(len(pubBuf))
+	rc := C.zkb_fullprove(c, (*C.char)(unsafe.Pointer(&inputs[0])), C.size_t(len(inputs)),
+		(*C.char)(unsafe.Pointer(&proofBuf[0])), &pn, (*C.char)(unsafe.Pointer(&pubBuf[0])), &qn,
+		(*C.char)(unsafe.Pointer(&errBuf[0])), C.size_t(len(errBuf)))
+	if rc != 0 { // 4 = circuit assert failed (the wasm's exceptionHandler(4))
+		return nil, fmt.Errorf("prove (%d): %s", rc, C.GoString((*C.char)(unsafe.Pointer(&errBuf[0]))))
+	}
+	return ParseProof(proofBuf[:pn], pubBuf[:qn]) // unchanged: zk_census_test.go:118
+}
+
+func sha256sum(b []byte) []byte { h := sha256.Sum256(b); return h[:] }
+
+// Verify runs the Groth16 pairing check on the GPU ((*Proof).Verify at zk_census_test.go:122).
+func Verify(vkey, pubSignals, proof []byte) error {
+	rc := C.zkb_verify((*C.char)(unsafe.Pointer(&vkey[0])), C.size_t(len(vkey)),
+		(*C.char)(unsafe.Pointer(&pubSignals[0])), C.size_t(len(pubSignals)),
+		(*C.char)(unsafe.Pointer(&proof[0])), C.size_t(len(proof)))
+	if rc != 0 {
+		return fmt.Errorf("verify (%d): %s", rc, C.GoString(C.zkb_last_error()))
+	}
+	return nil
+}

@@ -1,0 +1,14 @@
+// Types of the zkcensus_b200 addon: the subset of snarkjs' groth16 namespace the reference uses
+// (ts_inputs/src/example.ts:358-362).
+export interface Groth16Proof {
+  pi_a: string[];
+  pi_b: string[][];
+  pi_c: string[];
+  protocol: "groth16";
+  curve: "bn128";
+}
+export function fullProve(
+  inputs: Record<string, unknown> | string,
+  wasmPath: string,
+  zkeyPath: string
+): Promise<{ proof: Groth16Proof; publicSignals: string[] }>;
