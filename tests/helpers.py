@@ -57,3 +57,33 @@ def wtns_payload(wtns: bytes, n_vars: int) -> np.ndarray:
 
 def sha(b) -> str:
     return hashlib.sha256(bytes(b)).hexdigest()
+
+
+@functools.lru_cache(maxsize=None)
+def deep_voters():
+    """Maximum-depth census (checker side): 160 leaves whose addresses are `base` with one bit flipped, plus `base`
+    itself, so that base's Merkle path has a NON-ZERO sibling at every one of the 160 levels (the circuit's limit:
+    siblings[160] must be zero, census.circom:79-103 / SMTLevIns).  Returns inputs for `base` (depth 160), for the
+    leaf that splits off at level 0 (depth 1) and for the one that splits off at level 80 (depth 81)."""
+    G = census_gen
+    Hh = G.Poseidon(poseidon_tables())
+    base = int.from_bytes(hashlib.sha256(b"deep-census").digest()[:20], "little")
+    addrs = [base] + [base ^ (1 << j) for j in range(160)]
+    password = int.from_bytes(b"password123", "big") % G.P
+    election = G.bytes_to_arbo(bytes.fromhex(G.ELECTION_HEX))
+    vote_hash = G.bytes_to_arbo((10).to_bytes(1, "big"))
+    sigs = {a: int.from_bytes(hashlib.sha256(b"sig" + a.to_bytes(20, "little")).digest() * 2, "big") % G.P for a in addrs}
+    siks = {a: Hh([a, password, sigs[a]]) for a in addrs}
+    census = G.SMT(Hh, {a: 10 for a in addrs})
+    siktree = G.SMT(Hh, siks)
+    out = []
+    for a in (base, base ^ 1, base ^ (1 << 80)):
+        pad = lambda s: [str(x) for x in s] + ["0"] * (161 - len(s))
+        out.append({
+            "electionId": [str(election[0]), str(election[1])],
+            "nullifier": str(Hh([sigs[a], password, election[0], election[1]])),
+            "availableWeight": "10", "voteHash": [str(vote_hash[0]), str(vote_hash[1])],
+            "sikRoot": str(siktree.root), "censusRoot": str(census.root), "address": str(a),
+            "password": str(password), "signature": str(sigs[a]), "voteWeight": "5",
+            "censusSiblings": pad(census.siblings(a)), "sikSiblings": pad(siktree.siblings(a))})
+    return out

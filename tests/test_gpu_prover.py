@@ -318,3 +318,59 @@ def test_sharded_key_two_gpus(tmp_path):
     exp = O.ZKeyRef(zkey).prove(H.wtns_payload(wtns, n_wires), H.R_FIXED, H.S_FIXED)
     pj, sj = _sharded_proof(zkey, wtns, 2, [0, 1])
     assert O.proof_bin(json.loads(pj)) == exp
+
+
+def test_concurrent_callers(art_dir):
+    """cgo calls arrive on arbitrary OS threads (SURVEY 8b threading): 4 threads x 3 zkb_fullprove calls on one
+    circuit handle; every proof verifies and the public signals are the fixture's."""
+    import threading
+    from zk_franchise_proof_circuit_b200 import prover
+    c = prover.load(open(art_dir + "/proving_key.zkey", "rb").read(), open(art_dir + "/circuit.wasm", "rb").read())
+    doc = open(H.GOLDEN + "/inputs_example.json", "rb").read()
+    vkey = open(art_dir + "/verification_key.json", "rb").read()
+    out, errs = [], []
+
+    def work():
+        try:
+            for _ in range(3):
+                out.append(c.fullprove(doc))
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=work) for _ in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs and len(out) == 12
+    for pj, sj in out:
+        assert json.loads(sj) == json.load(open(H.GOLDEN + "/signals.json"))
+        prover.verify(vkey, sj, pj)
+    assert len({pj for pj, _ in out}) == 12       # fresh blinding every time
+
+
+def test_maximum_depth_census_bit_exact(circuit):
+    """Edge of the circuit: a voter whose path has a non-zero sibling at all 160 levels (no level block equals the
+    per-key template, the witness MSMs see ~80 k differing wires), next to depth-1 and depth-81 voters of the same
+    census.  Witness == reference wasm, A/B/C == CPU oracle with pinned r,s, every proof verifies."""
+    vs = H.deep_voters()
+    assert sum(1 for x in vs[0]["censusSiblings"] if x != "0") == 160
+    assert sum(1 for x in vs[1]["censusSiblings"] if x != "0") == 1
+    circuit.set_blinding(H.R_FIXED, H.S_FIXED)
+    try:
+        proofs, pubs, status = circuit.fullprove_batch([json.dumps(v) for v in vs])
+    finally:
+        circuit.set_blinding(None, None)
+    assert status == [0, 0, 0]
+    for v, pj, sj in zip(vs, proofs, pubs):
+        code, ref = _ref_witness(v)
+        assert code == 0
+        w = H.wtns_payload(circuit.witness(json.dumps(v)), circuit.n_vars)
+        assert np.array_equal(w, ref)
+        proof, pub = json.loads(pj), json.loads(sj)
+        assert O.proof_bin(proof) == H.zkey_ref().prove(ref, H.R_FIXED, H.S_FIXED)
+        assert O.verify(H.dev_vkey(), pub, proof)
+    # one more siblings entry than the circuit allows -> the wasm's assert (code 4), not a proof
+    bad = dict(vs[0])
+    bad["censusSiblings"] = vs[0]["censusSiblings"][:160] + ["1"]
+    assert circuit.fullprove_batch([json.dumps(bad)])[2] == [4]
+    assert _ref_witness(bad)[0] == 4

@@ -18,37 +18,33 @@ __global__ void k_fixed_table(Affine<F> *tab, const Affine<F> *base) {
 }
 
 
-// one CTA of 4 warps per proof, one warp per independent piece, so the four scalar
-// multiplications run on four schedulers instead of serialising as divergent lanes:
-//   warp 0: A = pi_a' + alpha1 + r*delta1, then s*A          warp 1: B1 = pi_b1' + beta1 + s*delta1, then r*B1
-//   warp 2: -(r*s)*delta1 and the public signals             warp 3: B = pi_b' + beta2 + s*delta2   (G2)
-//   then warp 0: C = pi_c' + pi_h + s*A + r*B1 - (r*s)*delta1
+// one CTA of 4 warps per proof, one warp per independent piece, so the scalar multiplications run on
+// four schedulers instead of serialising as divergent lanes.  Two phases keep the affine conversions (one field
+// inversion each) off the longest chain, the variable-base products:
+//   phase 1   warp 0: A = pi_a' + alpha1 + r*delta1      warp 1: B1 = pi_b1' + beta1 + s*delta1
+//             warp 2: -(r*s)*delta1, public signals      warp 3: B = pi_b' + beta2 + s*delta2   (G2)
+//             (warp 3 continues with B -> affine; it does not take part in the phase barrier)
+//   phase 2   warp 0: s*A      warp 1: r*B1      warp 2: A -> affine, then T = -(r*s)*delta1 + pi_c' + pi_h
+//   then      warp 0: C = s*A + r*B1 + T -> affine
 __global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
-  __shared__ XYZZ<Fq> sh[5];          // A, s*A | B1, r*B1 | -(rs)delta1
+  __shared__ XYZZ<Fq> sh[5];          // A, s*A | B1, r*B1 | T
   __shared__ XYZZ<Fq2> shB;
   const uint32_t p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t *out = P.out + (size_t)p * (256 + 32 * P.n_public);
   XYZZ<Fq> *scratch = P.scratch + ((size_t)p * 2) * 15;
+  const Fr r = P.rs[2 * p], s = P.rs[2 * p + 1];
   if (lane == 0) {
-    const Fr r = P.rs[2 * p], s = P.rs[2 * p + 1];
     if (warp == 0) {
       fin_point<Fq>(P.g1 + 3 * p, P.alpha1, P.d1tab, r.v, &sh[0]);
       if (P.tconst1) xyzz_add_ni(&sh[0], P.tconst1);
-      Affine<Fq> a;
-      xyzz_to_affine_ni(&sh[0], &a);
-      Fq x = a.x.from_mont(), y = a.y.from_mont();
-      memcpy(out, x.v, 32);
-      memcpy(out + 32, y.v, 32);
-      var_mul<Fq>(&sh[0], s.v, scratch, &sh[1]);
     } else if (warp == 1) {
       fin_point<Fq>(P.g1 + 3 * p + 1, P.beta1, P.d1tab, s.v, &sh[2]);
       if (P.tconst1) xyzz_add_ni(&sh[2], P.tconst1 + 1);
-      var_mul<Fq>(&sh[2], r.v, scratch + 15, &sh[3]);
     } else if (warp == 2) {
       fin_neg_rs_delta(P.d1tab, r, s, &sh[4]);
       const Fr *w = P.wtns + (size_t)p * P.wtns_stride;
       for (uint32_t i = 0; i < P.n_public; i++) memcpy(out + 256 + 32 * i, w[1 + i].v, 32);
-    } else {
+    } else {                     // the G2 point is the longest phase-1 piece: warp 3 goes straight on to its affine form
       fin_point<Fq2>(P.g2 + p, P.beta2, P.d2tab, s.v, &shB);
       if (P.tconst2) xyzz_add_ni(&shB, P.tconst2);
       Affine<Fq2> b;
@@ -57,14 +53,28 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
       memcpy(out + 64, c, 128);
     }
   }
+  if (warp < 3) asm volatile("bar.sync 1, 96;" ::: "memory");   // warps 0-2 only: A, B1 and -(rs)delta1 are ready
+  if (lane == 0) {
+    if (warp == 0) {
+      var_mul<Fq>(&sh[0], s.v, scratch, &sh[1]);
+    } else if (warp == 1) {
+      var_mul<Fq>(&sh[2], r.v, scratch + 15, &sh[3]);
+    } else if (warp == 2) {
+      Affine<Fq> a;
+      xyzz_to_affine_ni(&sh[0], &a);
+      Fq x = a.x.from_mont(), y = a.y.from_mont();
+      memcpy(out, x.v, 32);
+      memcpy(out + 32, y.v, 32);
+      xyzz_add_ni(&sh[4], P.g1 + 3 * p + 2);
+      xyzz_add_ni(&sh[4], P.g1h + p);
+      if (P.tconst1) xyzz_add_ni(&sh[4], P.tconst1 + 2);
+    }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     // C = pi_c' + pi_h + s*A + r*B1 - (r*s)*delta1, accumulated in sh[1]
     xyzz_add_ni(&sh[1], &sh[3]);
     xyzz_add_ni(&sh[1], &sh[4]);
-    xyzz_add_ni(&sh[1], P.g1 + 3 * p + 2);
-    xyzz_add_ni(&sh[1], P.g1h + p);
-    if (P.tconst1) xyzz_add_ni(&sh[1], P.tconst1 + 2);
     Affine<Fq> c;
     xyzz_to_affine_ni(&sh[1], &c);
     Fq x = c.x.from_mont(), y = c.y.from_mont();

@@ -17,7 +17,8 @@ namespace zkb {
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
-static constexpr int RED_CHUNK = 32;
+// level-1 reduction chunk: 2^5 buckets per thread in batch shape, 2^3 when a launch is small (latency shape)
+static constexpr int RED_LOG = 5, RED_LOG_LAT = 3;
 
 template <class T>
 __device__ __forceinline__ T ldg_pod(const T *p) {
@@ -360,13 +361,13 @@ __global__ void __launch_bounds__(32) k_accumulate_long(TablePtrs<F> tabs, int n
 // level 1: thread = chunk of 32 buckets:  R = sum (u+1) B[32t+u],  S = sum B[32t+u]
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_reduce1(const XYZZ<F> *buckets, XYZZ<F> *part_r, XYZZ<F> *part_s,
-                                                     uint32_t nbuckets) {
+                                                     uint32_t nbuckets, int red_log) {
   uint32_t t = blockIdx.x * THREADS + threadIdx.x;   // chunk
   uint32_t slot = blockIdx.y;
-  const uint32_t parts = nbuckets / RED_CHUNK;
-  const XYZZ<F> *B = buckets + (size_t)slot * nbuckets + (size_t)t * RED_CHUNK;
+  const uint32_t parts = nbuckets >> red_log;
+  const XYZZ<F> *B = buckets + (size_t)slot * nbuckets + ((size_t)t << red_log);
   XYZZ<F> run = XYZZ<F>::infinity(), acc = XYZZ<F>::infinity();
-  for (int u = RED_CHUNK - 1; u >= 0; u--) {
+  for (int u = (1 << red_log) - 1; u >= 0; u--) {
     XYZZ<F> x = ldg_pod(B + u);
     xyzz_add_ni(&run, &x);
     __syncwarp();
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(THREADS) k_reduce1(const XYZZ<F> *buckets, XYZ
   stg_pod(part_s + (size_t)slot * parts + t, run);
 }
 
-// level 2: one CTA of min(parts, 256) threads per slot.  total = sum_t R_t + 32 * sum_t t * S_t: a thread folds its
+// level 2: one CTA of min(parts, 256) threads per slot.  total = sum_t R_t + 2^red_log * sum_t t * S_t: a thread folds its
 // span of parts, forms t * sigma_t by double-and-add over the bits of t, and both sums are folded by a shared-memory
 // tree, so the depth is ~4 log2(threads) group operations instead of a serial pass over the parts.
 template <class F>
@@ -395,10 +396,10 @@ __device__ void block_tree_sum(XYZZ<F> *sm, XYZZ<F> &v, uint32_t t, uint32_t par
 
 template <class F>
 __global__ void __launch_bounds__(256) k_reduce2(const XYZZ<F> *part_r, const XYZZ<F> *part_s, XYZZ<F> *out,
-                                                 uint32_t parts) {
+                                                 uint32_t parts, int red_log) {
   extern __shared__ uint4 sm_raw[];
   XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(sm_raw);
-  const uint32_t slot = blockIdx.x, t = threadIdx.x, nthr = blockDim.x, span = parts / nthr;   // span = 1 or 4
+  const uint32_t slot = blockIdx.x, t = threadIdx.x, nthr = blockDim.x, span = parts / nthr;   // a power of two
   const XYZZ<F> *R = part_r + (size_t)slot * parts + t * span, *S = part_s + (size_t)slot * parts + t * span;
   // own span: r = sum R, sigma = sum S, rho = sum_u u * S_u
   XYZZ<F> r = XYZZ<F>::infinity(), sigma = XYZZ<F>::infinity(), rho = XYZZ<F>::infinity(), x;
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(256) k_reduce2(const XYZZ<F> *part_r, const XY
   __syncthreads();
   block_tree_sum<F>(sm, w, t, nthr);               // thread 0: sum_t t * S_t
   if (t == 0) {
-    for (int i = 0; i < 5; i++) xyzz_dbl_ni(&w);   // * 32 (chunk size)
+    for (int i = 0; i < red_log; i++) xyzz_dbl_ni(&w);   // * chunk size
     xyzz_add_ni(&w, &r);
     stg_pod(out + slot, w);
   }
@@ -496,10 +497,12 @@ template <class F>
 cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F> *out, cudaStream_t st) {
   if (slot0 + nslots > work.slots) return cudaErrorInvalidValue;
   constexpr int RT = AccCfg<F>::RED_THREADS;
-  const uint32_t nb = work.cfg.buckets, parts = work.cfg.parts();
+  const uint32_t nb = work.cfg.buckets;
+  const int red_log = (uint64_t)nslots * nb < 262144 ? RED_LOG_LAT : RED_LOG;
+  const uint32_t parts = nb >> red_log;
   dim3 g1(parts / RT, nslots);
   k_reduce1<F, RT><<<g1, RT, 0, st>>>(work.buckets + (size_t)slot0 * nb, work.part_r + (size_t)slot0 * parts,
-                                      work.part_s + (size_t)slot0 * parts, nb);
+                                      work.part_s + (size_t)slot0 * parts, nb, red_log);
   const uint32_t nthr = parts < 256 ? parts : 256;
   static bool attr_set[64] = {};            // function attributes are per device
   int dev = 0;
@@ -509,7 +512,7 @@ cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F
     attr_set[dev & 63] = true;
   }
   k_reduce2<F><<<nslots, nthr, nthr * sizeof(XYZZ<F>), st>>>(work.part_r + (size_t)slot0 * parts,
-                                                              work.part_s + (size_t)slot0 * parts, out, parts);
+                                                              work.part_s + (size_t)slot0 * parts, out, parts, red_log);
   return cudaGetLastError();
 }
 

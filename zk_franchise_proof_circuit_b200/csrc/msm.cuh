@@ -9,7 +9,7 @@ namespace zkb {
 struct MsmCfg {
   int c = 16, windows = 16;
   uint32_t buckets = 1u << 15;
-  uint32_t parts() const { return buckets / 32; }   // level-1 reduction chunks of 32 buckets
+  uint32_t parts() const { return buckets / 8; }    // capacity of the level-1 partial arrays (chunks of >= 8 buckets)
 };
 // c in [12, 16] (the reduction needs >= 2048 buckets); the top window must have room for the signed-digit carry
 inline MsmCfg msm_cfg(int c) {

@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr *data, size_t vec_s
                                                            const Fr *__restrict__ tw, const Fr *__restrict__ scale) {
   extern __shared__ uint32_t sm[];
   const int rows_log = hi - lo, rows = 1 << rows_log;
-  const int G = TILE >> rows_log;                    // groups per tile (columns or chunks)
+  const int g_log = TILE_LOG - rows_log, G = 1 << g_log;   // groups per tile (columns or chunks); all index math below
+  const int rows_mask = rows - 1, g_mask = G - 1;            // is shifts and masks (powers of two)
   const bool col = lo > 0;
   Fr *vec = data + (size_t)blockIdx.y * vec_stride;
   const int tile = blockIdx.x;
@@ -103,8 +104,8 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr *data, size_t vec_s
   size_t base;
   int low0 = 0;                                       // low bits (below lo) of group 0's index
   if (col) {
-    int low_groups = (1 << lo) / G;
-    int hi_idx = tile / low_groups, low_grp = tile % low_groups;
+    int lg_log = lo - g_log;                         // log2 of the tiles per high index
+    int hi_idx = tile >> lg_log, low_grp = tile & ((1 << lg_log) - 1);
     low0 = low_grp * G;
     base = ((size_t)hi_idx << hi) + low0;
   } else {
@@ -115,8 +116,8 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr *data, size_t vec_s
     int k, g;
     size_t addr;
     int sidx;
-    if (col) { g = i % G; k = i / G; addr = base + ((size_t)k << lo) + g; sidx = k * G + g; }
-    else { k = i % rows; g = i / rows; addr = base + (size_t)g * rows + k; sidx = g * rows + k; }
+    if (col) { g = i & g_mask; k = i >> g_log; addr = base + ((size_t)k << lo) + g; sidx = i; }
+    else { k = i & rows_mask; g = i >> rows_log; addr = base + i; sidx = i; }
     sts_fr(sm, sidx, ldg_fr(vec + addr));
   }
   __syncthreads();
@@ -128,9 +129,9 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr *data, size_t vec_s
     const int d = 1 << sb;
     for (int b = threadIdx.x; b < TILE / 2; b += NTT_THREADS) {
       int kk, g;
-      if (col) { g = b % G; kk = b / G; } else { kk = b % (rows / 2); g = b / (rows / 2); }
+      if (col) { g = b & g_mask; kk = b >> g_log; } else { kk = b & (rows_mask >> 1); g = b >> (rows_log - 1); }
       int k = ((kk >> sb) << (sb + 1)) | (kk & (d - 1));
-      int i0 = col ? (k * G + g) : (g * rows + k);
+      int i0 = col ? ((k << g_log) + g) : ((g << rows_log) + k);
       int i1 = i0 + d * stride;
       Fr u = lds_fr(sm, i0), v = lds_fr(sm, i1);
       if (s == 0) {                                   // half distance 1: every twiddle is omega^0 = 1 (block-uniform)
@@ -157,8 +158,8 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr *data, size_t vec_s
     int k, g;
     size_t addr;
     int sidx;
-    if (col) { g = i % G; k = i / G; addr = base + ((size_t)k << lo) + g; sidx = k * G + g; }
-    else { k = i % rows; g = i / rows; addr = base + (size_t)g * rows + k; sidx = g * rows + k; }
+    if (col) { g = i & g_mask; k = i >> g_log; addr = base + ((size_t)k << lo) + g; sidx = i; }
+    else { k = i & rows_mask; g = i >> rows_log; addr = base + i; sidx = i; }
     Fr x = lds_fr(sm, sidx);
     if (scale) x = x * ldg_fr(scale + addr);
     stg_fr(vec + addr, x);

@@ -263,7 +263,7 @@ struct Lane {
     if (work2.buckets) work2.free_all();
   }
 };
-static constexpr int MAX_LANES = 4;
+static constexpr int MAX_LANES = 8;
 
 struct Circuit {
   Ctx *ctx = nullptr;

@@ -146,8 +146,9 @@ class Circuit:
         qbuf = ctypes.create_string_buffer(qs * n)
         status = (ctypes.c_int * n)()
         _native.check(_lib().zkb_fullprove_batch(self.h, n, arr, lens, pbuf, ps, qbuf, qs, status))
-        proofs = [pbuf.raw[i * ps:(i + 1) * ps].split(b"\0", 1)[0] for i in range(n)]
-        pubs = [qbuf.raw[i * qs:(i + 1) * qs].split(b"\0", 1)[0] for i in range(n)]
+        praw, qraw = pbuf.raw, qbuf.raw          # one copy each (.raw copies the whole buffer every time it is read)
+        proofs = [praw[i * ps:praw.index(b"\0", i * ps)] for i in range(n)]
+        pubs = [qraw[i * qs:qraw.index(b"\0", i * qs)] for i in range(n)]
         return proofs, pubs, list(status)
 
     def fullprove(self, inputs_json):
