@@ -61,19 +61,27 @@ __global__ void k_hash_consts(CensusLayout L, const Fr *consts, Fr *hc) {
   hc[1] = poseidon_ex<4>(e, 0, z3, false);
 }
 
-// thread = (proof, task): the census witness program (census_witness.cuh) writing this proof's staging array.
-// inputs: [n][n_inputs] canonical; stage: [n][n_signals], zeroed
+// The census witness program (census_witness.cuh) writing each proof's staging array.  The two hash-chain tasks
+// (blockIdx.y < 2) run on COOP_LANES = 8 lanes per proof that share every Poseidon permutation; the three side tasks
+// use one lane of the group.  inputs: [n][n_inputs] canonical; stage: [n][n_signals], zeroed
 __global__ void __launch_bounds__(32) k_witness(CensusLayout L, const Fr *consts, const Fr *hc, const Fr *inputs,
                                                  Fr *stage, int *status, uint32_t n, int skip_const) {
-  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, p = t / COOP_LANES, li = t % COOP_LANES;
+  const int task = blockIdx.y;
+  if (p >= n) return;                          // whole lane groups leave together
+  const bool chain = task < 2;
+  if (!chain && li) return;
   WitnessEnv e;
   e.L = &L;
   e.consts = consts;
   e.stage = stage + (size_t)p * L.n_signals;
   e.status = 0;
-  census_witness_task(e, blockIdx.y, inputs + (size_t)p * L.n_inputs, hc[0], hc[1], skip_const != 0);
-  if (e.status) atomicMax(status + p, e.status);
+  e.coop = chain;
+  e.li = chain ? li : 0;
+  e.glane0 = threadIdx.x & ~(COOP_LANES - 1);
+  e.gmask = ((1u << COOP_LANES) - 1) << e.glane0;
+  census_witness_task(e, task, inputs + (size_t)p * L.n_inputs, hc[0], hc[1], skip_const != 0);
+  if (e.status && e.li == 0) atomicMax(status + p, e.status);
 }
 
 // thread = (wire, proof): wire value from its staged signal, or from the template when the signal was not produced
@@ -408,7 +416,7 @@ static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
 static int run_witness(Circuit *c, Lane &ln, uint32_t first, uint32_t n, cudaStream_t st) {
   CKR(cudaMemsetAsync(c->status + first, 0, (size_t)n * 4, st), "memset status");
   CKR(cudaMemsetAsync(ln.stage, 0, (size_t)n * c->L.n_signals * 32, st), "memset staging");
-  k_witness<<<dim3((n + 31) / 32, WITNESS_TASKS), 32, 0, st>>>(c->L, c->consts, c->hc,
+  k_witness<<<dim3((n * COOP_LANES + 31) / 32, WITNESS_TASKS), 32, 0, st>>>(c->L, c->consts, c->hc,
                                                                c->inputs + (size_t)first * c->L.n_inputs, ln.stage,
                                                                c->status + first, n, 1);
   k_witness_gather<<<dim3((c->n_vars + 255) / 256, n), 256, 0, st>>>(ln.stage, c->L.n_signals, c->wmap, c->tmpl,
