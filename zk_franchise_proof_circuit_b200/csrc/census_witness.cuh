@@ -515,15 +515,32 @@ ZKB_HDN void smt_verifier(WitnessEnv &e, const VerifierLayout &V, const Fr &key_
   if (side) e.put_u32(li + n, 1);
   // bitmask of zero siblings (n <= 254)
   uint32_t zmask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (uint32_t i = 0; i < n; i++) {
-    uint32_t z;
-    if (side) {
+  for (uint32_t i = 0; i < n; i++) zmask[i >> 5] |= (siblings_n[i].is_zero() ? 1u : 0u) << (i & 31);
+  if (side) {
+    // isZero[i] = IsZero {out, in, inv} for every sibling.  The inverses of all non-zero siblings come from ONE field
+    // inversion (Montgomery's trick): the running product before sibling i is parked in its `inv` slot on the way
+    // up and replaced by the inverse on the way down.  (One Fermat inversion per sibling was 0.11 ms each: 1.4 ms
+    // of this task for a 13-level path, 17 ms for a 160-level one.)
+    Fr run = Fr::one();
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t sg = li + 3 * n + 3 * i, z = (zmask[i >> 5] >> (i & 31)) & 1u;
       e.put_norm(li + n + 1 + i, siblings_n[i]);
-      z = is_zero_comp(e, li + 3 * n + 3 * i, siblings_n[i].to_mont());
-    } else {
-      z = siblings_n[i].is_zero() ? 1u : 0u;
+      e.put_u32(sg, z);
+      if (z) { e.put_u32(sg + 1, 0); e.put_u32(sg + 2, 0); continue; }
+      const Fr sm = siblings_n[i].to_mont();
+      e.put(sg + 1, sm);
+      e.put(sg + 2, run);
+      run = run * sm;
     }
-    zmask[i >> 5] |= z << (i & 31);
+    Fr inv = run.inv();
+    for (int i = (int)n - 1; i >= 0; i--) {
+      if ((zmask[i >> 5] >> (i & 31)) & 1u) continue;
+      const uint32_t sg = li + 3 * n + 3 * i;
+      Fr pre = e.stage[sg + 2];
+      pre.v[7] &= ~(TAG_WRITTEN | TAG_MONT);
+      e.put(sg + 2, inv * pre);
+      inv = inv * siblings_n[i].to_mont();
+    }
   }
   auto isz = [&](uint32_t i) { return (zmask[i >> 5] >> (i & 31)) & 1u; };
   if (side && !isz(n - 1)) e.fail();                          // (isZero[n-1].out - 1) * enabled === 0
