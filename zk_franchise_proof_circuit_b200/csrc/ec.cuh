@@ -13,8 +13,8 @@ struct Fq2;
 #if defined(__CUDACC__)
 // Out-of-line Fq2 product / square whose 3 (2) Fq products are inlined, so they interleave on the IMAD pipe
 // (instruction-level parallelism 3) while the call keeps the G2 point formulas small.
-template <int TAG = 0> __device__ __noinline__ Fq2 fq2_mul_call(const Fq2 &a, const Fq2 &b);
-template <int TAG = 0> __device__ __noinline__ Fq2 fq2_sqr_call(const Fq2 &a);
+template <int TAG = 0> __device__ __noinline__ Fq2 fq2_mul_call(Fq2 a, Fq2 b);
+template <int TAG = 0> __device__ __noinline__ Fq2 fq2_sqr_call(Fq2 a);
 #endif
 
 struct alignas(16) Fq2 {
@@ -59,8 +59,8 @@ struct alignas(16) Fq2 {
 };
 
 #if defined(__CUDACC__)
-template <int TAG> __device__ __noinline__ Fq2 fq2_mul_call(const Fq2 &a, const Fq2 &b) { return a * b; }
-template <int TAG> __device__ __noinline__ Fq2 fq2_sqr_call(const Fq2 &a) { return a.sqr(); }
+template <int TAG> __device__ __noinline__ Fq2 fq2_mul_call(Fq2 a, Fq2 b) { return a * b; }
+template <int TAG> __device__ __noinline__ Fq2 fq2_sqr_call(Fq2 a) { return a.sqr(); }
 #endif
 
 template <class F>

@@ -478,7 +478,8 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
       default: ZKB_ACC(4, true); break;     // measured best on B200: inlined products, 128 registers
     }
   } else {
-    switch (variant) {
+    static const int variant2 = getenv("ZKB_ACC_VARIANT_G2") ? atoi(getenv("ZKB_ACC_VARIANT_G2")) : 0;
+    switch (variant2) {
       case 1: ZKB_ACC(4, false); break;
       case 2: ZKB_ACC(5, false); break;
       case 3: ZKB_ACC(6, false); break;
