@@ -138,8 +138,9 @@ __device__ __forceinline__ void stg_fr8(Fr *p, const Fr &x) {
 // have 1 .. 319 terms, p99 = 60, and the last third of the domain is empty).
 struct CsrDev { const uint32_t *row_ptr, *wire; const Fr *value; };
 __global__ void __launch_bounds__(128) k_build_abc(CsrDev A, CsrDev B, const uint32_t *__restrict__ row_order,
-                                                   const Fr *wtns, size_t wtns_stride, Fr *abc, uint32_t domain) {
-  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+                                                   const Fr *wtns, size_t wtns_stride, Fr *abc, uint32_t domain,
+                                                   uint32_t n_long_rows) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x + n_long_rows;   // the first n_long_rows go to k_build_abc_long
   if (tid >= domain) return;
   const uint32_t row = row_order[tid];
   const Fr *w = wtns + (size_t)blockIdx.y * wtns_stride;
@@ -150,6 +151,39 @@ __global__ void __launch_bounds__(128) k_build_abc(CsrDev A, CsrDev B, const uin
   stg_fr8(out + row, a);
   stg_fr8(out + domain + row, b);
   stg_fr8(out + 2 * (size_t)domain + row, a * b);
+}
+
+// The rows with more than ABC_LONG_ROW terms (the head of row_order), one warp each: lanes stride the terms, the 32
+// partial sums are folded with shuffles.  A single thread walking a 300-term row was the whole kernel's tail (0.6 ms
+// for one proof).
+static constexpr uint32_t ABC_LONG_ROW = 48;
+__device__ __forceinline__ Fr warp_sum_fr(Fr x) {
+  for (int d = 16; d >= 1; d >>= 1) {
+    Fr o;
+#pragma unroll
+    for (int l = 0; l < 8; l++) o.v[l] = __shfl_down_sync(0xffffffffu, x.v[l], d);
+    x = x + o;
+  }
+  return x;
+}
+__global__ void __launch_bounds__(128) k_build_abc_long(CsrDev A, CsrDev B, const uint32_t *__restrict__ row_order,
+                                                        const Fr *wtns, size_t wtns_stride, Fr *abc, uint32_t domain,
+                                                        uint32_t n_long_rows) {
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= n_long_rows) return;
+  const uint32_t row = row_order[wid];
+  const Fr *w = wtns + (size_t)blockIdx.y * wtns_stride;
+  Fr a = Fr::zero(), b = Fr::zero();
+  for (uint32_t k = A.row_ptr[row] + lane, e = A.row_ptr[row + 1]; k < e; k += 32) a = a + ldg_fr8(A.value + k) * ldg_fr8(w + A.wire[k]);
+  for (uint32_t k = B.row_ptr[row] + lane, e = B.row_ptr[row + 1]; k < e; k += 32) b = b + ldg_fr8(B.value + k) * ldg_fr8(w + B.wire[k]);
+  a = warp_sum_fr(a);
+  b = warp_sum_fr(b);
+  if (lane == 0) {
+    Fr *out = abc + (size_t)blockIdx.y * 3 * domain;
+    stg_fr8(out + row, a);
+    stg_fr8(out + domain + row, b);
+    stg_fr8(out + 2 * (size_t)domain + row, a * b);
+  }
 }
 
 // h = a * b - c on the odd coset, back to canonical form (snarkjs joinABC)
@@ -282,6 +316,7 @@ struct Circuit {
   Fr *consts = nullptr, *hc = nullptr, *tmpl = nullptr;
   uint32_t *wmap = nullptr;        // wire -> circom signal (the wasm's witness table)
   uint32_t *csr_buf = nullptr, *row_order = nullptr;
+  uint32_t n_long_rows = 0;        // head of row_order: rows with more than ABC_LONG_ROW terms (one warp each)
   Fr *csr_val = nullptr;
   CsrDev csrA, csrB;
   NttPlan ntt;
@@ -462,7 +497,10 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
     CKR(msm_reduce<Fq>(ln.work1, 0, 3 * m * sW, outW, ln.sW), "msm reduce g1");
     if (splitW) CKR(msm_fold_subs<Fq>(outW, ln.g1out, m, sW, 3, ln.sW), "fold g1 ranges");
     cudaEventRecord(ln.e_W, ln.sW);
-    k_build_abc<<<g1, 128, 0, st>>>(c->csrA, c->csrB, c->row_order, w, c->n_vars, ln.abc, c->domain);
+    if (c->n_long_rows)
+      k_build_abc_long<<<dim3((c->n_long_rows * 32 + 127) / 128, m), 128, 0, st>>>(c->csrA, c->csrB, c->row_order, w, c->n_vars,
+                                                                                  ln.abc, c->domain, c->n_long_rows);
+    k_build_abc<<<g1, 128, 0, st>>>(c->csrA, c->csrB, c->row_order, w, c->n_vars, ln.abc, c->domain, c->n_long_rows);
     CKR(c->ntt.dif(ln.abc, 3 * m, c->domain, true, true, st), "ntt dif");
     CKR(c->ntt.dit(ln.abc, 3 * m, c->domain, false, st), "ntt dit");
     k_join<<<g2, 256, 0, st>>>(ln.abc, ln.hs, c->domain);
@@ -472,10 +510,13 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
     if (splitH) CKR(msm_fold_subs<Fq>(outH, ln.g1out + (size_t)3 * c->chunk, m, sH, 1, st), "fold g1 (H) ranges");
     cudaStreamWaitEvent(st, ln.e_W, 0);
     cudaStreamWaitEvent(st, ln.e_2, 0);
-    g_launches += 1 + 4 + 1 + 1 + (splitW ? 2 : 0) + (splitH ? 1 : 0);
+    g_launches += 1 + 4 + 1 + 1 + (splitW ? 2 : 0) + (splitH ? 1 : 0) + (c->n_long_rows ? 1 : 0);
   } else {
-    k_build_abc<<<g1, 128, 0, st>>>(c->csrA, c->csrB, c->row_order, w, c->n_vars, ln.abc, c->domain);
-    g_launches += 1 + 4 + 1;   // build_abc, 2 DIF + 2 DIT passes, join
+    if (c->n_long_rows)
+      k_build_abc_long<<<dim3((c->n_long_rows * 32 + 127) / 128, m), 128, 0, st>>>(c->csrA, c->csrB, c->row_order, w, c->n_vars,
+                                                                                  ln.abc, c->domain, c->n_long_rows);
+    k_build_abc<<<g1, 128, 0, st>>>(c->csrA, c->csrB, c->row_order, w, c->n_vars, ln.abc, c->domain, c->n_long_rows);
+    g_launches += 1 + 4 + 1 + (c->n_long_rows ? 1 : 0);   // build_abc (+ its long-row kernel), 2 DIF + 2 DIT passes, join
     if (ev) cudaEventRecord(ev[2], st);
     CKR(c->ntt.dif(ln.abc, 3 * m, c->domain, true, true, st), "ntt dif");
     CKR(c->ntt.dit(ln.abc, 3 * m, c->domain, false, st), "ntt dit");
@@ -722,6 +763,8 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
     for (uint32_t r = 0; r < z.domain; r++) start[maxlen - len[r] + 1]++;
     for (uint32_t i = 0; i <= maxlen; i++) start[i + 1] += start[i];
     for (uint32_t r = 0; r < z.domain; r++) order[start[maxlen - len[r]]++] = r;
+    c->n_long_rows = 0;
+    while (c->n_long_rows < z.domain && len[order[c->n_long_rows]] > ABC_LONG_ROW) c->n_long_rows++;
     CKR(upload(&c->row_order, order.data(), order.size() * 4), "upload row order");
   }
   CKR(c->ntt.init(z.power, st), "ntt plan");
