@@ -268,6 +268,9 @@ def test_generic_circuit_chain_bit_exact(tmp_path, links):
     proof, pub = json.loads(pj), json.loads(sj)
     assert O.proof_bin(proof) == exp
     assert pub == [str(int.from_bytes(w[1].tobytes(), "little"))]
+    if links == 40:                                  # committed known answer (tests/golden/chain40_kat.json)
+        kat = json.load(open(H.GOLDEN + "/chain40_kat.json"))
+        assert proof == kat["proof"] and pub == kat["public"]
     assert O.verify(json.loads(vkey), pub, proof)
     prover.verify(vkey, sj, pj)
     c.close()

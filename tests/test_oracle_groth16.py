@@ -79,3 +79,19 @@ def test_oracle_ntt_and_msm_self_consistency():
     buf = (ctypes.c_uint8 * 64)()
     O.lib().orc_g1_mul_gen(O._buf(O.le32(total)), buf)
     assert O.msm_g1(pts, s) == bytes(buf)
+
+
+def test_chain_circuit_golden_vector(tmp_path):
+    """The oracle's chain-circuit generator, dev setup and prover reproduce the committed known answer."""
+    import hashlib
+    kat = json.load(open(H.GOLDEN + "/chain40_kat.json"))
+    n_wires, n_cons, domain = O.chain_artifacts(kat["links"], kat["setup_seed"], str(tmp_path))
+    assert (n_wires, n_cons, domain) == (kat["n_wires"], kat["n_constraints"], kat["domain"])
+    zkey = open(tmp_path / "proving_key.zkey", "rb").read()
+    wtns = open(tmp_path / "witness.wtns", "rb").read()
+    assert hashlib.sha256(zkey).hexdigest() == kat["zkey_sha256"]
+    assert hashlib.sha256(wtns).hexdigest() == kat["wtns_sha256"]
+    w = H.wtns_payload(wtns, n_wires)
+    proof = O.proof_json(O.ZKeyRef(zkey).prove(w, kat["r"], kat["s"]))
+    assert proof == kat["proof"]
+    assert O.verify(json.load(open(tmp_path / "verification_key.json")), kat["public"], proof)

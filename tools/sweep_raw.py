@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--msm", default="16,18,20,22,24")
     ap.add_argument("--ntt", default="16,18,20,22,24")
     ap.add_argument("--ntt-dist", default="", help="sizes (log2, >= 24) for the 4-step NTT split over all ranks")
+    ap.add_argument("--nccl-compare", action="store_true",
+                    help="also time the NCCL collectives the P2P exchanges replace (all_gather of one 128-byte partial "
+                         "sum; all_to_all of the NTT columns), same GPUs, CUDA events")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -140,6 +143,42 @@ def main():
                           "no NCCL" if world > 1 else "local transpose", "scaling": "strong"})
         s.close()
         barrier()
+    if args.nccl_compare and world > 1:
+        # What NCCL would cost for the same exchanges (north_star: "no NCCL unless measured to help")
+        pg = dist.new_group(backend="nccl")
+        dev = torch.device("cuda", local)
+        part = torch.zeros(32, dtype=torch.int32, device=dev)                  # one XYZZ partial sum = 128 bytes
+        outl = [torch.zeros_like(part) for _ in range(world)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(20):
+            dist.all_gather(outl, part, group=pg)
+        torch.cuda.synchronize()
+        barrier()
+        e0.record()
+        for _ in range(200):
+            dist.all_gather(outl, part, group=pg)
+        e1.record()
+        torch.cuda.synchronize()
+        ag_us = reduce_max(e0.elapsed_time(e1) / 200 * 1e3)
+        emit({"kind": "nccl_compare", "what": "all_gather of one 128-byte partial sum (the MSM combine)", "n_gpus": world,
+              "nccl_us_per_call": ag_us, "note": "back-to-back calls on one stream, CUDA events; the P2P push is one 128-byte "
+              "store + flag inside the rank's last kernel"})
+        for logn in [int(x) for x in args.ntt_dist.split(",") if x]:
+            per = (1 << logn) // world
+            src = torch.zeros(per * 8, dtype=torch.int32, device=dev)
+            dst = torch.zeros_like(src)
+            for _ in range(3):
+                dist.all_to_all_single(dst, src, group=pg)
+            torch.cuda.synchronize()
+            barrier()
+            e0.record()
+            for _ in range(10):
+                dist.all_to_all_single(dst, src, group=pg)
+            e1.record()
+            torch.cuda.synchronize()
+            a2a = reduce_max(e0.elapsed_time(e1) / 10)
+            emit({"kind": "nccl_compare", "what": "all_to_all_single of the 4-step NTT columns (no transpose, no twiddles)",
+                  "logn": logn, "n_gpus": world, "nccl_ms": a2a, "bytes_per_gpu": per * 32})
     if rank == 0 and args.out:
         with open(os.path.join(ROOT, args.out), "w") as f:
             for d in lines:
