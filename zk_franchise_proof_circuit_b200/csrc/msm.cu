@@ -242,6 +242,10 @@ struct TablePtrs { const Affine<F> *tab[4]; };
 template <bool INL, class F> __device__ __forceinline__ F mulx(const F &a, const F &b) {
   if constexpr (INL) return a * b; else return a.mulc(b);
 }
+// squares: Fq2 has a 2-product complex squaring (3 for a general product); Fq squares are plain products
+template <bool INL, class F> __device__ __forceinline__ F sqrx(const F &a) {
+  if constexpr (INL) return a * a; else return a.sqrc();
+}
 
 template <class F, int THREADS, int MINB, bool INL>
 __global__ void __launch_bounds__(THREADS, MINB) k_accumulate(TablePtrs<F> tabs, int ntab, uint32_t n, int windows,
@@ -273,8 +277,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_accumulate(TablePtrs<F> tabs,
     F U2 = mulx<INL>(p.x, acc.ZZ), S2 = mulx<INL>(p.y, acc.ZZZ);
     F P = U2 - acc.X, R = S2 - acc.Y;
     const bool special = use && !acc_inf && P.is_zero();
-    F PP = mulx<INL>(P, P), PPP = mulx<INL>(P, PP), Q = mulx<INL>(acc.X, PP);
-    F X3 = mulx<INL>(R, R) - PPP - Q.dbl();
+    F PP = sqrx<INL>(P), PPP = mulx<INL>(P, PP), Q = mulx<INL>(acc.X, PP);
+    F X3 = sqrx<INL>(R) - PPP - Q.dbl();
     F Y3 = mulx<INL>(R, Q - X3) - mulx<INL>(acc.Y, PPP);
     F ZZ3 = mulx<INL>(acc.ZZ, PP), ZZZ3 = mulx<INL>(acc.ZZZ, PPP);
     const bool normal = use && !acc_inf && !special, first = use && acc_inf;
