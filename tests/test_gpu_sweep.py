@@ -126,3 +126,20 @@ def test_ntt_dist_two_gpus():
     x, out, times = _ntt_dist_group(24, 2, [0, 1])
     assert np.array_equal(out, raw.ntt_dif_forward(x))
     print("4-step NTT 2^24 on 2 GPUs, ms (total, columns, exchange, rows):", times)
+
+
+def test_session_argument_errors():
+    """Bad shapes are errors with a message, not crashes or silent fallbacks."""
+    from zk_franchise_proof_circuit_b200 import raw
+    from zk_franchise_proof_circuit_b200._native import NativeError
+    with pytest.raises(NativeError):
+        raw.MsmSession(30)                      # larger than the entry index allows
+    with pytest.raises(NativeError):
+        raw.MsmSession(16, rank=0, nranks=3)    # ranks must be a power of two
+    with pytest.raises(NativeError):
+        raw.NttDist(20)                         # the 4-step split needs 2^24 or more
+    s = raw.MsmSession(12)
+    s.run()
+    with pytest.raises(NativeError):
+        s.combine(0)
+    assert s.combine(1)[0] != bytes(64)

@@ -290,6 +290,7 @@ struct zkb_msm_session;
 
 // One rank's share of a 2^logn-point synthetic G1 MSM: points [rank * N / nranks, (rank + 1) * N / nranks), cut into
 // sub-MSMs of at most 2^17 points.  Generates bases + scalars on the device and builds the fixed-base window table.
+void zkb_msm_session_destroy(zkb_msm_session *h);
 int zkb_msm_session_create(int device, int logn, int rank, int nranks, uint64_t seed, int window_bits,
                            zkb_msm_session **out) {
   if (require_device()) return ZKB_ERROR;
@@ -300,6 +301,8 @@ int zkb_msm_session_create(int device, int logn, int rank, int nranks, uint64_t 
   }
   CKR(cudaSetDevice(device), "set device");
   MsmSession *s = new MsmSession();
+  // any failure below releases what was allocated so far
+#define CKS(x, what) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { zkb_msm_session_destroy(reinterpret_cast<zkb_msm_session *>(s)); return cuda_fail(e_, what); } } while (0)
   s->device = device;
   s->total = 1ull << logn;
   uint64_t mine = s->total / nranks;
@@ -309,28 +312,29 @@ int zkb_msm_session_create(int device, int logn, int rank, int nranks, uint64_t 
   s->seed = seed;
   s->slot = rank;
   s->cfg = msm_cfg(window_bits);
-  CKR(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking), "stream");
+  CKS(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking), "stream");
   cudaEventCreate(&s->e0); cudaEventCreate(&s->e1); cudaEventCreate(&s->e2);
-  CKR(cudaMalloc(&s->bases, mine * sizeof(Affine<Fq>)), "alloc bases");
-  CKR(cudaMalloc(&s->scalars, mine * sizeof(Fr)), "alloc scalars");
+  CKS(cudaMalloc(&s->bases, mine * sizeof(Affine<Fq>)), "alloc bases");
+  CKS(cudaMalloc(&s->scalars, mine * sizeof(Fr)), "alloc scalars");
   cudaEventRecord(s->e0, s->st);
   k_gen_points<<<(unsigned)((mine + 127) / 128), 128, 0, s->st>>>(s->bases, s->first, mine, seed);
   k_gen_scalars<<<(unsigned)((mine + 255) / 256), 256, 0, s->st>>>(s->scalars, s->first, mine, seed);
   cudaEventRecord(s->e1, s->st);
-  CKR(msm_build_table<Fq>(s->tab, s->bases, s->n_sub, s->cfg, s->st, s->subs), "build table");
+  CKS(msm_build_table<Fq>(s->tab, s->bases, s->n_sub, s->cfg, s->st, s->subs), "build table");
   cudaEventRecord(s->e2, s->st);
-  CKR(s->sort.alloc(s->n_sub, s->subs, s->cfg), "alloc sort");
-  CKR(s->work.alloc(s->subs, s->cfg), "alloc buckets");
-  CKR(cudaMalloc(&s->sub_out, (size_t)s->subs * sizeof(XYZZ<Fq>)), "alloc");
-  CKR(cudaMalloc(&s->partial, sizeof(XYZZ<Fq>)), "alloc");
-  CKR(cudaMalloc(&s->xbuf, MAX_RANKS * sizeof(ExSlot)), "alloc exchange");
-  CKR(cudaMemsetAsync(s->xbuf, 0, MAX_RANKS * sizeof(ExSlot), s->st), "memset");
-  CKR(cudaMalloc(&s->result, sizeof(Affine<Fq>)), "alloc");
-  CKR(cudaMalloc(&s->status, 4), "alloc");
+  CKS(s->sort.alloc(s->n_sub, s->subs, s->cfg), "alloc sort");
+  CKS(s->work.alloc(s->subs, s->cfg), "alloc buckets");
+  CKS(cudaMalloc(&s->sub_out, (size_t)s->subs * sizeof(XYZZ<Fq>)), "alloc");
+  CKS(cudaMalloc(&s->partial, sizeof(XYZZ<Fq>)), "alloc");
+  CKS(cudaMalloc(&s->xbuf, MAX_RANKS * sizeof(ExSlot)), "alloc exchange");
+  CKS(cudaMemsetAsync(s->xbuf, 0, MAX_RANKS * sizeof(ExSlot), s->st), "memset");
+  CKS(cudaMalloc(&s->result, sizeof(Affine<Fq>)), "alloc");
+  CKS(cudaMalloc(&s->status, 4), "alloc");
   s->root_x = s->xbuf;
-  CKR(cudaStreamSynchronize(s->st), "msm session setup");
+  CKS(cudaStreamSynchronize(s->st), "msm session setup");
   cudaEventElapsedTime(&s->gen_ms, s->e0, s->e1);
   cudaEventElapsedTime(&s->table_ms, s->e1, s->e2);
+#undef CKS
   *out = reinterpret_cast<zkb_msm_session *>(s);
   return ZKB_OK;
 }
@@ -339,14 +343,15 @@ void zkb_msm_session_destroy(zkb_msm_session *h) {
   MsmSession *s = reinterpret_cast<MsmSession *>(h);
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaStreamSynchronize(s->st);
+  if (s->st) cudaStreamSynchronize(s->st);
   if (s->root_is_ipc) cudaIpcCloseMemHandle(s->root_x);
   cudaFree(s->bases); cudaFree(s->scalars); cudaFree(s->tab.tab); cudaFree(s->sub_out); cudaFree(s->partial);
   cudaFree(s->xbuf); cudaFree(s->result); cudaFree(s->status);
   s->sort.free_all();
   s->work.free_all();
-  cudaEventDestroy(s->e0); cudaEventDestroy(s->e1); cudaEventDestroy(s->e2);
-  cudaStreamDestroy(s->st);
+  if (s->e0) { cudaEventDestroy(s->e0); cudaEventDestroy(s->e1); cudaEventDestroy(s->e2); }
+  if (s->st) cudaStreamDestroy(s->st);
+  cudaGetLastError();
   delete s;
 }
 

@@ -100,7 +100,8 @@ class MsmSession:
         """rank 0: (affine canonical point bytes, device ms from the start of this rank's run())."""
         out = ctypes.create_string_buffer(64)
         ms = ctypes.c_float()
-        _native.check(_native.lib().zkb_msm_session_combine(self.h, nslots or self.nranks, out, ctypes.byref(ms)))
+        _native.check(_native.lib().zkb_msm_session_combine(self.h, self.nranks if nslots is None else nslots, out,
+                                                            ctypes.byref(ms)))
         return out.raw, ms.value
 
     def madds(self) -> int:
