@@ -330,24 +330,46 @@ __device__ __noinline__ Fr poseidon_ex_coop(WitnessEnv &e, uint32_t base, const 
   sigma_full(3);
   ark(4, 4 * T);
   mix(3, Pm);
+  // Partial rounds in THREE product times.  With x = st[0], c = C[5T + r] and the sparse row S:
+  //   out[0] = S[0] (x^5 + c) + sum_{j>=1} S[j] st[j],      out[i] = st[i] + S[T+i-1] (x^5 + c).
+  // Lane 0 walks the S-box chain x^2, x^4, x^5 (its signals are needed); beside it, in the same three product slots,
+  // lanes 1..T-1 form S[j] st[j], and T helper lanes (lane T for out[0], lane T+i for out[i]) form S[.] x, S[.] c and
+  // finally x^4 (S[.] x) = S[.] x^5, so that everything is ready when the S-box is.  All exact field identities.
+  static_assert(2 * T <= (int)COOP_LANES, "helper lanes");
   for (int r = 0; r < RP; r++) {
     const uint32_t ss = base + pl.sigp + r * 4, ms = base + pl.mixs + r * 2 * T;
-    Fr y = fr_sbox_coop(e, ss, s, emit && li == 0);      // meaningful on lane 0
-    if (li == 0) s = y + C[5 * T + r];
-    const Fr s0 = shfl_fr(m, s, l0);
     const Fr *Sr = S + (2 * T - 1) * r;
-    // lane j < T: Sr[j] * st[j] (a term of out[0]); lane T + i - 1, i = 1..T-1: Sr[T + i - 1] * st[0] (for out[i])
-    const uint32_t pi = li < (uint32_t)(2 * T - 1) ? li : 0;
-    const Fr prod = Sr[pi] * (own ? s : s0);
-    Fr o0 = shfl_fr(m, prod, l0);
+    const Fr c = C[5 * T + r];
+    const bool helper = li >= (uint32_t)T && li < (uint32_t)(2 * T);
+    // the S coefficient this lane works with: lanes j < T: S[j]; helper lane T: S[0]; helper lane T+i: S[T+i-1]
+    const uint32_t ci = li < (uint32_t)T ? li : (li == (uint32_t)T ? 0u : (helper ? li - 1 : 0u));
+    const Fr coef = Sr[ci];
+    const Fr x = shfl_fr(m, s, l0);                       // st[0] before the S-box
+    // slot 1: lane 0: x^2; lanes 1..T-1: S[j] st[j]; helpers: S[.] x
+    const Fr p1 = (li == 0 ? x : coef) * (li == 0 || helper ? x : s);
+    // slot 2: lane 0: x^4; helpers: S[.] c
+    const Fr p2 = (li == 0 ? p1 : coef) * (li == 0 ? p1 : c);
+    const Fr x4 = shfl_fr(m, p2, l0);
+    // slot 3: lane 0: x^5; helpers: x^4 (S[.] x) = S[.] x^5
+    const Fr p3 = x4 * (li == 0 ? x : p1);
+    if (emit && li == 0) {                                // Sigma {out, in, in2, in4}
+      e.putf(ss + 1, x);
+      e.putf(ss + 2, p1);
+      e.putf(ss + 3, p2);
+      e.putf(ss, p3);
+    }
+    const Fr hsum = p3 + p2;                              // helpers: S[.] (x^5 + c)
+    // out[0] on lane 0: helper lane T's term + the S[j] st[j] of lanes 1..T-1
+    Fr o0 = shfl_fr(m, hsum, l0 + T);
 #pragma unroll
-    for (int j = 1; j < T; j++) o0 = o0 + shfl_fr(m, prod, l0 + j);
-    const Fr q = shfl_fr(m, prod, l0 + ((li >= 1 && own) ? (uint32_t)T + li - 1 : 0u));
-    if (wr) e.putf(ms + T + li, s);
+    for (int j = 1; j < T; j++) o0 = o0 + shfl_fr(m, p1, l0 + j);
+    const Fr q = shfl_fr(m, hsum, l0 + ((li >= 1 && own) ? (uint32_t)T + li : (uint32_t)T));
     if (li == 0) {
+      const Fr in0 = p3 + c;                              // st[0] after the S-box and the round constant
+      if (emit) { e.putf(ms + T, in0); e.putf(ms, o0); }
       s = o0;
-      if (emit) e.putf(ms, o0);
     } else if (own) {
+      if (emit) e.putf(ms + T + li, s);
       s = s + q;
       if (emit) e.putf(ms + li, s);
     }
