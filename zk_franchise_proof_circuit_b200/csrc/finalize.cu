@@ -24,7 +24,8 @@ __global__ void k_fixed_table(Affine<F> *tab, const Affine<F> *base) {
 //   phase 1   warp 0: A = pi_a' + alpha1 + r*delta1      warp 1: B1 = pi_b1' + beta1 + s*delta1
 //             warp 2: -(r*s)*delta1, public signals      warp 3: B = pi_b' + beta2 + s*delta2   (G2)
 //             (warp 3 continues with B -> affine; it does not take part in the phase barrier)
-//   phase 2   warp 0: s*A      warp 1: r*B1      warp 2: A -> affine, then T = -(r*s)*delta1 + pi_c' + pi_h
+//   phase 2   warp 0: s*A      warp 1: r*B1   (four lanes each share every point doubling / addition)
+//             warp 2: A -> affine, then T = -(r*s)*delta1 + pi_c' + pi_h
 //   then      warp 0: C = s*A + r*B1 + T -> affine
 __global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
   __shared__ XYZZ<Fq> sh[5];          // A, s*A | B1, r*B1 | T
@@ -54,12 +55,12 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
     }
   }
   if (warp < 3) asm volatile("bar.sync 1, 96;" ::: "memory");   // warps 0-2 only: A, B1 and -(rs)delta1 are ready
+  if (warp < 2 && lane < 4) {          // the two variable-base products, four lanes each (finalize.cuh, *_coop)
+    if (warp == 0) var_mul_coop(&sh[0], s.v, scratch, &sh[1], lane);
+    else var_mul_coop(&sh[2], r.v, scratch + 15, &sh[3], lane);
+  }
   if (lane == 0) {
-    if (warp == 0) {
-      var_mul<Fq>(&sh[0], s.v, scratch, &sh[1]);
-    } else if (warp == 1) {
-      var_mul<Fq>(&sh[2], r.v, scratch + 15, &sh[3]);
-    } else if (warp == 2) {
+    if (warp == 2) {
       Affine<Fq> a;
       xyzz_to_affine_ni(&sh[0], &a);
       Fq x = a.x.from_mont(), y = a.y.from_mont();
