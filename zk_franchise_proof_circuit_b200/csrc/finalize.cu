@@ -34,19 +34,31 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
   uint8_t *out = P.out + (size_t)p * (256 + 32 * P.n_public);
   XYZZ<Fq> *scratch = P.scratch + ((size_t)p * 2) * 15;
   const Fr r = P.rs[2 * p], s = P.rs[2 * p + 1];
+  // phase 1, the fixed-base products k * delta on 4 (G1) / 3 (G2) lanes of each warp ...
+  if (warp == 0 && lane < 4) fixed_mul_coop(P.d1tab, r.v, &sh[0], lane);
+  else if (warp == 1 && lane < 4) fixed_mul_coop(P.d1tab, s.v, &sh[2], lane);
+  else if (warp == 2 && lane < 4) {
+    Fr rs = (r.to_mont() * s.to_mont()).from_mont();
+    fixed_mul_coop(P.d1tab, rs.v, &sh[4], lane);
+  } else if (warp == 3 && lane < 3) fixed_mul2_coop(P.d2tab, s.v, &shB, lane);
+  __syncwarp();
+  // ... then lane 0 adds the fixed point and the MSM partial sum
   if (lane == 0) {
     if (warp == 0) {
-      fin_point<Fq>(P.g1 + 3 * p, P.alpha1, P.d1tab, r.v, &sh[0]);
+      xyzz_add_affine_ni(&sh[0], P.alpha1);
+      xyzz_add_ni(&sh[0], P.g1 + 3 * p);
       if (P.tconst1) xyzz_add_ni(&sh[0], P.tconst1);
     } else if (warp == 1) {
-      fin_point<Fq>(P.g1 + 3 * p + 1, P.beta1, P.d1tab, s.v, &sh[2]);
+      xyzz_add_affine_ni(&sh[2], P.beta1);
+      xyzz_add_ni(&sh[2], P.g1 + 3 * p + 1);
       if (P.tconst1) xyzz_add_ni(&sh[2], P.tconst1 + 1);
     } else if (warp == 2) {
-      fin_neg_rs_delta(P.d1tab, r, s, &sh[4]);
+      sh[4].Y = sh[4].Y.neg();                     // -(r s) delta1
       const Fr *w = P.wtns + (size_t)p * P.wtns_stride;
       for (uint32_t i = 0; i < P.n_public; i++) memcpy(out + 256 + 32 * i, w[1 + i].v, 32);
     } else {                     // the G2 point is the longest phase-1 piece: warp 3 goes straight on to its affine form
-      fin_point<Fq2>(P.g2 + p, P.beta2, P.d2tab, s.v, &shB);
+      xyzz_add_affine_ni(&shB, P.beta2);
+      xyzz_add_ni(&shB, P.g2 + p);
       if (P.tconst2) xyzz_add_ni(&shB, P.tconst2);
       Affine<Fq2> b;
       xyzz_to_affine_ni(&shB, &b);

@@ -98,6 +98,89 @@ static __device__ __noinline__ void xyzz_add_coop(XYZZ<Fq> *p, const XYZZ<Fq> *o
   const Fq Y3 = R * (Q - X3) - T;
   p->X = X3; p->Y = Y3; p->ZZ = ZZ3; p->ZZZ = ZZZ3;
 }
+// mixed addition p += q (q affine), 5 product times instead of 10
+static __device__ __noinline__ void xyzz_madd_coop(XYZZ<Fq> *p, const Affine<Fq> *q, uint32_t l) {
+  if (q->is_inf()) return;
+  if (p->is_inf()) { p->X = q->x; p->Y = q->y; p->ZZ = Fq::one(); p->ZZZ = Fq::one(); return; }
+  const Fq r1 = Fq::select(l == 0, q->x, q->y) * Fq::select(l == 0, p->ZZ, p->ZZZ);          // U2 | S2
+  const Fq P = bc4(r1, 0) - p->X, R = bc4(r1, 1) - p->Y;
+  if (P.is_zero()) {
+    if (R.is_zero()) *p = XYZZ<Fq>::dbl_affine(*q);
+    else *p = XYZZ<Fq>::infinity();
+    return;
+  }
+  const Fq a2 = Fq::select(l == 0, P, R);
+  const Fq r2 = a2 * a2;                                                                      // PP | RR
+  const Fq PP = bc4(r2, 0), RR = bc4(r2, 1);
+  const Fq r3 = sel4(l, P, p->X, p->ZZ, p->ZZ) * PP;                                          // PPP | Q | ZZ'
+  const Fq PPP = bc4(r3, 0), Q = bc4(r3, 1), ZZ3 = bc4(r3, 2);
+  const Fq r4 = Fq::select(l == 0, p->Y, p->ZZZ) * PPP;                                       // Y PPP | ZZZ'
+  const Fq T = bc4(r4, 0), ZZZ3 = bc4(r4, 1);
+  const Fq X3 = RR - PPP - Q.dbl();
+  const Fq Y3 = R * (Q - X3) - T;
+  p->X = X3; p->Y = Y3; p->ZZ = ZZ3; p->ZZZ = ZZZ3;
+}
+// fixed_mul on lanes 0..3; *out written by lane 0
+static __device__ __noinline__ void fixed_mul_coop(const Affine<Fq> *tab, const uint32_t k[8], XYZZ<Fq> *out, uint32_t l) {
+  XYZZ<Fq> acc = XYZZ<Fq>::infinity();
+  for (int w = 0; w < 64; w++) {
+    uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
+    if (d) {
+      Affine<Fq> t = tab[w * 15 + d - 1];
+      xyzz_madd_coop(&acc, &t, l);
+    }
+  }
+  if (l == 0) *out = acc;
+}
+
+// ---- G2: an Fq2 product is three Fq products - one each on lanes 0..2 (identical copies of all values) --------
+__device__ __forceinline__ Fq bc3(const Fq &x, int src) {
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0x7u, x.v[i], src);
+  return r;
+}
+__device__ __forceinline__ Fq2 fq2_mul_coop(const Fq2 &a, const Fq2 &b, uint32_t l) {   // Karatsuba, as Fq2::operator*
+  const Fq x = l == 0 ? a.a : (l == 1 ? a.b : a.a + a.b), y = l == 0 ? b.a : (l == 1 ? b.b : b.a + b.b);
+  const Fq t = x * y;
+  const Fq t0 = bc3(t, 0), t1 = bc3(t, 1), t2 = bc3(t, 2);
+  return {t0 - t1, t2 - t0 - t1};
+}
+__device__ __forceinline__ Fq2 fq2_sqr_coop(const Fq2 &a, uint32_t l) {                  // complex squaring, as Fq2::sqr
+  const Fq x = l == 0 ? a.a + a.b : a.a, y = l == 0 ? a.a - a.b : a.b;
+  const Fq t = x * y;
+  const Fq t0 = bc3(t, 0), t1 = bc3(t, 1);
+  return {t0, t1 + t1};
+}
+static __device__ __noinline__ void xyzz2_madd_coop(XYZZ<Fq2> *p, const Affine<Fq2> *q, uint32_t l) {
+  if (q->is_inf()) return;
+  if (p->is_inf()) { p->X = q->x; p->Y = q->y; p->ZZ = Fq2::one(); p->ZZZ = Fq2::one(); return; }
+  const Fq2 U2 = fq2_mul_coop(q->x, p->ZZ, l), S2 = fq2_mul_coop(q->y, p->ZZZ, l);
+  const Fq2 P = U2 - p->X, R = S2 - p->Y;
+  if (P.is_zero()) {
+    if (R.is_zero()) *p = XYZZ<Fq2>::dbl_affine(*q);
+    else *p = XYZZ<Fq2>::infinity();
+    return;
+  }
+  const Fq2 PP = fq2_sqr_coop(P, l), PPP = fq2_mul_coop(P, PP, l), Q = fq2_mul_coop(p->X, PP, l);
+  const Fq2 X3 = fq2_sqr_coop(R, l) - PPP - Q.dbl();
+  const Fq2 Y3 = fq2_mul_coop(R, Q - X3, l) - fq2_mul_coop(p->Y, PPP, l);
+  p->ZZ = fq2_mul_coop(p->ZZ, PP, l);
+  p->ZZZ = fq2_mul_coop(p->ZZZ, PPP, l);
+  p->X = X3; p->Y = Y3;
+}
+static __device__ __noinline__ void fixed_mul2_coop(const Affine<Fq2> *tab, const uint32_t k[8], XYZZ<Fq2> *out, uint32_t l) {
+  XYZZ<Fq2> acc = XYZZ<Fq2>::infinity();
+  for (int w = 0; w < 64; w++) {
+    uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
+    if (d) {
+      Affine<Fq2> t = tab[w * 15 + d - 1];
+      xyzz2_madd_coop(&acc, &t, l);
+    }
+  }
+  if (l == 0) *out = acc;
+}
+
 // var_mul on lanes 0..3 (l = lane): *p is readable by all four, tb = 15 points of scratch shared by the group,
 // *out is written by lane 0.
 static __device__ __noinline__ void var_mul_coop(const XYZZ<Fq> *p, const uint32_t k[8], XYZZ<Fq> *tb, XYZZ<Fq> *out, uint32_t l) {
