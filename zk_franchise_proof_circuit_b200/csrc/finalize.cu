@@ -34,13 +34,16 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
   uint8_t *out = P.out + (size_t)p * (256 + 32 * P.n_public);
   XYZZ<Fq> *scratch = P.scratch + ((size_t)p * 2) * 15;
   const Fr r = P.rs[2 * p], s = P.rs[2 * p + 1];
-  // phase 1, the fixed-base products k * delta on 4 (G1) / 3 (G2) lanes of each warp ...
-  if (warp == 0 && lane < 4) fixed_mul_coop(P.d1tab, r.v, &sh[0], lane);
-  else if (warp == 1 && lane < 4) fixed_mul_coop(P.d1tab, s.v, &sh[2], lane);
-  else if (warp == 2 && lane < 4) {
-    Fr rs = (r.to_mont() * s.to_mont()).from_mont();
-    fixed_mul_coop(P.d1tab, rs.v, &sh[4], lane);
-  } else if (warp == 3 && lane < 3) fixed_mul2_coop(P.d2tab, s.v, &shB, lane);
+  // phase 1, the fixed-base products k * delta on the first lane group of each warp (ec_coop.cuh) ...
+  const LaneGroup grp = LaneGroup::of(lane);
+  if (lane < 4) {
+    if (warp == 0) fixed_mul_coop<Fq>(P.d1tab, r.v, &sh[0], grp);
+    else if (warp == 1) fixed_mul_coop<Fq>(P.d1tab, s.v, &sh[2], grp);
+    else if (warp == 2) {
+      Fr rs = (r.to_mont() * s.to_mont()).from_mont();
+      fixed_mul_coop<Fq>(P.d1tab, rs.v, &sh[4], grp);
+    } else fixed_mul_coop<Fq2>(P.d2tab, s.v, &shB, grp);
+  }
   __syncwarp();
   // ... then lane 0 adds the fixed point and the MSM partial sum
   if (lane == 0) {
@@ -68,8 +71,8 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeParams P) {
   }
   if (warp < 3) asm volatile("bar.sync 1, 96;" ::: "memory");   // warps 0-2 only: A, B1 and -(rs)delta1 are ready
   if (warp < 2 && lane < 4) {          // the two variable-base products, four lanes each (finalize.cuh, *_coop)
-    if (warp == 0) var_mul_coop(&sh[0], s.v, scratch, &sh[1], lane);
-    else var_mul_coop(&sh[2], r.v, scratch + 15, &sh[3], lane);
+    if (warp == 0) var_mul_coop(&sh[0], s.v, scratch, &sh[1], grp);
+    else var_mul_coop(&sh[2], r.v, scratch + 15, &sh[3], grp);
   }
   if (lane == 0) {
     if (warp == 2) {
