@@ -11,6 +11,7 @@
 // A/B1/B2/C share the witness as scalars, so they share one sort; bases at infinity ((0,0)) are
 // skipped by the mixed add.  Integer pipe (IMAD.WIDE carry chains) only - no tensor-core work here.
 #include "msm.cuh"
+#include "ec_coop.cuh"
 #include <cstdlib>
 
 namespace zkb {
@@ -362,77 +363,95 @@ __global__ void __launch_bounds__(32) k_accumulate_long(TablePtrs<F> tabs, int n
 // ---------------------------------------------------------------------------------------------
 // bucket reduction  sum_i (i+1) B_i
 // ---------------------------------------------------------------------------------------------
-// level 1: thread = chunk of 32 buckets:  R = sum (u+1) B[32t+u],  S = sum B[32t+u]
-template <class F, int THREADS>
+// COOP = true (small launches, latency shape): every "thread" below is a group of 4 lanes that shares each point
+// addition / doubling (ec_coop.cuh), e.g. 5 instead of 14 product times for a G1 addition.
+template <bool COOP, class F>
+__device__ __forceinline__ void gadd(XYZZ<F> *a, const XYZZ<F> *b, const LaneGroup &g) {
+  if constexpr (COOP) coop_add(a, b, g); else xyzz_add_ni(a, b);
+}
+template <bool COOP, class F>
+__device__ __forceinline__ void gdbl(XYZZ<F> *a, const LaneGroup &g) {
+  if constexpr (COOP) coop_dbl(a, g); else xyzz_dbl_ni(a);
+}
+
+// level 1: thread = chunk of 2^red_log buckets:  R = sum (u+1) B[chunk + u],  S = sum B[chunk + u]
+template <class F, int THREADS, bool COOP>
 __global__ void __launch_bounds__(THREADS) k_reduce1(const XYZZ<F> *buckets, XYZZ<F> *part_r, XYZZ<F> *part_s,
                                                      uint32_t nbuckets, int red_log) {
-  uint32_t t = blockIdx.x * THREADS + threadIdx.x;   // chunk
-  uint32_t slot = blockIdx.y;
+  const uint32_t t = (blockIdx.x * THREADS + threadIdx.x) >> (COOP ? 2 : 0);   // chunk
+  const LaneGroup g = LaneGroup::of(threadIdx.x & 31);
+  const uint32_t slot = blockIdx.y;
   const uint32_t parts = nbuckets >> red_log;
   const XYZZ<F> *B = buckets + (size_t)slot * nbuckets + ((size_t)t << red_log);
   XYZZ<F> run = XYZZ<F>::infinity(), acc = XYZZ<F>::infinity();
   for (int u = (1 << red_log) - 1; u >= 0; u--) {
     XYZZ<F> x = ldg_pod(B + u);
-    xyzz_add_ni(&run, &x);
+    gadd<COOP>(&run, &x, g);
     __syncwarp();
-    xyzz_add_ni(&acc, &run);
+    gadd<COOP>(&acc, &run, g);
     __syncwarp();
   }
-  stg_pod(part_r + (size_t)slot * parts + t, acc);
-  stg_pod(part_s + (size_t)slot * parts + t, run);
+  if (!COOP || g.l == 0) {
+    stg_pod(part_r + (size_t)slot * parts + t, acc);
+    stg_pod(part_s + (size_t)slot * parts + t, run);
+  }
 }
 
 // level 2: one CTA of min(parts, 256) threads per slot.  total = sum_t R_t + 2^red_log * sum_t t * S_t: a thread folds its
 // span of parts, forms t * sigma_t by double-and-add over the bits of t, and both sums are folded by a shared-memory
 // tree, so the depth is ~4 log2(threads) group operations instead of a serial pass over the parts.
-template <class F>
-__device__ void block_tree_sum(XYZZ<F> *sm, XYZZ<F> &v, uint32_t t, uint32_t parts) {
-  stg_pod(sm + t, v);
+template <bool COOP, class F>
+__device__ void block_tree_sum(XYZZ<F> *sm, XYZZ<F> &v, uint32_t t, uint32_t parts, const LaneGroup &g) {
+  const bool writer = !COOP || g.l == 0;
+  if (writer) stg_pod(sm + t, v);
   __syncthreads();
   for (uint32_t stride = parts / 2; stride >= 1; stride >>= 1) {
     if (t < stride) {
-      xyzz_add_ni(&v, sm + t + stride);
-      stg_pod(sm + t, v);
+      XYZZ<F> x = sm[t + stride];
+      gadd<COOP>(&v, &x, g);
+      if (writer) stg_pod(sm + t, v);
     }
     __syncthreads();
   }
 }
 
-template <class F>
-__global__ void __launch_bounds__(256) k_reduce2(const XYZZ<F> *part_r, const XYZZ<F> *part_s, XYZZ<F> *out,
-                                                 uint32_t parts, int red_log) {
+template <class F, bool COOP>
+__global__ void __launch_bounds__(COOP ? 512 : 256) k_reduce2(const XYZZ<F> *part_r, const XYZZ<F> *part_s, XYZZ<F> *out,
+                                                              uint32_t parts, int red_log) {
   extern __shared__ uint4 sm_raw[];
   XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(sm_raw);
-  const uint32_t slot = blockIdx.x, t = threadIdx.x, nthr = blockDim.x, span = parts / nthr;   // a power of two
+  const LaneGroup g = LaneGroup::of(threadIdx.x & 31);
+  const uint32_t slot = blockIdx.x, t = threadIdx.x >> (COOP ? 2 : 0), nthr = blockDim.x >> (COOP ? 2 : 0);
+  const uint32_t span = parts / nthr;   // a power of two
   const XYZZ<F> *R = part_r + (size_t)slot * parts + t * span, *S = part_s + (size_t)slot * parts + t * span;
   // own span: r = sum R, sigma = sum S, rho = sum_u u * S_u
   XYZZ<F> r = XYZZ<F>::infinity(), sigma = XYZZ<F>::infinity(), rho = XYZZ<F>::infinity(), x;
   for (uint32_t u = 0; u < span; u++) {
     x = ldg_pod(R + u);
-    xyzz_add_ni(&r, &x);
+    gadd<COOP>(&r, &x, g);
   }
   for (uint32_t u = span - 1; u >= 1; u--) {
     x = ldg_pod(S + u);
-    xyzz_add_ni(&sigma, &x);
-    xyzz_add_ni(&rho, &sigma);
+    gadd<COOP>(&sigma, &x, g);
+    gadd<COOP>(&rho, &sigma, g);
   }
   x = ldg_pod(S);
-  xyzz_add_ni(&sigma, &x);
-  block_tree_sum<F>(sm, r, t, nthr);               // thread 0: sum_t R_t
+  gadd<COOP>(&sigma, &x, g);
+  block_tree_sum<COOP, F>(sm, r, t, nthr, g);      // thread 0: sum_t R_t
   // sum over the span of (t*span + u) * S = span * (t * sigma) + rho
   XYZZ<F> w = XYZZ<F>::infinity();
   for (int bit = 31 - __clz((int)nthr) - 1; bit >= 0; bit--) {   // t < nthr
-    xyzz_dbl_ni(&w);
-    if ((t >> bit) & 1u) xyzz_add_ni(&w, &sigma);
+    gdbl<COOP>(&w, g);
+    if ((t >> bit) & 1u) gadd<COOP>(&w, &sigma, g);
   }
-  for (uint32_t s = span; s > 1; s >>= 1) xyzz_dbl_ni(&w);
-  xyzz_add_ni(&w, &rho);
+  for (uint32_t s = span; s > 1; s >>= 1) gdbl<COOP>(&w, g);
+  gadd<COOP>(&w, &rho, g);
   __syncthreads();
-  block_tree_sum<F>(sm, w, t, nthr);               // thread 0: sum_t t * S_t
+  block_tree_sum<COOP, F>(sm, w, t, nthr, g);      // thread 0: sum_t t * S_t
   if (t == 0) {
-    for (int i = 0; i < red_log; i++) xyzz_dbl_ni(&w);   // * chunk size
-    xyzz_add_ni(&w, &r);
-    stg_pod(out + slot, w);
+    for (int i = 0; i < red_log; i++) gdbl<COOP>(&w, g);   // * chunk size
+    gadd<COOP>(&w, &r, g);
+    if (!COOP || g.l == 0) stg_pod(out + slot, w);
   }
 }
 
@@ -503,21 +522,31 @@ cudaError_t msm_reduce(MsmWork<F> &work, uint32_t slot0, uint32_t nslots, XYZZ<F
   if (slot0 + nslots > work.slots) return cudaErrorInvalidValue;
   constexpr int RT = AccCfg<F>::RED_THREADS;
   const uint32_t nb = work.cfg.buckets;
-  const int red_log = (uint64_t)nslots * nb < 262144 ? RED_LOG_LAT : RED_LOG;
+  if ((uint64_t)nslots * nb < 262144) {
+    // latency shape: lane groups of 4 share every point operation; chunks of 8 buckets (32 for the 2^15-bucket H sums)
+    const int red_log = nb > 8192 ? RED_LOG : RED_LOG_LAT;
+    const uint32_t parts = nb >> red_log, nthr = parts < 128 ? parts : 128;
+    k_reduce1<F, 128, true><<<dim3(parts * 4 / 128, nslots), 128, 0, st>>>(
+        work.buckets + (size_t)slot0 * nb, work.part_r + (size_t)slot0 * parts, work.part_s + (size_t)slot0 * parts, nb, red_log);
+    k_reduce2<F, true><<<nslots, nthr * 4, nthr * sizeof(XYZZ<F>), st>>>(work.part_r + (size_t)slot0 * parts,
+                                                                       work.part_s + (size_t)slot0 * parts, out, parts, red_log);
+    return cudaGetLastError();
+  }
+  const int red_log = RED_LOG;
   const uint32_t parts = nb >> red_log;
   dim3 g1(parts / RT, nslots);
-  k_reduce1<F, RT><<<g1, RT, 0, st>>>(work.buckets + (size_t)slot0 * nb, work.part_r + (size_t)slot0 * parts,
-                                      work.part_s + (size_t)slot0 * parts, nb, red_log);
+  k_reduce1<F, RT, false><<<g1, RT, 0, st>>>(work.buckets + (size_t)slot0 * nb, work.part_r + (size_t)slot0 * parts,
+                                             work.part_s + (size_t)slot0 * parts, nb, red_log);
   const uint32_t nthr = parts < 256 ? parts : 256;
   static bool attr_set[64] = {};            // function attributes are per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaFuncSetAttribute(k_reduce2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * (int)sizeof(XYZZ<F>));
+    cudaFuncSetAttribute(k_reduce2<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * (int)sizeof(XYZZ<F>));
     attr_set[dev & 63] = true;
   }
-  k_reduce2<F><<<nslots, nthr, nthr * sizeof(XYZZ<F>), st>>>(work.part_r + (size_t)slot0 * parts,
-                                                              work.part_s + (size_t)slot0 * parts, out, parts, red_log);
+  k_reduce2<F, false><<<nslots, nthr, nthr * sizeof(XYZZ<F>), st>>>(work.part_r + (size_t)slot0 * parts,
+                                                                     work.part_s + (size_t)slot0 * parts, out, parts, red_log);
   return cudaGetLastError();
 }
 
