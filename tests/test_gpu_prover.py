@@ -377,3 +377,21 @@ def test_maximum_depth_census_bit_exact(circuit):
     bad["censusSiblings"] = vs[0]["censusSiblings"][:160] + ["1"]
     assert circuit.fullprove_batch([json.dumps(bad)])[2] == [4]
     assert _ref_witness(bad)[0] == 4
+
+
+def test_inputs_are_reduced_mod_r_like_circom_runtime(circuit):
+    """circom_runtime normalises every input with Fr.e(): values >= r and negative values are taken mod r.  The same
+    inputs.json with voteHash[0] + r and voteHash[1] - r must give the same witness and public signals."""
+    inp = H.fixture_inputs()
+    R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    alt = dict(inp)
+    alt["voteHash"] = [str(int(inp["voteHash"][0]) + R), str(int(inp["voteHash"][1]) - R)]
+    w0 = H.wtns_payload(circuit.witness(json.dumps(inp)), circuit.n_vars)
+    w1 = H.wtns_payload(circuit.witness(json.dumps(alt)), circuit.n_vars)
+    assert np.array_equal(w0, w1)
+    _, sj = circuit.fullprove(json.dumps(alt))
+    assert json.loads(sj) == json.load(open(H.GOLDEN + "/signals.json"))
+    # bare JSON numbers are accepted as well as strings
+    alt2 = dict(inp)
+    alt2["voteWeight"] = int(inp["voteWeight"])
+    assert np.array_equal(H.wtns_payload(circuit.witness(json.dumps(alt2)), circuit.n_vars), w0)
