@@ -43,6 +43,17 @@ def test_no_gpu_means_error_not_fallback():
     assert b"no CPU fallback" in L.zkb_last_error()
     buf = (ctypes.c_uint8 * 64)()
     assert L.zkb_raw_field_op(0, 0, buf, buf, buf, ctypes.c_size_t(2)) == 1
+    # the raw sessions and the verifier are compute entry points too
+    h = ctypes.c_void_p()
+    assert L.zkb_msm_session_create(0, 16, 0, 1, ctypes.c_uint64(1), 16, ctypes.byref(h)) == 1
+    assert L.zkb_ntt_dist_create(0, 24, 0, 1, ctypes.c_uint64(1), ctypes.byref(h)) == 1
+    f = ctypes.c_float()
+    assert L.zkb_ntt_bench(0, 16, 1, 1, ctypes.byref(f), ctypes.byref(f)) == 1
+    vk = open(H.GOLDEN + "/verification_key.json", "rb").read()
+    pf = open(H.GOLDEN + "/proof.json", "rb").read()
+    pub = open(H.GOLDEN + "/signals.json", "rb").read()
+    L.zkb_verify.argtypes = [ctypes.c_char_p, ctypes.c_size_t] * 3
+    assert L.zkb_verify(vk, len(vk), pub, len(pub), pf, len(pf)) == 1     # error, not "valid" and not a CPU pairing
 
 
 def test_product_does_not_import_oracle():
