@@ -174,6 +174,15 @@ def run_ours(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    # stdout carries exactly ONE JSON line: native libraries that print to fd 1 (NCCL's version banner under
+    # NCCL_DEBUG=VERSION/INFO) are sent to stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def restore_stdout():
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -295,8 +304,10 @@ def run_ours(args, rank, world, local_rank):
             "stage_ms_per_step": {k: float(v) for k, v in zip(
                 ("witness", "build_abc", "ntt_join", "msm_sort", "msm_acc_g1", "msm_acc_g2", "msm_reduce", "finalize"), stages)},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
+    restore_stdout()
     print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
