@@ -220,7 +220,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     launches = prover.launch_count() - launches0
     # per-kernel durations: the same K steps once more, instrumented with CUDA events between the stages and run
-    # serially on one lane (in the timed loop above chunks overlap on two streams, which would smear the brackets)
+    # serially on one lane (in the timed loop above chunks overlap on four streams, which would smear the brackets)
     stages = np.zeros(8, dtype=np.float64)
     for _ in range(args.steps):
         stages += c.prove_resident(batch, stages=True)
@@ -276,7 +276,7 @@ def run_ours(args, rank, world, local_rank):
                                "137 IMAD.WIDE each); MEASURED_PEAKS.json has no integer-pipe figure",
                 "share_of_step": float(stages[4] / stages.sum()) if stages.sum() else None,
                 "measured_in": "instrumented serial pass (1 lane) over the same K steps, CUDA events on the launching "
-                               "stream; the timed loop overlaps chunks on 2 streams",
+                               "stream; the timed loop overlaps chunks on 4 streams",
                 "traffic_note": "dram__bytes_read+write of the largest k_accumulate<Fq> launch (H MSM of one 128-proof chunk: "
                                 "128 x 2.1 M gathered 64-byte table points = 17.2 GB algorithmic) from profiles/r01_traffic.json",
                 "hbm_gbs_measured": measured_peaks().get("hbm_gbs")}

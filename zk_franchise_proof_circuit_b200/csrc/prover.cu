@@ -3,7 +3,7 @@
 // (`zk_census_test.go:89`) / `groth16.fullProve` (`ts_inputs/src/example.ts:358-362`):
 //
 //   inputs.json --host parse--> 2n+12 canonical Fr values per proof --H2D-->
-//   k_witness        census witness, 3 threads per proof            
+//   k_witness        census witness, 5 tasks per proof (hash chains on 8 lanes each), then k_witness_gather (W1-W7)
 //   k_build_abc      A_T, B_T from the CSR coefficients, C_T = A_T o B_T   (G2)
 //   NTT              iNTT -> coset shift -> NTT on 3 vectors per proof     (G3)
 //   k_join           h = a*b - c, to canonical form                        (G4)
