@@ -1,10 +1,14 @@
+#!/usr/bin/env python3
+"""Host-side view of single-proof latency: medians of zkb_fullprove (inputs.json -> proof.json), of the resident
+device pass alone, and of the copies around it."""
 import json,os,sys,time
-sys.path.insert(0,"/root/repo")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import numpy as np
 from zk_franchise_proof_circuit_b200 import prover
-ART="/root/repo/artifacts/zkCensus/dev/160"
+ART = os.path.join(ROOT, "artifacts", "zkCensus", "dev", "160")
 c=prover.load(open(ART+"/proving_key.zkey","rb").read(),open(ART+"/circuit.wasm","rb").read())
-doc=open("/root/repo/tests/golden/inputs_example.json","rb").read()
+doc=open(os.path.join(ROOT, "tests", "golden", "inputs_example.json"),"rb").read()
 inp=json.loads(doc)
 for _ in range(5): c.fullprove(doc)
 def med(f,n=30):
