@@ -51,6 +51,12 @@ void *zkb_ctx_stream(zkb_ctx *ctx); /* cudaStream_t the pipeline runs on (for ex
  * Returns ZKB_UNSUPPORTED_CIRCUIT when the wasm is not a census.circom witness calculator. */
 int zkb_load_circuit(zkb_ctx *ctx, const void *zkey, size_t zkey_len, const void *wasm, size_t wasm_len,
                      zkb_circuit **out);
+/* flags bit 0 (ZKB_LOAD_DENSE): switch the proof-independent-wire shortcut off - every SMT level is
+ * hashed and the four witness MSMs run over all nVars wires, i.e. the work snarkjs / rapidsnark do.  Measurement aid:
+ * bench.py reports this point next to the default so the GPU speed-up can be separated from the algorithmic one. */
+#define ZKB_LOAD_DENSE 1u
+int zkb_load_circuit_ex(zkb_ctx *ctx, const void *zkey, size_t zkey_len, const void *wasm, size_t wasm_len,
+                        uint32_t flags, zkb_circuit **out);
 void zkb_circuit_destroy(zkb_circuit *c);
 /* info[8] = nVars, nPublic, domainSize, nInputs, nLevels+1, nSignals, chunk, resident capacity */
 int zkb_circuit_info(zkb_circuit *c, uint32_t *info);
@@ -103,6 +109,17 @@ int groth16_prover(const void *zkey_buffer, unsigned long zkey_size, const void 
                    char *proof_buffer, unsigned long *proof_size, char *public_buffer, unsigned long *public_size,
                    char *error_msg, unsigned long error_msg_maxsize);
 
+/* Entry points later rapidsnark releases added to prover.h (bound by newer go-rapidsnark/prover versions); same
+ * names and argument order, `unsigned long` == their `unsigned long long` on LP64.  Return 0 / 1 / 2 as above. */
+void groth16_proof_size(unsigned long *proof_size);
+int groth16_public_size_for_zkey_buf(const void *zkey_buffer, unsigned long zkey_size, unsigned long *public_size,
+                                     char *error_msg, unsigned long error_msg_maxsize);
+int groth16_public_size_for_zkey_file(const char *zkey_fname, unsigned long *public_size, char *error_msg,
+                                      unsigned long error_msg_maxsize);
+int groth16_prover_zkey_file(const char *zkey_file_path, const void *wtns_buffer, unsigned long wtns_size,
+                             char *proof_buffer, unsigned long *proof_size, char *public_buffer,
+                             unsigned long *public_size, char *error_msg, unsigned long error_msg_maxsize);
+
 /* Groth16 verification on the GPU (one proof per thread): (*Proof).Verify(vkey) of zk_census_test.go:122 /
  * `snarkjs groth16 verify`.  Documents are the reference's JSON files (verification_key.json, signals.json,
  * proof.json).  zkb_verify returns ZKB_OK when the proof is valid and ZKB_INVALID_PROOF when it is not;
@@ -112,6 +129,9 @@ int zkb_verify(const char *vkey_json, size_t vkey_len, const char *public_json, 
                const char *proof_json, size_t proof_len);
 int zkb_verify_batch(const char *vkey_json, size_t vkey_len, int n, const char *const *publics_json,
                      const size_t *publics_len, const char *const *proofs_json, const size_t *proofs_len, int *ok);
+
+/* The same check on binary results (the layout of zkb_batch_get_results): proofs256 = n x 256 B, publics = n x nPublic x 32 B. */
+int zkb_verify_batch_bin(const char *vkey_json, size_t vkey_len, int n, const void *publics, const void *proofs256, int *ok);
 
 /* Batched Poseidon with the circuit's constants (arity 2..4): the hash function of the census and SIK trees
  * (arbo.HashFunctionPoseidon, internal/helpers.go:45-49; circomlibjs in ts_inputs/src/inputs.ts:16,33).

@@ -242,16 +242,58 @@ template <class F> static Jac<F> smul(const Aff<F> &p, const Fr &k) {
 
 struct ProofPts { G1A A, C; G2A B; };
 
+// The proof-independent-wire shortcut of SURVEY.md 8a W7 on the CPU (the "CPU with the same shortcut" leg of the bench):
+// sum_i w_i P_i = sum_i tmpl_i P_i + sum_i (w_i - tmpl_i) P_i, the first sum cached per (key, template), the second
+// over the few thousand wires that differ.  The H MSM and the transforms are unchanged.
+struct TemplateSums {
+  const ZKey *z = nullptr;
+  std::vector<uint8_t> tmpl;
+  G1J a, b1, c;
+  G2J b2;
+};
+static TemplateSums g_tsums;
+
 static void prove(const ZKey &z, const uint8_t *wtns, const Fr &r, const Fr &s, ProofPts &out,
-                  uint8_t *partials /* optional: pi_a', pi_b1', pi_b' (G2), pi_c', pi_h as raw */) {
+                  uint8_t *partials /* optional: pi_a', pi_b1', pi_b' (G2), pi_c', pi_h as raw */,
+                  const uint8_t *tmpl = nullptr /* optional: template witness (shortcut) */) {
   std::vector<Fr> h;
   compute_h(z, wtns, h);
   std::vector<uint8_t> hb;
   fr_vec_to_bytes(h, hb);
-  G1J pa = msm<Fq>(z.A.data(), wtns, z.nVars);
-  G1J pb1 = msm<Fq>(z.B1.data(), wtns, z.nVars);
-  G2J pb = msm<Fq2>(z.B2.data(), wtns, z.nVars);
-  G1J pc = msm<Fq>(z.C.data(), wtns + 32 * (z.nPublic + 1), z.nVars - z.nPublic - 1);
+  G1J pa, pb1, pc;
+  G2J pb;
+  if (tmpl) {
+    TemplateSums &t = g_tsums;
+    if (t.z != &z || t.tmpl.size() != (size_t)z.nVars * 32 || memcmp(t.tmpl.data(), tmpl, t.tmpl.size()) != 0) {
+      t.z = &z;
+      t.tmpl.assign(tmpl, tmpl + (size_t)z.nVars * 32);
+      t.a = msm<Fq>(z.A.data(), tmpl, z.nVars);
+      t.b1 = msm<Fq>(z.B1.data(), tmpl, z.nVars);
+      t.b2 = msm<Fq2>(z.B2.data(), tmpl, z.nVars);
+      t.c = msm<Fq>(z.C.data(), tmpl + 32 * (z.nPublic + 1), z.nVars - z.nPublic - 1);
+    }
+    std::vector<G1A> ba, bb1, bc;
+    std::vector<G2A> bb2;
+    std::vector<uint8_t> sd, sdc;
+    for (size_t i = 0; i < z.nVars; i++) {
+      if (memcmp(wtns + 32 * i, tmpl + 32 * i, 32) == 0) continue;
+      Fr d = Fr::from_bytes(wtns + 32 * i) - Fr::from_bytes(tmpl + 32 * i);
+      uint8_t db[32];
+      d.to_bytes(db);
+      sd.insert(sd.end(), db, db + 32);
+      ba.push_back(z.A[i]); bb1.push_back(z.B1[i]); bb2.push_back(z.B2[i]);
+      if (i > z.nPublic) { bc.push_back(z.C[i - z.nPublic - 1]); sdc.insert(sdc.end(), db, db + 32); }
+    }
+    pa = t.a.add(msm<Fq>(ba.data(), sd.data(), ba.size()));
+    pb1 = t.b1.add(msm<Fq>(bb1.data(), sd.data(), bb1.size()));
+    pb = t.b2.add(msm<Fq2>(bb2.data(), sd.data(), bb2.size()));
+    pc = t.c.add(msm<Fq>(bc.data(), sdc.data(), bc.size()));
+  } else {
+    pa = msm<Fq>(z.A.data(), wtns, z.nVars);
+    pb1 = msm<Fq>(z.B1.data(), wtns, z.nVars);
+    pb = msm<Fq2>(z.B2.data(), wtns, z.nVars);
+    pc = msm<Fq>(z.C.data(), wtns + 32 * (z.nPublic + 1), z.nVars - z.nPublic - 1);
+  }
   G1J ph = msm<Fq>(z.H.data(), hb.data(), z.domainSize);
   if (partials) {
     write_g1_raw(partials, pa.to_aff());
@@ -783,6 +825,20 @@ int orc_prove(const uint8_t *zkey, size_t len, const uint8_t *wtns, const uint8_
   if (!z) return 1;
   ProofPts pf;
   prove(*z, wtns, Fr::from_bytes(r32), Fr::from_bytes(s32), pf, partials);
+  write_g1_raw(proof256, pf.A);
+  write_g2_raw(proof256 + 64, pf.B);
+  write_g1_raw(proof256 + 192, pf.C);
+  return 0;
+}
+
+// same proof through the template-difference shortcut (tmpl: nVars x 32 canonical LE, e.g. the witness of another voter)
+int orc_prove_shortcut(const uint8_t *zkey, size_t len, const uint8_t *wtns, const uint8_t *tmpl, const uint8_t *r32,
+                       const uint8_t *s32, uint8_t *proof256) {
+  oracle_init();
+  ZKey *z = get_zkey(zkey, len);
+  if (!z) return 1;
+  ProofPts pf;
+  prove(*z, wtns, Fr::from_bytes(r32), Fr::from_bytes(s32), pf, nullptr, tmpl);
   write_g1_raw(proof256, pf.A);
   write_g2_raw(proof256 + 64, pf.B);
   write_g1_raw(proof256 + 192, pf.C);

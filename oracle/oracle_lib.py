@@ -21,6 +21,7 @@ def lib():
         L.orc_setup.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, u64]
         L.orc_zkey_info.argtypes = [vp, sz, vp]
         L.orc_prove.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+        L.orc_prove_shortcut.argtypes = [vp, sz, vp, vp, vp, vp, vp]
         L.orc_h_scalars.argtypes = [vp, sz, vp, vp, vp]
         L.orc_verify.argtypes = [vp, vp, i32, vp, vp]
         L.orc_verify_many.argtypes = [vp, vp, i32, vp, vp, i32, vp]
@@ -144,6 +145,18 @@ class ZKeyRef:
         if rc:
             raise RuntimeError("orc_prove failed")
         return (out.tobytes(), part.tobytes()) if partials else out.tobytes()
+
+    def prove_shortcut(self, wtns: np.ndarray, tmpl: np.ndarray, r: int, s: int):
+        """Same proof as prove(), computed with the proof-independent-wire shortcut: the four witness
+        MSMs run over (wtns - tmpl) only, the template sums are cached per (key, template)."""
+        w = np.ascontiguousarray(wtns, dtype=np.uint8)
+        t = np.ascontiguousarray(tmpl, dtype=np.uint8)
+        out = np.zeros(256, dtype=np.uint8)
+        rc = lib().orc_prove_shortcut(self.arr.ctypes.data, self.arr.size, w.ctypes.data, t.ctypes.data, _buf(le32(r)),
+                                      _buf(le32(s)), out.ctypes.data)
+        if rc:
+            raise RuntimeError("orc_prove_shortcut failed")
+        return out.tobytes()
 
     def h_scalars(self, wtns: np.ndarray, abc=False):
         w = np.ascontiguousarray(wtns, dtype=np.uint8)

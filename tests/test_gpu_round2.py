@@ -1,0 +1,204 @@
+"""GPU parity tests added in round 2: the full 1,024-proof configuration, the proof-independent-wire shortcut
+switched off (ZKB_LOAD_DENSE), censuses of a chosen depth, the binary batch verifier, the hardened .wtns parser and the
+later rapidsnark prover.h entry points.  Everything goes through the C ABI (ctypes)."""
+import ctypes
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import helpers as H
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def files(art_dir):
+    return (open(art_dir + "/proving_key.zkey", "rb").read(), open(art_dir + "/circuit.wasm", "rb").read(),
+            open(art_dir + "/verification_key.json", "rb").read())
+
+
+@pytest.fixture(scope="module")
+def circuit(files):
+    from zk_franchise_proof_circuit_b200 import prover
+    return prover.load(files[0], files[1])
+
+
+def _ref_witness(inputs):
+    import ref_witness as RW
+    if not RW.available():
+        pytest.skip("oracle/_ref not built")
+    return RW.witness(inputs)
+
+
+def test_config2_all_1024_proofs_verify_and_sample_matches_oracle(circuit, files):
+    """BASELINE configs[1] at its full size: 1,024 proofs with r = 1234567, s = 7654321; ALL verified (GPU verifier and,
+    for a slice, the CPU oracle's verifier), 6 spread over the four pipeline lanes compared limb for limb with the
+    CPU oracle."""
+    from zk_franchise_proof_circuit_b200 import prover
+    vs = H.voters(1024)
+    packed = np.stack([prover.pack_inputs(v) for v in vs])
+    circuit.set_blinding(H.R_FIXED, H.S_FIXED)
+    try:
+        circuit.set_inputs(packed)
+        circuit.prove_resident()
+    finally:
+        circuit.set_blinding(None, None)
+    proofs, pubs, status = circuit.get_results()
+    assert (status == 0).all()
+    assert prover.verify_batch_bin(files[2], pubs, proofs).sum() == 1024
+    assert O.verify_many(H.dev_vkey(), pubs[:32].tobytes(), proofs[:32].tobytes(), 32).all()
+    for i in (0, 127, 128, 511, 640, 1023):
+        code, w = _ref_witness(vs[i])
+        assert code == 0
+        assert proofs[i].tobytes() == H.zkey_ref().prove(w, H.R_FIXED, H.S_FIXED), f"voter {i}"
+    # tampering is caught by the binary verifier too
+    bad = proofs[:4].copy()
+    bad[1, 0] ^= 1
+    bad[2, 255] = 0xFF                                   # coordinate >= q
+    assert list(prover.verify_batch_bin(files[2], pubs[:4], bad)) == [1, 0, 0, 1]
+
+
+def test_dense_circuit_matches_oracle(files):
+    """ZKB_LOAD_DENSE: no template, all 161 levels hashed, A/B1/B2/C over all wires - same witness, same proof."""
+    from zk_franchise_proof_circuit_b200 import prover
+    c = prover.load(files[0], files[1], dense=True)
+    vs = [H.fixture_inputs()] + list(H.voters(3)) + [H.deep_voters()[0]]
+    c.set_blinding(H.R_FIXED, H.S_FIXED)
+    try:
+        proofs, pubs, status = c.fullprove_batch([json.dumps(v) for v in vs])
+    finally:
+        c.set_blinding(None, None)
+    assert status == [0] * len(vs)
+    for i, v in enumerate(vs):
+        code, w = _ref_witness(v)
+        assert np.array_equal(c.get_witness(i, 1)[0], w), f"witness {i}"
+        assert O.proof_bin(json.loads(proofs[i])) == H.zkey_ref().prove(w, H.R_FIXED, H.S_FIXED), f"proof {i}"
+    c.close()
+    prover._circuits.clear()
+
+
+@pytest.mark.parametrize("depth", [1, 4, 40, 160])
+def test_census_of_chosen_depth(circuit, files, depth):
+    """census_tree.gen_census_depth (bench.py's depth sweep): inputs pass the reference wasm, the GPU witness is
+    bit-exact, proofs == oracle and verify."""
+    from zk_franchise_proof_circuit_b200 import prover, census_tree
+    vs = census_tree.gen_census_depth(circuit, 3, depth, seed=11)
+    assert all(census_tree.tree_depth(v) == depth for v in vs)
+    circuit.set_blinding(H.R_FIXED, H.S_FIXED)
+    try:
+        proofs, pubs, status = circuit.fullprove_batch([json.dumps(v) for v in vs])
+    finally:
+        circuit.set_blinding(None, None)
+    assert status == [0, 0, 0]
+    assert prover.verify_batch(files[2], pubs, proofs) == [1, 1, 1]
+    code, w = _ref_witness(vs[1])
+    assert code == 0
+    assert np.array_equal(circuit.get_witness(1, 1)[0], w)
+    assert O.proof_bin(json.loads(proofs[1])) == H.zkey_ref().prove(w, H.R_FIXED, H.S_FIXED)
+
+
+def _wtns_bytes(w, n8=32, prime=None, data_len=None):
+    prime = prime if prime is not None else census_r()
+    body = w.tobytes()
+    if data_len is not None:
+        body = body[:data_len]
+    return (b"wtns" + struct.pack("<II", 2, 2) + struct.pack("<IQ", 1, 40) + struct.pack("<I", n8) +
+            prime.to_bytes(32, "little") + struct.pack("<I", w.shape[0]) + struct.pack("<IQ", 2, len(body)) + body)
+
+
+def census_r():
+    return 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def test_wtns_parser_rejects_malformed(circuit):
+    """short data sections, wrong field size / prime and non-canonical values are errors, not reads past
+    the caller's buffer."""
+    from zk_franchise_proof_circuit_b200.prover import NativeError
+    code, w = _ref_witness(H.fixture_inputs())
+    good = _wtns_bytes(w)
+    pj, sj = circuit.prove_wtns(good)
+    assert json.loads(sj) == json.load(open(H.GOLDEN + "/signals.json"))
+    for bad in (_wtns_bytes(w, data_len=w.size - 32), _wtns_bytes(w, n8=64), _wtns_bytes(w, prime=census_r() + 2)):
+        with pytest.raises(NativeError):
+            circuit.prove_wtns(bad)
+    w2 = w.copy()
+    w2[5] = np.frombuffer((census_r() + 1).to_bytes(32, "little"), dtype=np.uint8)
+    with pytest.raises(NativeError):
+        circuit.prove_wtns(_wtns_bytes(w2))
+    with pytest.raises(NativeError):
+        circuit.prove_wtns(good[:200])
+
+
+def test_rapidsnark_later_entry_points(files, tmp_path):
+    """groth16_public_size_for_zkey_buf / _file, groth16_proof_size, groth16_prover_zkey_file: same answers as
+    groth16_prover; the key cache tells two keys of equal size apart."""
+    from zk_franchise_proof_circuit_b200 import _native, prover
+    L = _native.lib()
+    ul, vp = ctypes.c_ulong, ctypes.c_void_p
+    L.groth16_proof_size.argtypes = [ctypes.POINTER(ul)]
+    L.groth16_proof_size.restype = None
+    L.groth16_public_size_for_zkey_buf.argtypes = [vp, ul, ctypes.POINTER(ul), vp, ul]
+    L.groth16_public_size_for_zkey_file.argtypes = [ctypes.c_char_p, ctypes.POINTER(ul), vp, ul]
+    L.groth16_prover_zkey_file.argtypes = [ctypes.c_char_p, vp, ul, vp, ctypes.POINTER(ul), vp, ctypes.POINTER(ul), vp, ul]
+    prover._lib()
+    zkey = files[0]
+    zb = (ctypes.c_char * len(zkey)).from_buffer_copy(zkey)
+    n = ul(0)
+    L.groth16_proof_size(ctypes.byref(n))
+    assert n.value >= 700
+    err = ctypes.create_string_buffer(256)
+    assert L.groth16_public_size_for_zkey_buf(ctypes.addressof(zb), len(zkey), ctypes.byref(n), err, 256) == 0
+    assert n.value >= 8 * 80
+    assert L.groth16_public_size_for_zkey_buf(ctypes.addressof(zb), 100, ctypes.byref(n), err, 256) == 1
+    zpath = os.path.join(H.ART, "proving_key.zkey").encode()
+    assert L.groth16_public_size_for_zkey_file(zpath, ctypes.byref(n), err, 256) == 0
+    code, w = _ref_witness(H.fixture_inputs())
+    wt = _wtns_bytes(w)
+    wb = (ctypes.c_char * len(wt)).from_buffer_copy(wt)
+    pbuf, qbuf = ctypes.create_string_buffer(2048), ctypes.create_string_buffer(2048)
+    pn, qn = ul(2048), ul(2048)
+    assert L.groth16_prover_zkey_file(zpath, ctypes.addressof(wb), len(wt), pbuf, ctypes.byref(pn), qbuf, ctypes.byref(qn), err, 256) == 0, err.value
+    assert json.loads(qbuf.raw[:qn.value]) == json.load(open(H.GOLDEN + "/signals.json"))
+    assert O.verify(H.dev_vkey(), json.loads(qbuf.raw[:qn.value]), json.loads(pbuf.raw[:pn.value]))
+    # a second key of the SAME size that differs only deep inside a point section must not reuse the cached tables:
+    # flip one bit in section 9 (H points) -> the proof of the same witness changes (and no longer verifies)
+    z2 = bytearray(zkey)
+    pos, off9 = 12, None
+    for _ in range(struct.unpack_from("<I", zkey, 8)[0]):
+        sid, sz = struct.unpack_from("<IQ", zkey, pos)
+        if sid == 9:
+            off9 = pos + 12
+        pos += 12 + sz
+    z2[off9 + 64 * 777 + 5] ^= 1
+    z2b = (ctypes.c_char * len(z2)).from_buffer_copy(bytes(z2))
+    outs = []
+    for key in (zb, z2b, zb):
+        buf = ctypes.create_string_buffer(2048)
+        pn, qn = ul(2048), ul(2048)
+        assert L.groth16_prover(ctypes.addressof(key), len(zkey), ctypes.addressof(wb), len(wt), buf, ctypes.byref(pn), qbuf,
+                                ctypes.byref(qn), err, 256) == 0, err.value
+        outs.append(json.loads(buf.raw[:pn.value]))
+    pub = json.load(open(H.GOLDEN + "/signals.json"))
+    assert O.verify(H.dev_vkey(), pub, outs[0]) and O.verify(H.dev_vkey(), pub, outs[2])
+    assert not O.verify(H.dev_vkey(), pub, outs[1])
+
+
+def test_verify_runs_on_the_current_device(files):
+    """the verifier caches its device objects per GPU (no cross-device pointers)."""
+    from zk_franchise_proof_circuit_b200 import prover, _native
+    pf = open(H.GOLDEN + "/proof.json", "rb").read()
+    pub = open(H.GOLDEN + "/signals.json", "rb").read()
+    vk = open(H.GOLDEN + "/verification_key.json", "rb").read()
+    prover.verify(vk, pub, pf)
+    if _native.lib().zkb_device_count() >= 2:
+        cuda = ctypes.CDLL("libcudart.so.12")
+        cuda.cudaSetDevice(1)
+        try:
+            prover.verify(vk, pub, pf)
+        finally:
+            cuda.cudaSetDevice(0)
+    prover.verify(vk, pub, pf)

@@ -54,6 +54,35 @@ def test_oracle_prove_verifies_and_matches_closed_form(art_dir):
     assert pf2 != pf and O.verify(H.dev_vkey(), pub, O.proof_json(pf2))
 
 
+def test_oracle_shortcut_prove_equals_dense_prove(art_dir):
+    """The "CPU with the same shortcut" leg of bench.py (SURVEY 8a W7 / BASELINE.md section 3): the four witness MSMs
+    over (w - template) + cached template sums give the same proof as the dense prover, whatever the template."""
+    import ref_witness as RW
+    if not RW.available():
+        pytest.skip("oracle/_ref not built")
+    _, w = RW.witness(H.fixture_inputs())
+    _, t = RW.witness(H.voters(2)[1])
+    zk = H.zkey_ref()
+    want = zk.prove(w, H.R_FIXED, H.S_FIXED)
+    assert zk.prove_shortcut(w, t, H.R_FIXED, H.S_FIXED) == want
+    assert zk.prove_shortcut(w, w, H.R_FIXED, H.S_FIXED) == want          # empty difference
+    assert zk.prove_shortcut(w, np.zeros_like(w), H.R_FIXED, H.S_FIXED) == want   # empty template
+
+
+def test_chain600_kat_pins_the_committed_artifacts():
+    """tests/golden/chain600_kat.json (what bench.py --gpus N compares the sharded proof with) matches the key and
+    witness build() generates into artifacts/chain600, and its proof verifies under that key's vkey."""
+    import hashlib
+    d = os.path.join(H.ROOT, "artifacts", "chain600")
+    if not os.path.exists(os.path.join(d, "proving_key.zkey")):
+        pytest.skip("artifacts/chain600 not generated (run __graft_entry__.build())")
+    kat = json.load(open(H.GOLDEN + "/chain600_kat.json"))
+    assert hashlib.sha256(open(os.path.join(d, "proving_key.zkey"), "rb").read()).hexdigest() == kat["zkey_sha256"]
+    assert hashlib.sha256(open(os.path.join(d, "witness.wtns"), "rb").read()).hexdigest() == kat["wtns_sha256"]
+    vk = json.load(open(os.path.join(d, "verification_key.json")))
+    assert O.verify(vk, kat["public"], kat["proof"])
+
+
 def test_oracle_ntt_and_msm_self_consistency():
     rng = np.random.default_rng(3)
     v = rng.integers(0, 256, size=(1 << 10, 32), dtype=np.uint8)

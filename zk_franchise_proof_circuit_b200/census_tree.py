@@ -118,3 +118,74 @@ def gen_census(circuit, n_voters, seed=0xC0FFEE, n_levels=160, available_weight=
             "sikSiblings": pad(siktree.siblings(a)),
         })
     return out
+
+
+def tree_depth(inputs: dict) -> int:
+    """Depth of a voter's Merkle path as the circuit sees it: index of the last non-zero sibling + 1, maximum over the
+    census and SIK trees (SMTLevIns; the levels below are the proof-independent Poseidon2(0,0) blocks of SURVEY 8a W7)."""
+    d = 0
+    for k in ("censusSiblings", "sikSiblings"):
+        nz = [i for i, x in enumerate(inputs[k]) if int(x) != 0]
+        d = max(d, nz[-1] + 1 if nz else 0)
+    return d
+
+
+def gen_census_depth(circuit, n_voters, depth, seed=0xC0FFEE, n_levels=160, available_weight=10, vote_weight=5):
+    """n_voters inputs dicts whose Merkle paths have exactly `depth` non-zero siblings in both trees (1 <= depth <=
+    n_levels): every voter sits in its own comb-shaped census of depth + 1 leaves - the voter's address plus, for every
+    level j < depth, the address with bit j flipped, which splits off alone at level j (arbo semantics as in
+    SparseMerkleTree).  The sibling at level j is then that leaf's hash and the voter's own leaf sits at level `depth`.
+    All voters' trees are hashed together, one batched Poseidon launch per level (zkb_poseidon_hash).
+    Used by bench.py to measure throughput as a function of the tree depth (SURVEY.md 8a W7 measurement rule):
+    depth 4 is the reference's own 10-leaf shape (internal/helpers.go:56-61), depth 160 the circuit's maximum."""
+    assert 1 <= depth <= n_levels
+    H = circuit.poseidon
+    sd = seed.to_bytes(8, "big")
+    password = int.from_bytes(b"password123", "big") % R_MOD
+    election = bytes_to_arbo(bytes.fromhex(ELECTION_HEX))
+    vote_hash = bytes_to_arbo(available_weight.to_bytes(1, "big"))
+    addrs, sigs = [], []
+    for i in range(n_voters):
+        ib = i.to_bytes(4, "big") + depth.to_bytes(2, "big")
+        addrs.append(int.from_bytes(hashlib.sha256(sd + b"deep-addr" + ib).digest()[:20], "little"))
+        sig = b"".join(hashlib.sha256(sd + b"deep-sig" + ib + bytes([c])).digest() for c in range(2))
+        sigs.append(int.from_bytes(sig, "big") % R_MOD)
+    nulls = H([(s, password, election[0], election[1]) for s in sigs])
+    sik_own = H([(a, password, s) for a, s in zip(addrs, sigs)])
+    # the flipped-bit neighbours: census value = weight, SIK value = an arbitrary non-zero field element
+    nb_keys = [[a ^ (1 << j) for j in range(depth)] for a in addrs]
+    nb_sik = [[int.from_bytes(hashlib.sha256(sd + b"nb-sik" + k.to_bytes(20, "little")).digest(), "big") % R_MOD
+               for k in ks] for ks in nb_keys]
+    out = []
+    roots, sibs = {}, {}
+    for name, own_val, nb_val in (("census", [available_weight] * n_voters, None), ("sik", sik_own, nb_sik)):
+        leaf_rows = []
+        for v in range(n_voters):
+            leaf_rows.append((addrs[v], own_val[v], 1))
+            for j in range(depth):
+                leaf_rows.append((nb_keys[v][j], available_weight if nb_val is None else nb_val[v][j], 1))
+        lh = H(leaf_rows)
+        own = [lh[v * (depth + 1)] for v in range(n_voters)]
+        sib = [[lh[v * (depth + 1) + 1 + j] for j in range(depth)] for v in range(n_voters)]
+        node = own
+        for j in range(depth - 1, -1, -1):        # node at level j = H(left, right), the voter's side chosen by bit j
+            rows = [((sib[v][j], node[v]) if (addrs[v] >> j) & 1 else (node[v], sib[v][j])) for v in range(n_voters)]
+            node = H(rows)
+        roots[name], sibs[name] = node, sib
+    pad = lambda s: [str(x) for x in s] + ["0"] * (n_levels + 1 - len(s))
+    for v in range(n_voters):
+        out.append({
+            "electionId": [str(election[0]), str(election[1])],
+            "nullifier": str(nulls[v]),
+            "availableWeight": str(available_weight),
+            "voteHash": [str(vote_hash[0]), str(vote_hash[1])],
+            "sikRoot": str(roots["sik"][v]),
+            "censusRoot": str(roots["census"][v]),
+            "address": str(addrs[v]),
+            "password": str(password),
+            "signature": str(sigs[v]),
+            "voteWeight": str(vote_weight),
+            "censusSiblings": pad(sibs["census"][v]),
+            "sikSiblings": pad(sibs["sik"][v]),
+        })
+    return out

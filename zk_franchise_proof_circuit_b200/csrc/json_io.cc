@@ -76,7 +76,7 @@ static bool dec_to_mod(const char *s, size_t len, uint32_t out[8], const uint32_
 std::string u256_to_dec(const uint32_t val[8]) {
   uint32_t t[8];
   memcpy(t, val, 32);
-  char buf[80];
+  char buf[96];   // 2^256 - 1 has 78 digits; 9 passes of 9 digits each write up to 81 before the zeros are trimmed
   int n = 0;
   for (;;) {
     bool zero = true;

@@ -300,6 +300,140 @@ __global__ void __launch_bounds__(THREADS, MINB) k_accumulate(TablePtrs<F> tabs,
   if (mine) stg_pod(buckets + ((size_t)(b * ntab + t) * nbuckets + bucket), acc);
 }
 
+// G2 bucket accumulation on lane PAIRS: lane 0 of a pair holds (X, ZZ) of the bucket's XYZZ<Fq2> accumulator and the x
+// coordinate of the incoming point, lane 1 holds (Y, ZZZ) and the y coordinate.  The ten Fq2 products of madd-2008-s
+// split 5 / 5 with both lanes running the SAME instruction stream on different operands:
+//   step 1   U2 = x ZZ, P = U2 - X        |  S2 = y ZZZ, R = S2 - Y
+//   step 2   PP = P^2                     |  RR = R^2
+//   step 3   PPP = P PP                   |  Q = X PP                (X, PP from the partner)
+//   step 4   ZZ' = ZZ PP                  |  ZZZ' = ZZZ PPP          (PPP from the partner)
+//   step 5   Y PPP                        |  X' = RR - PPP - 2Q,  R (Q - X')
+//   finish   X' from the partner          |  Y' = R (Q - X') - Y PPP
+// Four 16-word exchanges per addition, no extra products (28 Fq products per addition in total, as on one lane), and
+// each lane keeps 2 instead of 4 Fq2 accumulators: the one-lane kernel needed 128 registers + 576 B of stack, i.e. its
+// accumulator lived in local memory (ncu: 11 GB of DRAM writes per launch against 0.13 GB of bucket stores).
+__device__ __forceinline__ Fq2 pair_xchg(const Fq2 &v, uint32_t mask = 0xffffffffu) {
+  Fq2 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.a.v[i] = __shfl_xor_sync(mask, v.a.v[i], 1);
+    r.b.v[i] = __shfl_xor_sync(mask, v.b.v[i], 1);
+  }
+  return r;
+}
+
+template <int THREADS, int MINB, bool INL, bool SMB>
+__global__ void __launch_bounds__(THREADS, MINB) k_accumulate_g2pair(TablePtrs<Fq2> tabs, int ntab, uint32_t n, int windows,
+                                                                   uint32_t nbuckets, const uint32_t *__restrict__ offsets,
+                                                                   const uint32_t *__restrict__ entries,
+                                                                   const uint32_t *__restrict__ order,
+                                                                   const uint32_t *__restrict__ n_long, XYZZ<Fq2> *buckets,
+                                                                   size_t tab_batch_stride, uint32_t tab_mod) {
+  const uint32_t t = blockIdx.y, b = blockIdx.z;
+  const uint32_t tid = blockIdx.x * THREADS + threadIdx.x, pos = tid >> 1;
+  const bool h = tid & 1u;                      // 0: (X, ZZ, x)   1: (Y, ZZZ, y)
+  if ((pos | 15u) < n_long[b]) return;          // the 16 buckets of this warp all belong to k_accumulate_long
+  const bool mine = pos >= n_long[b];
+  const uint32_t bucket = order[(size_t)b * nbuckets + pos];
+  const Affine<Fq2> *tab = (t == 0 ? tabs.tab[0] : (t == 1 ? tabs.tab[1] : (t == 2 ? tabs.tab[2] : tabs.tab[3]))) +
+                           (size_t)(b % tab_mod) * tab_batch_stride;
+  const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
+  const uint32_t *ent = entries + (size_t)b * n * windows;
+  const uint32_t beg = off[bucket], len = mine ? off[bucket + 1] - beg : 0u;
+  const uint32_t maxlen = __reduce_max_sync(0xffffffffu, len);
+  Fq2 A = Fq2::zero(), B = Fq2::zero();         // (X | Y), (ZZ | ZZZ)
+  // SMB: (ZZ | ZZZ) lives in shared memory between its two uses of an iteration (word-interleaved, conflict-free),
+  // which takes 16 registers off the live set
+  __shared__ uint32_t smB[SMB ? 16 * THREADS : 1];
+  auto putB = [&](const Fq2 &v) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) { smB[w * THREADS + threadIdx.x] = v.a.v[w]; smB[(8 + w) * THREADS + threadIdx.x] = v.b.v[w]; }
+  };
+  auto getB = [&]() {
+    Fq2 v;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { v.a.v[w] = smB[w * THREADS + threadIdx.x]; v.b.v[w] = smB[(8 + w) * THREADS + threadIdx.x]; }
+    return v;
+  };
+  if (SMB) putB(B);
+  bool acc_inf = true;
+  for (uint32_t i = 0; i < maxlen; i++) {
+    const bool active = i < len;
+    const uint32_t x = active ? ent[beg + i] : 0u;
+    Fq2 pc = ldg_pod(reinterpret_cast<const Fq2 *>(tab + (x & 0x7fffffffu)) + (h ? 1 : 0));
+    if (SMB) B = getB();
+    const bool myzero = pc.is_zero();
+    const bool p_inf = myzero && __shfl_xor_sync(0xffffffffu, (int)myzero, 1);
+    const bool use = active && !p_inf;
+    pc = Fq2::select(h && (x >> 31) != 0, pc.neg(), pc);
+    // step 1
+    const Fq2 D = mulx<INL>(pc, B) - A;         // P | R
+    const bool dz = D.is_zero();
+    const bool Pz = __shfl_sync(0xffffffffu, (int)dz, (threadIdx.x & 31u) & ~1u);
+    const bool special = use && !acc_inf && Pz;
+    const bool normal = use && !acc_inf && !special, first = use && acc_inf;
+    // an empty accumulator takes the point itself; what the steps below compute from it is discarded (normal = false)
+    A = Fq2::select(first, pc, A);
+    // step 2
+    const Fq2 DD = sqrx<INL>(D);                // PP | RR
+    Fq2 M3;
+    {
+      const Fq2 oDD = pair_xchg(DD), oA = pair_xchg(A);     // lane 1 now has PP and X
+      // step 3
+      M3 = mulx<INL>(Fq2::select(h, oA, D), Fq2::select(h, oDD, DD));           // PPP | Q
+    }
+    Fq2 X3;
+    {
+      const Fq2 oM3 = pair_xchg(M3);            // Q | PPP
+      // step 4
+      if (SMB) B = getB();
+      const Fq2 B3 = mulx<INL>(B, Fq2::select(h, oM3, DD));                      // ZZ PP | ZZZ PPP
+      B = Fq2::select(normal, B3, Fq2::select(first, Fq2::one(), B));
+      if (SMB) putB(B);
+      X3 = DD - oM3 - M3.dbl();                 // lane 1: RR - PPP - 2Q
+    }
+    // step 5
+    Fq2 M5;
+    {
+      const Fq2 oA = pair_xchg(A);              // lane 0 now has Y (exchanged a second time: 16 registers fewer live)
+      M5 = mulx<INL>(Fq2::select(h, D, oA), Fq2::select(h, M3 - X3, M3));       // Y PPP | R (Q - X')
+    }
+    {
+      const Fq2 o5 = pair_xchg(Fq2::select(h, X3, M5));     // lane 0 receives X', lane 1 receives Y PPP
+      A = Fq2::select(normal, Fq2::select(h, M5 - o5, o5), A);                  // X' | Y'
+    }
+    acc_inf = acc_inf && !first;
+    if (__any_sync(0xffffffffu, special)) {     // P == +-acc: rare, pair-uniform
+      if (special) {
+        const uint32_t pm = 3u << ((threadIdx.x & 31u) & ~1u);
+        const bool Rz = __shfl_sync(pm, (int)dz, (threadIdx.x & 31u) | 1u);
+        Fq2 pcr = ldg_pod(reinterpret_cast<const Fq2 *>(tab + (x & 0x7fffffffu)) + (h ? 1 : 0));   // the point again
+        pcr = Fq2::select(h && (x >> 31) != 0, pcr.neg(), pcr);
+        const Fq2 po = pair_xchg(pcr, pm);
+        if (Rz) {
+          Affine<Fq2> pt;
+          pt.x = h ? po : pcr;
+          pt.y = h ? pcr : po;
+          XYZZ<Fq2> d = XYZZ<Fq2>::dbl_affine(pt);
+          A = h ? d.Y : d.X;
+          B = h ? d.ZZZ : d.ZZ;
+        } else {
+          A = Fq2::zero(); B = Fq2::zero(); acc_inf = true;
+        }
+        if (SMB) putB(B);
+      }
+      __syncwarp();
+    }
+  }
+  if (SMB) B = getB();
+  if (acc_inf) { A = Fq2::zero(); B = Fq2::zero(); }
+  if (mine) {
+    Fq2 *dst = reinterpret_cast<Fq2 *>(buckets + ((size_t)(b * ntab + t) * nbuckets + bucket));
+    stg_pod(dst + (h ? 1 : 0), A);
+    stg_pod(dst + (h ? 3 : 2), B);
+  }
+}
+
 // One warp per long bucket (the n_long[b] largest): lanes take entries l, l + 32, ... with the same branch-free
 // mixed add, then the 32 partial sums are folded with shuffles.  Long lists come from many scalars sharing a digit
 // (e.g. hundreds of 0/1-valued wires that flip with respect to the template all have the difference +-1).
@@ -502,12 +636,19 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
     }
   } else {
     static const int variant2 = getenv("ZKB_ACC_VARIANT_G2") ? atoi(getenv("ZKB_ACC_VARIANT_G2")) : 0;
+    dim3 gpair(nb * 2 / 128, ntab, nbatch);
+#define ZKB_ACC2(MINB, INL, SMB) k_accumulate_g2pair<128, MINB, INL, SMB><<<gpair, 128, 0, st>>>(tp, ntab, sort.n, sort.cfg.windows, nb, sort.offsets, sort.entries, sort.order, sort.n_long, dst, tab_batch_stride, tab_mod)
     switch (variant2) {
-      case 1: ZKB_ACC(4, false); break;
-      case 2: ZKB_ACC(5, false); break;
-      case 3: ZKB_ACC(6, false); break;
-      default: ZKB_ACC(8, false); break;
+      case 1: ZKB_ACC(4, false); break;      // one lane per bucket (round 1): 128 registers + 576 B of stack
+      case 2: ZKB_ACC(8, false); break;
+      case 3: ZKB_ACC2(4, false, true); break;
+      case 4: ZKB_ACC2(3, true, true); break;
+      case 5: ZKB_ACC2(4, true, true); break;
+      case 6: ZKB_ACC2(2, false, false); break;
+      case 7: ZKB_ACC2(3, false, false); break;
+      default: ZKB_ACC2(3, false, true); break;    // lane pairs
     }
+#undef ZKB_ACC2
   }
 #undef ZKB_ACC
   dim3 glong(sort.max_long, ntab, nbatch);

@@ -20,6 +20,7 @@
 #include <map>
 #include <mutex>
 #include <sys/random.h>
+#include <sys/stat.h>
 #include <cerrno>
 #include <memory>
 #include <atomic>
@@ -329,6 +330,9 @@ struct Circuit {
   // blinding override (tests): when set every proof uses these r, s
   bool fixed_rs = false;
   uint32_t fr[8], fs[8];
+  // dense: the proof-independent-wire shortcut is off - every SMT level is hashed and the four witness
+  // MSMs run over the full witness, as snarkjs / rapidsnark do (measurement aid: zkb_load_circuit_ex flag 1)
+  bool dense = false;
   // batch workspace
   uint32_t cap = 0;                // proofs resident at once (witness group)
   uint32_t chunk = 0;              // proofs per NTT/MSM chunk
@@ -392,17 +396,32 @@ static uint32_t default_chunk(const Circuit *c) {
   return env_u32("ZKB_CHUNK", fit);
 }
 
-static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
-  if (c->cap >= cap && c->chunk >= chunk) return ZKB_OK;
-  // (re)allocate everything; sizes are small next to the 180 GB of HBM
+static void free_workspace(Circuit *c) {
   cudaFree(c->inputs); cudaFree(c->wtns); cudaFree(c->rs); cudaFree(c->status); cudaFree(c->out);
+  c->inputs = c->wtns = c->rs = nullptr; c->status = nullptr; c->out = nullptr;
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_inputs) cudaFreeHost(c->h_inputs);
   if (c->h_rs) cudaFreeHost(c->h_rs);
   if (c->h_status) cudaFreeHost(c->h_status);
+  c->h_out = nullptr; c->h_inputs = nullptr; c->h_rs = nullptr; c->h_status = nullptr;
   for (int i = 0; i < MAX_LANES; i++) c->lanes[i].free_all();
+  c->cap = 0;
+  c->chunk = 0;
+}
+
+static int alloc_workspace(Circuit *c, uint32_t cap, uint32_t chunk);
+static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
+  if (c->cap >= cap && c->chunk >= chunk) return ZKB_OK;
+  free_workspace(c);
+  int rc = alloc_workspace(c, cap, chunk);
+  if (rc) { free_workspace(c); return rc; }
   c->cap = cap;
   c->chunk = chunk;
+  return ZKB_OK;
+}
+
+static int alloc_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
+  // (re)allocate everything; sizes are small next to the 180 GB of HBM
   // more than one lane only pays when there is more than one chunk
   int want = (int)env_u32("ZKB_LANES", 4);   // measured on B200, 1,024-proof batch: 2 lanes 1312, 4 lanes 1356 proofs/s
   if (want > MAX_LANES) want = MAX_LANES;
@@ -453,7 +472,7 @@ static int run_witness(Circuit *c, Lane &ln, uint32_t first, uint32_t n, cudaStr
   CKR(cudaMemsetAsync(ln.stage, 0, (size_t)n * c->L.n_signals * 32, st), "memset staging");
   k_witness<<<dim3((n * COOP_LANES + 31) / 32, WITNESS_TASKS), 32, 0, st>>>(c->L, c->consts, c->hc,
                                                                c->inputs + (size_t)first * c->L.n_inputs, ln.stage,
-                                                               c->status + first, n, 1);
+                                                               c->status + first, n, c->dense ? 0 : 1);
   k_witness_gather<<<dim3((c->n_vars + 255) / 256, n), 256, 0, st>>>(ln.stage, c->L.n_signals, c->wmap, c->tmpl,
                                                                      c->wtns + (size_t)first * c->n_vars, c->n_vars);
   g_launches += 2;
@@ -590,10 +609,15 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
 // serial (one lane); without stage_ms chunks alternate over the lanes and overlap.
 static int prove_resident(Circuit *c, uint32_t n, bool with_witness, float *stage_ms) {
   cudaStream_t st = c->ctx->stream;
-  std::vector<cudaEvent_t> evs;
+  struct EvBag {                         // destroyed on every exit path
+    std::vector<cudaEvent_t> v;
+    ~EvBag() { for (auto e : v) cudaEventDestroy(e); }
+  } bag;
+  std::vector<cudaEvent_t> &evs = bag.v;
   auto newev = [&]() { cudaEvent_t e; cudaEventCreate(&e); evs.push_back(e); return e; };
   cudaEvent_t start;
   CKR(cudaEventCreateWithFlags(&start, cudaEventDisableTiming), "event");
+  evs.push_back(start);
   cudaEventRecord(start, st);            // inputs / blinding were queued on the context stream
   // an instrumented pass runs on one lane: event-bracketed stage times are then not shared with another stream
   const int n_lanes = stage_ms ? 1 : c->n_lanes;
@@ -609,7 +633,7 @@ static int prove_resident(Circuit *c, uint32_t n, bool with_witness, float *stag
       cudaEventRecord(ev[0], ln.st);
     }
     int rc = run_prove_chunk(c, ln, first, m, with_witness, stage_ms ? ev : nullptr);
-    if (rc) return rc;
+    if (rc) { cudaDeviceSynchronize(); return rc; }    // side streams of a forked chunk are joined before the error returns
     c->last_chunk_m = m;
     c->last_lane = (int)(k % n_lanes);
   }
@@ -618,13 +642,11 @@ static int prove_resident(Circuit *c, uint32_t n, bool with_witness, float *stag
     cudaStreamWaitEvent(st, c->lanes[i].done, 0);
   }
   CKR(cudaStreamSynchronize(st), "prove");
-  cudaEventDestroy(start);
   if (stage_ms) {
     for (int i = 0; i < 8; i++) stage_ms[i] = 0;
     for (size_t q = 0; q + 8 < chunk_ev.size(); q += 9)
       for (int i = 0; i < 8; i++) { float t; cudaEventElapsedTime(&t, chunk_ev[q + i], chunk_ev[q + i + 1]); stage_ms[i] += t; }
   }
-  for (auto e : evs) cudaEventDestroy(e);
   return ZKB_OK;
 }
 
@@ -662,7 +684,7 @@ static cudaError_t upload(T **dptr, const void *src, size_t bytes) {
 }
 
 static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const uint8_t *wasm, size_t wasm_len,
-                        Circuit **out, int shard_rank = 0, int shard_n = 1) {
+                        Circuit **out, int shard_rank = 0, int shard_n = 1, uint32_t flags = 0) {
   CKR(cudaSetDevice(ctx->device), "set device");
   std::string err;
   ZkeyView z;
@@ -670,6 +692,7 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
   std::unique_ptr<Circuit> c(new Circuit());
   c->ctx = ctx;
   c->n_vars = z.n_vars; c->n_public = z.n_public; c->domain = z.domain; c->power = z.power;
+  c->dense = (flags & 1u) != 0 || env_u32("ZKB_DENSE", 0) != 0;
   cudaStream_t st = ctx->stream;
   memset(&c->L, 0, sizeof c->L);
 
@@ -772,15 +795,19 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
   {
     Affine<Fq> *d1 = nullptr;
     Affine<Fq2> *d2 = nullptr;
-    c->cfgW = msm_cfg((int)env_u32("ZKB_C_WITNESS", c->tmpl ? 13 : 16));
+    const bool use_tmpl = c->tmpl && !c->dense;
+    c->cfgW = msm_cfg((int)env_u32("ZKB_C_WITNESS", use_tmpl ? 13 : 16));
     c->cfgH = msm_cfg((int)env_u32("ZKB_C_H", 16));
     // point ranges (see Circuit::subW): 2^17 points each once a key has more than 2^18; the last range is padded
     // with points at infinity
-    const uint32_t SUB = 1u << 17;
-    c->nsubW = (z.n_vars > 2 * SUB && !c->tmpl) ? SUB : z.n_vars;
+    // (a key sharded over more ranks than it has 2^17-point ranges is cut finer, so that every rank owns a range)
+    uint32_t SUB = 1u << 17;
+    if (shard_n > 1)
+      while (SUB > 4096 && ((z.n_vars + SUB - 1) / SUB < (uint32_t)shard_n || z.domain / SUB < (uint32_t)shard_n)) SUB >>= 1;
+    c->nsubW = ((z.n_vars > 2 * SUB || shard_n > 1) && !use_tmpl) ? SUB : z.n_vars;
     c->subW = (z.n_vars + c->nsubW - 1) / c->nsubW;
     c->n_pad = c->subW * c->nsubW;
-    c->nsubH = z.domain > 2 * SUB ? SUB : z.domain;
+    c->nsubH = (z.domain > 2 * SUB || (shard_n > 1 && z.domain > SUB)) ? SUB : z.domain;
     c->subH = z.domain / c->nsubH;
     c->loW = c->loH = 0;
     c->cntW = c->subW;
@@ -789,7 +816,7 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
     c->shard_n = shard_n;
     if (shard_n > 1) {
       if (c->subW < (uint32_t)shard_n || c->subH < (uint32_t)shard_n) {
-        set_error("key too small to shard: every rank needs at least one 2^17-point range of each MSM");
+        set_error("key too small to shard: every rank needs at least one 4096-point range of each MSM");
         return ZKB_ERROR;
       }
       c->loW = (uint32_t)((uint64_t)c->subW * shard_rank / shard_n);
@@ -830,7 +857,7 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
     cudaFree(d2);
   }
   // constant part of the four witness MSMs: sum_i tmpl_i * base_i (once per key)
-  if (c->tmpl) {
+  if (c->tmpl && !c->dense) {
     MsmSort s1;
     MsmWork<Fq> w1;
     MsmWork<Fq2> w2;
@@ -909,6 +936,7 @@ static int prove_group(Circuit *c, uint32_t n, bool with_witness, float *stage_m
     CKR(cudaMemcpyAsync(c->inputs, c->h_inputs, (size_t)n * c->L.n_inputs * 32, cudaMemcpyHostToDevice, st), "h2d inputs");
   if (!fill_blinding(c, n)) return ZKB_ERROR;
   CKR(cudaMemcpyAsync(c->rs, c->h_rs, (size_t)n * 64, cudaMemcpyHostToDevice, st), "h2d rs");
+  if (!with_witness) CKR(cudaMemsetAsync(c->status, 0, (size_t)n * 4, st), "memset status");
   int rc = prove_resident(c, n, with_witness, stage_ms);
   if (rc) return rc;
   CKR(cudaMemcpyAsync(c->h_out, c->out, (size_t)n * c->out_stride(), cudaMemcpyDeviceToHost, st), "d2h");
@@ -950,14 +978,18 @@ void zkb_ctx_destroy(zkb_ctx *x) {
 
 void *zkb_ctx_stream(zkb_ctx *x) { return (void *)x->c.stream; }
 
-int zkb_load_circuit(zkb_ctx *ctx, const void *zkey, size_t zkey_len, const void *wasm, size_t wasm_len,
-                     zkb_circuit **out) {
+int zkb_load_circuit_ex(zkb_ctx *ctx, const void *zkey, size_t zkey_len, const void *wasm, size_t wasm_len,
+                        uint32_t flags, zkb_circuit **out) {
   if (!ctx || !zkey || !out) { set_error("null argument"); return ZKB_ERROR; }
   Circuit *c = nullptr;
-  int rc = load_circuit(&ctx->c, (const uint8_t *)zkey, zkey_len, (const uint8_t *)wasm, wasm_len, &c);
+  int rc = load_circuit(&ctx->c, (const uint8_t *)zkey, zkey_len, (const uint8_t *)wasm, wasm_len, &c, 0, 1, flags);
   if (rc) return rc;
   *out = new zkb_circuit{c};
   return ZKB_OK;
+}
+int zkb_load_circuit(zkb_ctx *ctx, const void *zkey, size_t zkey_len, const void *wasm, size_t wasm_len,
+                     zkb_circuit **out) {
+  return zkb_load_circuit_ex(ctx, zkey, zkey_len, wasm, wasm_len, 0, out);
 }
 
 // A proving key sharded over `nranks` GPUs (one context / process per GPU): rank `rank` keeps the fixed-base tables of
@@ -973,6 +1005,7 @@ int zkb_load_circuit_shard(zkb_ctx *ctx, const void *zkey, size_t zkey_len, int 
 }
 // rank 0: the 64-byte CUDA IPC handle of its exchange buffer
 int zkb_shard_export(zkb_circuit *h, void *handle64) {
+  if (!h || !handle64) { set_error("null argument"); return ZKB_ERROR; }
   Circuit *c = h->c;
   CKR(cudaSetDevice(c->ctx->device), "set device");
   if (!c->xbuf) { set_error("not a sharded key"); return ZKB_ERROR; }
@@ -983,6 +1016,7 @@ int zkb_shard_export(zkb_circuit *h, void *handle64) {
 }
 // ranks > 0: map rank 0's exchange buffer (their partial sums are written there over NVLink)
 int zkb_shard_attach(zkb_circuit *h, const void *handle64) {
+  if (!h || !handle64) { set_error("null argument"); return ZKB_ERROR; }
   Circuit *c = h->c;
   CKR(cudaSetDevice(c->ctx->device), "set device");
   if (!c->xbuf) { set_error("not a sharded key"); return ZKB_ERROR; }
@@ -996,6 +1030,7 @@ int zkb_shard_attach(zkb_circuit *h, const void *handle64) {
 }
 // same process (several contexts): publish straight into the root circuit's buffer
 int zkb_shard_attach_local(zkb_circuit *h, zkb_circuit *root) {
+  if (!h || !root) { set_error("null argument"); return ZKB_ERROR; }
   Circuit *c = h->c, *r = root->c;
   CKR(cudaSetDevice(c->ctx->device), "set device");
   if (!c->xbuf || !r->xbuf) { set_error("not a sharded key"); return ZKB_ERROR; }
@@ -1019,6 +1054,7 @@ void zkb_circuit_destroy(zkb_circuit *h) {
 
 // info: n_vars, n_public, domain, n_inputs, n_levels_plus1, n_signals, chunk, cap
 int zkb_circuit_info(zkb_circuit *h, uint32_t *info) {
+  if (!h || !info) { set_error("null argument"); return ZKB_ERROR; }
   Circuit *c = h->c;
   info[0] = c->n_vars; info[1] = c->n_public; info[2] = c->domain; info[3] = c->L.n_inputs;
   info[4] = c->L.n; info[5] = c->L.n_signals; info[6] = c->chunk; info[7] = c->cap;
@@ -1027,6 +1063,7 @@ int zkb_circuit_info(zkb_circuit *h, uint32_t *info) {
 
 // r32 / s32: canonical little-endian scalars < r; both NULL restores random blinding
 int zkb_set_blinding(zkb_circuit *h, const uint8_t *r32, const uint8_t *s32) {
+  if (!h) { set_error("null handle"); return ZKB_ERROR; }
   Circuit *c = h->c;
   std::lock_guard<std::mutex> g(c->mu);
   if (!r32 || !s32) { c->fixed_rs = false; return ZKB_OK; }
@@ -1040,6 +1077,7 @@ int zkb_set_blinding(zkb_circuit *h, const uint8_t *r32, const uint8_t *s32) {
 // inputs: n x n_inputs canonical 32-byte values in main-signal order (electionId[2], nullifier, voteHash[2],
 // sikRoot, censusRoot, voteWeight, availableWeight, address, password, signature, censusSiblings, sikSiblings)
 int zkb_batch_set_inputs(zkb_circuit *h, int n, const void *inputs) {
+  if (!h || !inputs || n <= 0) { set_error("batch_set_inputs: null handle / inputs or n <= 0"); return ZKB_ERROR; }
   Circuit *c = h->c;
   if (!c->consts) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
   std::lock_guard<std::mutex> g(c->mu);
@@ -1056,6 +1094,7 @@ int zkb_batch_set_inputs(zkb_circuit *h, int n, const void *inputs) {
 
 // runs witness + Groth16 on the resident inputs, results stay on the device.  stage_ms: 5 floats or NULL.
 int zkb_batch_prove_resident(zkb_circuit *h, int n, float *stage_ms) {
+  if (!h || n <= 0) { set_error("batch_prove_resident: null handle or n <= 0"); return ZKB_ERROR; }
   Circuit *c = h->c;
   std::lock_guard<std::mutex> g(c->mu);
   CKR(cudaSetDevice(c->ctx->device), "set device");
@@ -1065,8 +1104,10 @@ int zkb_batch_prove_resident(zkb_circuit *h, int n, float *stage_ms) {
 
 // proofs256: n x 256 B; publics: n x n_public x 32 B; status: n ints (0 ok, 4 assert failed)
 int zkb_batch_get_results(zkb_circuit *h, int n, void *proofs256, void *publics, int *status) {
+  if (!h) { set_error("null handle"); return ZKB_ERROR; }
   Circuit *c = h->c;
   std::lock_guard<std::mutex> g(c->mu);
+  if (n <= 0 || (uint32_t)n > c->cap) { set_error("batch_get_results: n outside the resident batch"); return ZKB_ERROR; }
   CKR(cudaSetDevice(c->ctx->device), "set device");
   cudaStream_t st = c->ctx->stream;
   CKR(cudaMemcpyAsync(c->h_out, c->out, (size_t)n * c->out_stride(), cudaMemcpyDeviceToHost, st), "d2h");
@@ -1083,8 +1124,10 @@ int zkb_batch_get_results(zkb_circuit *h, int n, void *proofs256, void *publics,
 
 // device copy of the n resident witnesses (n x n_vars x 32 B, canonical) - parity tests
 int zkb_batch_get_witness(zkb_circuit *h, int first, int n, void *wtns) {
+  if (!h || !wtns) { set_error("null argument"); return ZKB_ERROR; }
   Circuit *c = h->c;
   std::lock_guard<std::mutex> g(c->mu);
+  if (first < 0 || n <= 0 || (uint64_t)first + (uint64_t)n > c->cap) { set_error("batch_get_witness: range outside the resident batch"); return ZKB_ERROR; }
   CKR(cudaSetDevice(c->ctx->device), "set device");
   CKR(cudaMemcpy(wtns, c->wtns + (size_t)first * c->n_vars, (size_t)n * c->n_vars * 32, cudaMemcpyDeviceToHost), "d2h witness");
   return ZKB_OK;
@@ -1322,11 +1365,15 @@ int zkb_prove_wtns_stages(zkb_circuit *h, const void *wtns, size_t wtns_size, ch
     return (r1 || r2) ? ZKB_SHORT_BUFFER : ZKB_OK;
   }
   if (wtns_size < 12 || memcmp(b, "wtns", 4) != 0) { set_error("wtns: bad magic"); return ZKB_ERROR; }
+  static const uint32_t RMOD[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
   uint32_t nsec;
   memcpy(&nsec, b + 8, 4);
   size_t p = 12;
   const uint8_t *data = nullptr;
+  uint64_t data_sz = 0;
   uint32_t nw = 0;
+  bool have_hdr = false;
   for (uint32_t i = 0; i < nsec && p + 12 <= wtns_size; i++) {
     uint32_t id;
     uint64_t sz;
@@ -1334,12 +1381,31 @@ int zkb_prove_wtns_stages(zkb_circuit *h, const void *wtns, size_t wtns_size, ch
     memcpy(&sz, b + p + 4, 8);
     p += 12;
     if (sz > wtns_size - p) { set_error("wtns: truncated"); return ZKB_ERROR; }
-    if (id == 1 && sz >= 40) memcpy(&nw, b + p + 36, 4);
-    if (id == 2) data = b + p;
+    if (id == 1) {
+      uint32_t n8 = 0;
+      if (sz < 40) { set_error("wtns: header section too short"); return ZKB_ERROR; }
+      memcpy(&n8, b + p, 4);
+      if (n8 != 32 || memcmp(b + p + 4, RMOD, 32) != 0) { set_error("wtns: not a BN254 scalar-field witness (n8 / prime)"); return ZKB_ERROR; }
+      memcpy(&nw, b + p + 36, 4);
+      have_hdr = true;
+    }
+    if (id == 2) { data = b + p; data_sz = sz; }
     p += sz;
   }
+  if (!have_hdr) { set_error("wtns: no header section"); return ZKB_ERROR; }
   if (!data) { set_error("wtns: no data section"); return ZKB_ERROR; }
   if (nw != c->n_vars) { set_error("wtns: witness length does not match the zkey"); return ZKB_INVALID_WITNESS_LENGTH; }
+  if (data_sz < (uint64_t)nw * 32) { set_error("wtns: data section shorter than nVars x 32 bytes"); return ZKB_INVALID_WITNESS_LENGTH; }
+  for (uint32_t i = 0; i < nw; i++) {          // canonical values only: they feed Montgomery products and MSM digits
+    uint32_t top;
+    memcpy(&top, data + (size_t)i * 32 + 28, 4);
+    if (top < RMOD[7]) continue;
+    uint32_t v[8];
+    memcpy(v, data + (size_t)i * 32, 32);
+    bool lt = false;
+    for (int k = 7; k >= 0; k--) { if (v[k] != RMOD[k]) { lt = v[k] < RMOD[k]; break; } }
+    if (!lt) { set_error("wtns: value not in [0, r)"); return ZKB_ERROR; }
+  }
   std::lock_guard<std::mutex> g(c->mu);
   CKR(cudaSetDevice(c->ctx->device), "set device");
   int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : default_chunk(c));
@@ -1364,39 +1430,154 @@ int zkb_prove_wtns_stages(zkb_circuit *h, const void *wtns, size_t wtns_size, ch
   return (r1 || r2) ? ZKB_SHORT_BUFFER : ZKB_OK;
 }
 
+// ---- rapidsnark prover.h ------------------------------------------------------------------------------------------
+// Key cache of the rapidsnark-shaped entry points: one resident circuit per process, identified by the key's size
+// and a 64-bit hash over ALL of its bytes.  The full hash (8 bytes per step, ~10 ms for the 55 MB census key) runs
+// when a (pointer, size) pair is first seen or when its cheap fingerprint changed; the fingerprint checked on every
+// call covers sections 1-3 completely (protocol, Groth16 header with alpha/beta/gamma/delta, IC: two keys of one
+// circuit from different setups always differ there) plus every 4,099th byte of the rest.
+static uint64_t mix64(uint64_t h, uint64_t v) {
+  h ^= v;
+  h *= 0x9E3779B97F4A7C15ull;
+  return h ^ (h >> 29);
+}
+static uint64_t hash_all(const uint8_t *b, size_t n) {
+  uint64_t h = 0x243F6A8885A308D3ull ^ n;
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) { uint64_t v; memcpy(&v, b + i, 8); h = mix64(h, v); }
+  uint64_t tail = 0;
+  if (i < n) memcpy(&tail, b + i, n - i);
+  return mix64(h, tail);
+}
+static uint64_t key_fingerprint(const uint8_t *b, size_t n) {
+  // sections 1..3 sit at the front of a snarkjs zkey: 12-byte file header, then {id, len, payload}
+  size_t p = 12, head = n < 12 ? n : 12;
+  for (int s = 0; s < 3 && p + 12 <= n; s++) {
+    uint64_t sz;
+    memcpy(&sz, b + p + 4, 8);
+    if (sz > n - p - 12) break;
+    p += 12 + (size_t)sz;
+    head = p;
+  }
+  if (head > ((size_t)1 << 20)) head = (size_t)1 << 20;
+  uint64_t h = hash_all(b, head);
+  for (size_t i = head; i < n; i += 4099) h = mix64(h, b[i]);
+  return h;
+}
+struct KeyCache {
+  std::mutex mu;
+  zkb_ctx *ctx = nullptr;
+  zkb_circuit *circuit = nullptr;
+  const void *ptr = nullptr;
+  size_t size = 0;
+  uint64_t fingerprint = 0, full = 0;
+};
+static KeyCache g_keys;
+
+// the circuit for this key, loading it when it is not the resident one (g_keys.mu held)
+static int cached_circuit(const void *zkey, size_t size, zkb_circuit **out) {
+  KeyCache &k = g_keys;
+  if (!zkey || size < 12) { set_error("zkey: empty buffer"); return ZKB_ERROR; }
+  if (!k.ctx && zkb_ctx_create((int)env_u32("ZKB_DEVICE", 0) % (zkb_device_count() ? zkb_device_count() : 1), &k.ctx)) return ZKB_ERROR;
+  const uint64_t fp = key_fingerprint((const uint8_t *)zkey, size);
+  if (k.circuit && k.size == size && k.fingerprint == fp && k.ptr == zkey) { *out = k.circuit; return ZKB_OK; }
+  const uint64_t full = hash_all((const uint8_t *)zkey, size);
+  if (!(k.circuit && k.size == size && k.full == full)) {
+    if (k.circuit) { zkb_circuit_destroy(k.circuit); k.circuit = nullptr; }
+    int rc = zkb_load_circuit(k.ctx, zkey, size, nullptr, 0, &k.circuit);
+    if (rc) return rc;
+  }
+  k.ptr = zkey; k.size = size; k.fingerprint = fp; k.full = full;
+  *out = k.circuit;
+  return ZKB_OK;
+}
+
 // rapidsnark's prover.h entry point, same symbol and signature (go-rapidsnark links against it):
-// returns 0 PROVER_OK, 1 PROVER_ERROR, 2 PROVER_ERROR_SHORT_BUFFER.  The parsed key + device tables are cached
-// per (pointer, size, checksum) so repeated calls with the same zkey do not re-upload it.
+// returns 0 PROVER_OK, 1 PROVER_ERROR, 2 PROVER_ERROR_SHORT_BUFFER.
 int groth16_prover(const void *zkey_buffer, unsigned long zkey_size, const void *wtns_buffer, unsigned long wtns_size,
                    char *proof_buffer, unsigned long *proof_size, char *public_buffer, unsigned long *public_size,
                    char *error_msg, unsigned long error_msg_maxsize) {
-  static std::mutex mu;
-  static zkb_ctx *ctx = nullptr;
-  static zkb_circuit *cached = nullptr;
-  static uint64_t cached_sum = 0;
-  static unsigned long cached_size = 0;
   auto fail = [&](int rc) {
     if (error_msg && error_msg_maxsize) snprintf(error_msg, error_msg_maxsize, "%s", zkb_last_error());
     return rc == ZKB_SHORT_BUFFER ? 2 : 1;
   };
-  std::lock_guard<std::mutex> g(mu);
-  if (!ctx && zkb_ctx_create((int)env_u32("ZKB_DEVICE", 0) % (zkb_device_count() ? zkb_device_count() : 1), &ctx)) return fail(1);
-  uint64_t sum = 1469598103934665603ull;
-  const uint8_t *zb = (const uint8_t *)zkey_buffer;
-  for (unsigned long i = 0; i < zkey_size; i += 4099) { sum ^= zb[i]; sum *= 1099511628211ull; }
-  if (!cached || cached_sum != sum || cached_size != zkey_size) {
-    if (cached) { zkb_circuit_destroy(cached); cached = nullptr; }
-    int rc = zkb_load_circuit(ctx, zkey_buffer, zkey_size, nullptr, 0, &cached);
-    if (rc) return fail(rc);
-    cached_sum = sum;
-    cached_size = zkey_size;
-  }
+  if (!proof_size || !public_size) { set_error("null size pointer"); return fail(1); }
+  std::lock_guard<std::mutex> g(g_keys.mu);
+  zkb_circuit *c = nullptr;
+  int rc = cached_circuit(zkey_buffer, zkey_size, &c);
+  if (rc) return fail(rc);
   size_t ps = *proof_size, qs = *public_size;
-  int rc = zkb_prove_wtns(cached, wtns_buffer, wtns_size, proof_buffer, &ps, public_buffer, &qs);
+  rc = zkb_prove_wtns(c, wtns_buffer, wtns_size, proof_buffer, &ps, public_buffer, &qs);
   *proof_size = ps;
   *public_size = qs;
   if (rc) return fail(rc);
   return 0;
+}
+
+// Later rapidsnark releases (prover.h of v0.0.2+, bound by go-rapidsnark/prover >= v0.0.11) added these; exported so
+// that newer wrappers link too.  `unsigned long` and their `unsigned long long` are the same 64-bit type on LP64.
+void groth16_proof_size(unsigned long *proof_size) {
+  if (proof_size) *proof_size = 810;      // 8 coordinates of <= 77 digits + JSON punctuation, as rapidsnark reports
+}
+int groth16_public_size_for_zkey_buf(const void *zkey_buffer, unsigned long zkey_size, unsigned long *public_size,
+                                     char *error_msg, unsigned long error_msg_maxsize) {
+  ZkeyView z;
+  std::string err;
+  if (!zkey_buffer || !public_size || !parse_zkey((const uint8_t *)zkey_buffer, zkey_size, z, err)) {
+    if (error_msg && error_msg_maxsize) snprintf(error_msg, error_msg_maxsize, "%s", err.empty() ? "null argument" : err.c_str());
+    return 1;
+  }
+  *public_size = 4 + (unsigned long)z.n_public * 82;     // ["<=77 digits",...] + NUL
+  return 0;
+}
+static bool read_file(const char *path, std::vector<uint8_t> &out, std::string &err) {
+  FILE *f = path ? fopen(path, "rb") : nullptr;
+  if (!f) { err = std::string("cannot open ") + (path ? path : "(null)"); return false; }
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out.resize(n > 0 ? (size_t)n : 0);
+  bool ok = n >= 0 && fread(out.data(), 1, out.size(), f) == out.size();
+  fclose(f);
+  if (!ok) err = std::string("cannot read ") + path;
+  return ok;
+}
+int groth16_public_size_for_zkey_file(const char *zkey_fname, unsigned long *public_size, char *error_msg,
+                                      unsigned long error_msg_maxsize) {
+  std::vector<uint8_t> buf;
+  std::string err;
+  if (!read_file(zkey_fname, buf, err)) {
+    if (error_msg && error_msg_maxsize) snprintf(error_msg, error_msg_maxsize, "%s", err.c_str());
+    return 1;
+  }
+  return groth16_public_size_for_zkey_buf(buf.data(), buf.size(), public_size, error_msg, error_msg_maxsize);
+}
+// The file is re-read only when its path, size or mtime changed since the last call.
+int groth16_prover_zkey_file(const char *zkey_file_path, const void *wtns_buffer, unsigned long wtns_size,
+                             char *proof_buffer, unsigned long *proof_size, char *public_buffer,
+                             unsigned long *public_size, char *error_msg, unsigned long error_msg_maxsize) {
+  static std::mutex fmu;
+  static std::string cached_path;
+  static std::vector<uint8_t> cached_bytes;
+  static long long cached_mtime = 0, cached_len = -1;
+  std::lock_guard<std::mutex> g(fmu);
+  struct stat sb;
+  if (!zkey_file_path || stat(zkey_file_path, &sb) != 0) {
+    if (error_msg && error_msg_maxsize) snprintf(error_msg, error_msg_maxsize, "cannot stat %s", zkey_file_path ? zkey_file_path : "(null)");
+    return 1;
+  }
+  const long long mt = (long long)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec;
+  if (cached_path != zkey_file_path || cached_mtime != mt || cached_len != (long long)sb.st_size) {
+    std::string err;
+    if (!read_file(zkey_file_path, cached_bytes, err)) {
+      if (error_msg && error_msg_maxsize) snprintf(error_msg, error_msg_maxsize, "%s", err.c_str());
+      cached_path.clear();
+      return 1;
+    }
+    cached_path = zkey_file_path; cached_mtime = mt; cached_len = (long long)sb.st_size;
+  }
+  return groth16_prover(cached_bytes.data(), cached_bytes.size(), wtns_buffer, wtns_size, proof_buffer, proof_size,
+                        public_buffer, public_size, error_msg, error_msg_maxsize);
 }
 
 }  // extern "C"

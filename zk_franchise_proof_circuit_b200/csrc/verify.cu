@@ -59,14 +59,21 @@ struct VKeyDev {
   uint32_t n_public = 0;
 };
 
+// Device objects are cached per GPU: a verify runs on the calling thread's current device (whatever the last prove on
+// this thread bound, or the default device) and never touches another GPU's allocations.
 static std::mutex g_mu;
-static PairingConsts *g_pc = nullptr;
-static std::map<std::string, VKeyDev> g_vkeys;     // keyed by the vkey JSON text
+static constexpr int MAX_DEV = 64;
+static constexpr size_t MAX_VKEYS = 16;             // per device; the oldest entry is evicted
+static PairingConsts *g_pc_dev[MAX_DEV] = {};
+struct VKeyEntry { std::string text; VKeyDev dv; };
+static std::vector<VKeyEntry> g_vkeys_dev[MAX_DEV]; // keyed by the vkey JSON text
 
-static int get_vkey(const char *json, size_t len, VKeyDev &out) {
+static int get_vkey(int dev, const char *json, size_t len, VKeyDev &out, PairingConsts *&g_pc) {
   std::string key(json, len);
-  auto it = g_vkeys.find(key);
-  if (it != g_vkeys.end()) { out = it->second; return ZKB_OK; }
+  auto &g_vkeys = g_vkeys_dev[dev];
+  g_pc = g_pc_dev[dev];
+  for (auto &e : g_vkeys)
+    if (e.text == key) { out = e.dv; return ZKB_OK; }
   std::map<std::string, std::vector<uint32_t>> m;
   std::string err;
   json_reset_reduced();
@@ -85,6 +92,7 @@ static int get_vkey(const char *json, size_t len, VKeyDev &out) {
   if (!g_pc) {
     CKR(cudaMalloc(&g_pc, sizeof(PairingConsts)), "alloc");
     k_pairing_consts<<<1, 1>>>(g_pc);
+    g_pc_dev[dev] = g_pc;
   }
   VerifyingKey h;
   memset(&h, 0, sizeof h);
@@ -103,8 +111,32 @@ static int get_vkey(const char *json, size_t len, VKeyDev &out) {
   CKR(cudaMemcpy(dv.ic, ic.data(), ic.size(), cudaMemcpyHostToDevice), "h2d");
   k_vkey_prepare<<<(n_public + 1 + 31) / 32, 32>>>(dv.vk, dv.ic, n_public + 1, g_pc);
   CKR(cudaDeviceSynchronize(), "vkey prepare");
-  g_vkeys[key] = dv;
+  if (g_vkeys.size() >= MAX_VKEYS) {
+    cudaFree(g_vkeys.front().dv.vk);
+    cudaFree(g_vkeys.front().dv.ic);
+    g_vkeys.erase(g_vkeys.begin());
+  }
+  g_vkeys.push_back({key, dv});
   out = dv;
+  return ZKB_OK;
+}
+
+// proofs: n x 64 words (8 canonical Fq), pubs: n x n_public x 8 words (canonical Fr) -> ok[i]
+static int verify_device(const VKeyDev &vk, const PairingConsts *g_pc, const uint32_t *proofs, const uint32_t *pubs, int n,
+                         int *ok) {
+  Fq *dp = nullptr;
+  Fr *dq = nullptr;
+  int *dok = nullptr;
+  const size_t pw = (size_t)n * 64, qw = (size_t)n * vk.n_public * 8;
+  CKR(cudaMalloc(&dp, pw * 4), "alloc");
+  CKR(cudaMalloc(&dq, qw * 4 + 32), "alloc");
+  CKR(cudaMalloc(&dok, (size_t)n * 4), "alloc");
+  CKR(cudaMemcpy(dp, proofs, pw * 4, cudaMemcpyHostToDevice), "h2d");
+  CKR(cudaMemcpy(dq, pubs, qw * 4, cudaMemcpyHostToDevice), "h2d");
+  k_verify<<<(n + 31) / 32, 32>>>(vk.vk, vk.ic, g_pc, dp, dq, dok, (uint32_t)n);
+  CKR(cudaGetLastError(), "verify launch");
+  CKR(cudaMemcpy(ok, dok, (size_t)n * 4, cudaMemcpyDeviceToHost), "d2h");
+  cudaFree(dp); cudaFree(dq); cudaFree(dok);
   return ZKB_OK;
 }
 
@@ -121,8 +153,12 @@ int zkb_verify_batch(const char *vkey_json, size_t vkey_len, int n, const char *
                      const size_t *publics_len, const char *const *proofs_json, const size_t *proofs_len, int *ok) {
   if (require_device()) return ZKB_ERROR;
   std::lock_guard<std::mutex> g(g_mu);
+  int dev = 0;
+  CKR(cudaGetDevice(&dev), "get device");
+  if (dev < 0 || dev >= MAX_DEV) { set_error("verify: device index out of range"); return ZKB_ERROR; }
   VKeyDev vk;
-  int rc = get_vkey(vkey_json, vkey_len, vk);
+  PairingConsts *g_pc = nullptr;
+  int rc = get_vkey(dev, vkey_json, vkey_len, vk, g_pc);
   if (rc) return rc;
   if (n <= 0) return ZKB_OK;
   std::vector<uint32_t> proofs((size_t)n * 64, 0), pubs((size_t)n * vk.n_public * 8, 0);
@@ -145,18 +181,42 @@ int zkb_verify_batch(const char *vkey_json, size_t vkey_len, int n, const char *
     memcpy(p + 48, m["pi_c"].data(), 64);
     memcpy(pubs.data() + (size_t)i * vk.n_public * 8, pv.data(), pv.size() * 4);
   }
-  Fq *dp = nullptr;
-  Fr *dq = nullptr;
-  int *dok = nullptr;
-  CKR(cudaMalloc(&dp, proofs.size() * 4), "alloc");
-  CKR(cudaMalloc(&dq, pubs.size() * 4 + 32), "alloc");
-  CKR(cudaMalloc(&dok, (size_t)n * 4), "alloc");
-  CKR(cudaMemcpy(dp, proofs.data(), proofs.size() * 4, cudaMemcpyHostToDevice), "h2d");
-  CKR(cudaMemcpy(dq, pubs.data(), pubs.size() * 4, cudaMemcpyHostToDevice), "h2d");
-  k_verify<<<(n + 31) / 32, 32>>>(vk.vk, vk.ic, g_pc, dp, dq, dok, (uint32_t)n);
-  CKR(cudaGetLastError(), "verify launch");
-  CKR(cudaMemcpy(ok, dok, (size_t)n * 4, cudaMemcpyDeviceToHost), "d2h");
-  cudaFree(dp); cudaFree(dq); cudaFree(dok);
+  rc = verify_device(vk, g_pc, proofs.data(), pubs.data(), n, ok);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++)
+    if (bad[i]) ok[i] = 0;
+  return ZKB_OK;
+}
+
+// Same check on binary results (what zkb_batch_get_results returns): proofs256 = n x 256 B canonical LE coordinates
+// (A.x A.y B.x.c0 B.x.c1 B.y.c0 B.y.c1 C.x C.y), publics = n x nPublic x 32 B canonical LE.  Values outside
+// [0, q) / [0, r) make the proof invalid (ok[i] = 0).
+int zkb_verify_batch_bin(const char *vkey_json, size_t vkey_len, int n, const void *publics, const void *proofs256, int *ok) {
+  if (require_device()) return ZKB_ERROR;
+  if (!vkey_json || (n > 0 && (!publics || !proofs256 || !ok))) { set_error("null argument"); return ZKB_ERROR; }
+  std::lock_guard<std::mutex> g(g_mu);
+  int dev = 0;
+  CKR(cudaGetDevice(&dev), "get device");
+  if (dev < 0 || dev >= MAX_DEV) { set_error("verify: device index out of range"); return ZKB_ERROR; }
+  VKeyDev vk;
+  PairingConsts *g_pc = nullptr;
+  int rc = get_vkey(dev, vkey_json, vkey_len, vk, g_pc);
+  if (rc) return rc;
+  if (n <= 0) return ZKB_OK;
+  static const uint32_t QMOD[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+  static const uint32_t RMOD[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+  auto below = [](const uint32_t *v, const uint32_t *m) {
+    for (int k = 7; k >= 0; k--) if (v[k] != m[k]) return v[k] < m[k];
+    return false;
+  };
+  const uint32_t *pw = (const uint32_t *)proofs256, *qw = (const uint32_t *)publics;
+  std::vector<int> bad(n, 0);
+  for (int i = 0; i < n; i++) {
+    for (int k = 0; k < 8; k++) if (!below(pw + (size_t)i * 64 + 8 * k, QMOD)) bad[i] = 1;
+    for (uint32_t k = 0; k < vk.n_public; k++) if (!below(qw + ((size_t)i * vk.n_public + k) * 8, RMOD)) bad[i] = 1;
+  }
+  rc = verify_device(vk, g_pc, pw, qw, n, ok);
+  if (rc) return rc;
   for (int i = 0; i < n; i++)
     if (bad[i]) ok[i] = 0;
   return ZKB_OK;

@@ -35,6 +35,8 @@ def _lib():
         L.zkb_ctx_stream.argtypes = [_vp]
         L.zkb_ctx_stream.restype = _vp
         L.zkb_load_circuit.argtypes = [_vp, _vp, _sz, _vp, _sz, ctypes.POINTER(_vp)]
+        L.zkb_load_circuit_ex.argtypes = [_vp, _vp, _sz, _vp, _sz, ctypes.c_uint32, ctypes.POINTER(_vp)]
+        L.zkb_verify_batch_bin.argtypes = [ctypes.c_char_p, _sz, _i32, _vp, _vp, _vp]
         L.zkb_load_circuit_shard.argtypes = [_vp, _vp, _sz, _i32, _i32, ctypes.POINTER(_vp)]
         L.zkb_shard_export.argtypes = [_vp, _vp]
         L.zkb_shard_attach.argtypes = [_vp, _vp]
@@ -91,9 +93,11 @@ class Context:
 class Circuit:
     """A proving key + witness calculator loaded onto the GPU (zkb_load_circuit)."""
 
-    def __init__(self, ctx: Context, zkey: bytes, wasm: bytes = None, shard=None):
-        """shard = (rank, nranks): keep only this rank's point ranges of the key (zkb_load_circuit_shard)."""
+    def __init__(self, ctx: Context, zkey: bytes, wasm: bytes = None, shard=None, dense=False):
+        """shard = (rank, nranks): keep only this rank's point ranges of the key (zkb_load_circuit_shard).
+        dense = True: ZKB_LOAD_DENSE, the proof-independent-wire shortcut is off (measurement aid)."""
         self.ctx = ctx
+        self.dense = dense
         self.h = _vp()
         self.shard = shard
         zb = (ctypes.c_char * len(zkey)).from_buffer_copy(zkey)
@@ -102,9 +106,9 @@ class Circuit:
             _native.check(_lib().zkb_load_circuit_shard(ctx.h, ctypes.addressof(zb), len(zkey), shard[0], shard[1],
                                                         ctypes.byref(self.h)))
         else:
-            _native.check(_lib().zkb_load_circuit(ctx.h, ctypes.addressof(zb), len(zkey),
-                                                  ctypes.addressof(wb) if wasm else None, len(wasm) if wasm else 0,
-                                                  ctypes.byref(self.h)))
+            _native.check(_lib().zkb_load_circuit_ex(ctx.h, ctypes.addressof(zb), len(zkey),
+                                                     ctypes.addressof(wb) if wasm else None, len(wasm) if wasm else 0,
+                                                     1 if dense else 0, ctypes.byref(self.h)))
         info = np.zeros(8, dtype=np.uint32)
         _lib().zkb_circuit_info(self.h, info.ctypes.data)
         self.n_vars, self.n_public, self.domain, self.n_inputs, self.n_levels1 = (int(x) for x in info[:5])
@@ -284,11 +288,11 @@ def _context(device=None):
     return _ctx[device]
 
 
-def load(zkey: bytes, wasm: bytes = None, device=None) -> Circuit:
+def load(zkey: bytes, wasm: bytes = None, device=None, dense=False) -> Circuit:
     """Cached zkb_load_circuit."""
-    key = (hashlib.sha256(zkey).digest(), hashlib.sha256(wasm).digest() if wasm else None, device)
+    key = (hashlib.sha256(zkey).digest(), hashlib.sha256(wasm).digest() if wasm else None, device, dense)
     if key not in _circuits:
-        _circuits[key] = Circuit(_context(device), zkey, wasm)
+        _circuits[key] = Circuit(_context(device), zkey, wasm, dense=dense)
     return _circuits[key]
 
 
@@ -331,6 +335,17 @@ def verify_batch(vkey: bytes, public_signals: list, proofs: list) -> list:
     ok = (ctypes.c_int * n)()
     _native.check(_lib().zkb_verify_batch(vk, len(vk), n, pa, pl, fa, fl, ok))
     return list(ok)
+
+
+def verify_batch_bin(vkey: bytes, publics: np.ndarray, proofs256: np.ndarray) -> np.ndarray:
+    """ok flags for binary results as Circuit.get_results returns them (zkb_verify_batch_bin)."""
+    vk = vkey if isinstance(vkey, bytes) else (vkey.encode() if isinstance(vkey, str) else json.dumps(vkey).encode())
+    pr = np.ascontiguousarray(proofs256, dtype=np.uint8)
+    pb = np.ascontiguousarray(publics, dtype=np.uint8)
+    n = pr.shape[0]
+    ok = np.zeros(n, dtype=np.int32)
+    _native.check(_lib().zkb_verify_batch_bin(vk, len(vk), n, pb.ctypes.data, pr.ctypes.data, ok.ctypes.data))
+    return ok
 
 
 # ---- snarkjs-shaped API -------------------------------------------------------------------------------
