@@ -30,6 +30,8 @@ METRIC = "census Groth16 proofs/sec"
 UNIT = "proofs/s"
 WORKLOAD = "census.circom nLevels=160 (82,754 wires, domain 2^17), batch of 1024 proofs per GPU, synthetic 1024-voter census seed 0xC0FFEE"
 MODMUL_PER_MADD_G1 = 10      # XYZZ mixed add: 8M + 2S
+MODMUL_PER_AFFINE_ADD = 6    # batched-affine add: prefix product, 2 for the shared inverse, lambda, lambda^2, y3
+MODMUL_PER_INVERSION = 256 + 110   # Fermat: square-and-multiply over the 256-bit exponent q - 2 (110 set bits)
 
 
 # ---- helpers shared with the CPU (gloo) tests ---------------------------------------------------------
@@ -544,9 +546,12 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel: G1 bucket accumulation (integer pipe) ----
     stages /= args.steps                     # ms per step: witness, abc, ntt+join, sort, acc_g1, acc_g2, reduce, finalize
     peak_modmul, _ = raw.bench_modmul("fq", 4096, 8)
-    madds_g1 = work["g1_madds_per_proof"] * batch
+    # executed field products of the G1 accumulation stage (XYZZ mixed adds + the H MSM's affine pair tree)
+    g1_modmul_per_proof = (work["g1_madds_per_proof"] * MODMUL_PER_MADD_G1 +
+                           work["g1_affine_adds_per_proof"] * MODMUL_PER_AFFINE_ADD +
+                           work["g1_inversions_per_proof"] * MODMUL_PER_INVERSION)
     acc_g1_s = stages[4] * 1e-3
-    achieved = madds_g1 * MODMUL_PER_MADD_G1 / acc_g1_s if acc_g1_s > 0 else 0.0
+    achieved = g1_modmul_per_proof * batch / acc_g1_s if acc_g1_s > 0 else 0.0
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (tools/ncu_summary.py --raw)
     traffic = None
     for name in ("r02_traffic.json", "r01_traffic.json"):
@@ -556,12 +561,16 @@ def run_ours(args, rank, world, local_rank):
             break
     # executed modmuls per proof (what this pipeline runs; SURVEY 8d: never divide dense work by shortcut time)
     logd = c.domain.bit_length() - 1
-    executed = (work["g1_madds_per_proof"] * 10 + work["g2_madds_per_proof"] * 28     # bucket accumulation
+    executed = (g1_modmul_per_proof + work["g2_madds_per_proof"] * 28                 # bucket accumulation
                 + 6 * (c.domain // 2) * logd + 3 * c.domain                          # 6 transforms + coset scale
                 + 462889 + 2 * c.domain                                              # buildABC (nnz) + join
                 + 2 * 32768 * 14 + 3 * 2 * 4096 * 14 + 2 * 4096 * 14 * 3             # bucket reductions: H, A/B1/C, B2 (x3 Fq)
                 + 2.0e4 + 8.0e3)                                                     # witness (levels above the leaf), assembly
-    roofline = {"bound": "imad", "kernel": "k_accumulate<Fq> (G1 bucket accumulation, XYZZ mixed adds)",
+    roofline = {"bound": "imad", "kernel": "G1 bucket accumulation: k_affine_level (H MSM pair tree, batched-affine adds) + "
+                                           "k_accumulate<Fq> / k_accumulate_pts (XYZZ mixed adds)",
+                "executed_per_proof": {"xyzz_madds": work["g1_madds_per_proof"], "affine_adds": work["g1_affine_adds_per_proof"],
+                                       "inversions": work["g1_inversions_per_proof"], "modmul": g1_modmul_per_proof,
+                                       "modmul_if_all_xyzz": (work["g1_madds_per_proof"] + work["g1_affine_adds_per_proof"]) * 10},
                 "achieved": achieved / 1e9, "peak": peak_modmul / 1e9, "unit": "Gmodmul/s",
                 "frac": achieved / peak_modmul if peak_modmul else None, "traffic": traffic,
                 "peak_source": "measured in this run: zkb_bench_modmul (dependent 254-bit Montgomery products, "

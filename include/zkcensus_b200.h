@@ -153,7 +153,8 @@ int zkb_batch_prove_resident(zkb_circuit *c, int n, float *stage_ms);
 int zkb_batch_get_results(zkb_circuit *c, int n, void *proofs256, void *publics, int *status);
 int zkb_batch_get_witness(zkb_circuit *c, int first, int n, void *wtns);
 /* measurement aids: kernels launched so far by the proving pipeline; executed MSM work of the last chunk
- * (out[6]: G1 mixed adds, G2 mixed adds, witness digit entries, H digit entries, proofs in chunk, chunk capacity) */
+ * (out[8]: G1 XYZZ mixed adds, G2 mixed adds, witness digit entries, H digit entries, proofs in chunk, chunk capacity,
+ * affine additions of the H MSM's pair tree (6 field products each), field inversions of the pair tree) */
 uint64_t zkb_launch_count(void);
 int zkb_work_counters(zkb_circuit *c, uint64_t *out);
 /* debugging aid for parity tests: the five MSM partial sums (pi_a' pi_b1' pi_b' pi_c' pi_h, 384 B affine canonical)
@@ -173,6 +174,10 @@ int zkb_raw_msm_g1(const void *bases, size_t n, const void *scalars, int nbatch,
                    float *table_ms);
 int zkb_raw_msm_g2(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
                    float *table_ms);
+/* flags bit 0: bucket lists summed by the batched-affine pair tree (what the prover's H MSM uses in batch shape);
+ * bits 8-11: tree levels (0 = 3), bits 16-31: additions sharing one field inversion (0 = 512) */
+int zkb_raw_msm_g1_ex(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
+                      float *table_ms, uint32_t flags);
 
 
 /* --- device-resident raw sessions: large MSM split by point range, across GPUs (BASELINE.json configs 4-5) -------

@@ -203,7 +203,10 @@ def test_stage_timing_and_work_counters(circuit):
     wc = circuit.work_counters()
     # H is dense (131,072 full-width scalars x 16 windows, minus zero digits and one free add per bucket); the four
     # witness MSMs only see the wires that differ from the per-key template, far below 16 x 82,754
-    assert 16 * 131072 * 0.9 < wc["g1_madds_per_proof"] < 16 * 131072 + 3 * 16 * 82754 * 0.25
+    # (the H MSM's additions are split between the batched-affine pair tree and the XYZZ tail)
+    adds = wc["g1_madds_per_proof"] + wc["g1_affine_adds_per_proof"]
+    assert 16 * 131072 * 0.9 < adds < 16 * 131072 + 3 * 16 * 82754 * 0.25
+    assert wc["g1_affine_adds_per_proof"] == 0 or wc["g1_inversions_per_proof"] > 0
     assert 0 < wc["g2_madds_per_proof"] < 16 * 82754 * 0.25
     print("stage ms for 32 proofs:", [round(float(x), 2) for x in st], wc)
 

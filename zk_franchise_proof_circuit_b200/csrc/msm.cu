@@ -13,6 +13,7 @@
 #include "msm.cuh"
 #include "ec_coop.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace zkb {
 
@@ -492,6 +493,338 @@ __global__ void __launch_bounds__(32) k_accumulate_long(TablePtrs<F> tabs, int n
     __syncwarp();
   }
   if (lane == 0) stg_pod(buckets + ((size_t)(b * ntab + t) * nbuckets + bucket), acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched-affine pair tree (see MsmAffineWs in msm.cuh)
+// ---------------------------------------------------------------------------------------------
+// One CTA per batch item: lvl_off[l][b][0..B] = exclusive scan of len_{l+1}[j] = ceil(len_l[j] / 2), l < levels,
+// starting from the sorted-entry offsets (len_0).  1024 threads, buckets / 1024 <= 32 counters each.
+__global__ void __launch_bounds__(1024) k_affine_scans(const uint32_t *offsets, uint32_t *lvl_off, uint32_t buckets,
+                                                       uint32_t nbatch, int levels) {
+  __shared__ uint32_t warp_tot[32];
+  const uint32_t b = blockIdx.x, t = threadIdx.x, per = buckets / 1024;
+  const uint32_t *o0 = offsets + (size_t)b * (buckets + 1) + t * per;
+  uint32_t len[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++)
+    if ((uint32_t)i < per) len[i] = o0[i + 1] - o0[i];
+  for (int l = 0; l < levels; l++) {
+    uint32_t loc[32], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+      if ((uint32_t)i < per) { len[i] = (len[i] + 1) >> 1; loc[i] = sum; sum += len[i]; }
+    uint32_t x = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if ((t & 31) >= d) x += y;
+    }
+    __syncthreads();                         // warp_tot of the previous level is no longer read
+    if ((t & 31) == 31) warp_tot[t >> 5] = x;
+    __syncthreads();
+    if (t < 32) {
+      uint32_t v = warp_tot[t], z = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, z, d);
+        if (t >= d) z += y;
+      }
+      warp_tot[t] = z - v;
+    }
+    __syncthreads();
+    const uint32_t base = warp_tot[t >> 5] + x - sum;
+    uint32_t *o = lvl_off + ((size_t)l * nbatch + b) * (buckets + 1) + t * per;
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+      if ((uint32_t)i < per) o[i] = base + loc[i];
+    if (t == 1023) lvl_off[((size_t)l * nbatch + b) * (buckets + 1) + buckets] = base + sum;
+  }
+}
+
+__device__ __forceinline__ Fq ldg_fq(const Fq *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  const uint4 a = __ldg(q), b = __ldg(q + 1);
+  Fq r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void stg_fq(Fq *p, const Fq &x) {
+  uint4 *q = reinterpret_cast<uint4 *>(p);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+
+// What one output of a level is made of.  kind: 0 = sum of two distinct points (divisor x2 - x1), 1 = copy of a single
+// point (odd tail of a list), 2 = first operand at infinity (take the second), 3 = second at infinity (take the first),
+// 4 = doubling (equal points, divisor 2 y1), 5 = opposite points (result at infinity).  Kinds 2..5 only occur with
+// degenerate bases (repeated or at infinity); they cost a branch that is never taken for a real proving key.
+struct PairSrc {
+  const Affine<Fq> *p1, *p2;
+  bool neg1, neg2, has2;
+};
+template <bool FIRST>
+__device__ __forceinline__ PairSrc pair_src(const Affine<Fq> *tab, const uint32_t *ent, const Affine<Fq> *pin, uint32_t in0,
+                                            bool has2) {
+  PairSrc s;
+  s.has2 = has2;
+  if (FIRST) {
+    const uint32_t e1 = ent[in0], e2 = has2 ? ent[in0 + 1] : 0u;
+    s.p1 = tab + (e1 & 0x7fffffffu);
+    s.p2 = tab + (e2 & 0x7fffffffu);
+    s.neg1 = (e1 >> 31) != 0;
+    s.neg2 = (e2 >> 31) != 0;
+  } else {
+    s.p1 = pin + in0;
+    s.p2 = pin + in0 + (has2 ? 1 : 0);
+    s.neg1 = s.neg2 = false;
+  }
+  return s;
+}
+// divisor of the pair (Montgomery one when the output needs no division) and its kind
+__device__ __forceinline__ Fq pair_divisor(const PairSrc &s, int &kind) {
+  if (!s.has2) { kind = 1; return Fq::one(); }
+  const Fq x1 = ldg_fq(&s.p1->x), x2 = ldg_fq(&s.p2->x);
+  Fq d = x2 - x1;
+  kind = 0;
+  if (x1.is_zero() || x2.is_zero() || d.is_zero()) {       // rare: look at y
+    Fq y1 = ldg_fq(&s.p1->y), y2 = ldg_fq(&s.p2->y);
+    if (s.neg1) y1 = y1.neg();
+    if (s.neg2) y2 = y2.neg();
+    if (x1.is_zero() && y1.is_zero()) { kind = 2; d = Fq::one(); }
+    else if (x2.is_zero() && y2.is_zero()) { kind = 3; d = Fq::one(); }
+    else if (d.is_zero()) {
+      if (y1 == y2 && !y1.is_zero()) { kind = 4; d = y1.dbl(); }
+      else { kind = 5; d = Fq::one(); }
+    }
+  }
+  return d;
+}
+
+// thread = `group` consecutive outputs of level l + 1 of batch item blockIdx.y
+template <bool FIRST>
+__global__ void __launch_bounds__(128) k_affine_level(const Affine<Fq> *tab, size_t tab_batch_stride, uint32_t tab_mod,
+                                                      const uint32_t *__restrict__ entries, size_t ent_stride,
+                                                      const Affine<Fq> *pin, size_t pin_stride,
+                                                      const uint32_t *__restrict__ off_in_all,
+                                                      const uint32_t *__restrict__ off_out_all, Affine<Fq> *pout_all,
+                                                      size_t pout_stride, Fq *park_all, size_t park_stride,
+                                                      uint32_t nbuckets, uint32_t group) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t *off_in = off_in_all + (size_t)b * (nbuckets + 1), *off_out = off_out_all + (size_t)b * (nbuckets + 1);
+  const uint32_t total = off_out[nbuckets];
+  const uint32_t o0 = (blockIdx.x * 128u + threadIdx.x) * group;
+  if (o0 >= total) return;
+  const uint32_t cnt = min(group, total - o0);
+  const Affine<Fq> *tb = FIRST ? tab + (size_t)(b % tab_mod) * tab_batch_stride : nullptr;
+  const uint32_t *ent = FIRST ? entries + (size_t)b * ent_stride : nullptr;
+  const Affine<Fq> *pi = FIRST ? nullptr : pin + (size_t)b * pin_stride;
+  Affine<Fq> *pout = pout_all + (size_t)b * pout_stride;
+  Fq *park = park_all + (size_t)b * park_stride;
+  // bucket of the first output: the j with off_out[j] <= o0 < off_out[j + 1]
+  uint32_t lo = 0, hi = nbuckets;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (off_out[mid] <= o0) lo = mid; else hi = mid;
+  }
+  uint32_t j = lo, k = o0 - off_out[lo];
+  const uint32_t j0 = j, k0 = k;
+  uint32_t out_end = off_out[j + 1] - off_out[j];          // outputs of bucket j
+  uint32_t in_beg = off_in[j], in_len = off_in[j + 1] - in_beg;
+  // pass 1: prefix products of the divisors
+  Fq acc = Fq::one();
+  for (uint32_t i = 0; i < cnt; i++) {
+    while (k == out_end) {                                 // next non-empty bucket
+      j++; k = 0;
+      out_end = off_out[j + 1] - off_out[j];
+      in_beg = off_in[j]; in_len = off_in[j + 1] - in_beg;
+    }
+    const PairSrc s = pair_src<FIRST>(tb, ent, pi, in_beg + 2 * k, 2 * k + 1 < in_len);
+    int kind;
+    const Fq d = pair_divisor(s, kind);
+    acc = acc * d;
+    stg_fq(park + o0 + i, acc);
+    k++;
+  }
+  Fq inv = acc.inv();
+  // pass 2, backwards: 1 / d_i = inv(d_0 .. d_i) * (d_0 .. d_{i-1})
+  k--;                                                     // (j, k) = last output of the range
+  for (uint32_t i = cnt; i-- > 0;) {
+    const PairSrc s = pair_src<FIRST>(tb, ent, pi, in_beg + 2 * k, 2 * k + 1 < in_len);
+    int kind;
+    const Fq d = pair_divisor(s, kind);
+    const Fq prev = i ? park[o0 + i - 1] : Fq::one();     // written by this thread in pass 1: plain (coherent) load
+    const Fq dinv = inv * prev;
+    inv = inv * d;
+    Affine<Fq> r;
+    Fq x1 = ldg_fq(&s.p1->x), y1 = ldg_fq(&s.p1->y);
+    if (s.neg1) y1 = y1.neg();
+    if (kind == 0 || kind == 4) {
+      Fq x2, lam;
+      if (kind == 0) {
+        x2 = ldg_fq(&s.p2->x);
+        Fq y2 = ldg_fq(&s.p2->y);
+        if (s.neg2) y2 = y2.neg();
+        lam = (y2 - y1) * dinv;
+      } else {
+        x2 = x1;
+        const Fq xx = x1 * x1;
+        lam = (xx.dbl() + xx) * dinv;
+      }
+      r.x = lam * lam - x1 - x2;
+      r.y = lam * (x1 - r.x) - y1;
+    } else if (kind == 1 || kind == 3) {
+      r.x = x1; r.y = y1;
+    } else if (kind == 2) {
+      r.x = ldg_fq(&s.p2->x);
+      r.y = ldg_fq(&s.p2->y);
+      if (s.neg2) r.y = r.y.neg();
+    } else {
+      r.x = Fq::zero(); r.y = Fq::zero();
+    }
+    stg_pod(pout + o0 + i, r);
+    if (i) {
+      if (k == 0) {                                        // previous non-empty bucket (never before (j0, k0))
+        do {
+          j--;
+          out_end = off_out[j + 1] - off_out[j];
+        } while (out_end == 0);
+        k = out_end;
+        in_beg = off_in[j]; in_len = off_in[j + 1] - in_beg;
+      }
+      k--;
+    }
+  }
+  (void)j0; (void)k0;
+}
+
+// XYZZ tail: thread = bucket, summing its remaining affine points (list of the last level)
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_accumulate_pts(const Affine<Fq> *pts_all, size_t pts_stride,
+                                                                  const uint32_t *__restrict__ off_all,
+                                                                  const uint32_t *__restrict__ order, uint32_t nbuckets,
+                                                                  XYZZ<Fq> *buckets) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t pos = blockIdx.x * THREADS + threadIdx.x;
+  const uint32_t bucket = order[(size_t)b * nbuckets + pos];
+  const uint32_t *off = off_all + (size_t)b * (nbuckets + 1);
+  const Affine<Fq> *pts = pts_all + (size_t)b * pts_stride;
+  const uint32_t beg = off[bucket], len = off[bucket + 1] - beg;
+  const uint32_t maxlen = __reduce_max_sync(0xffffffffu, len);
+  XYZZ<Fq> acc = XYZZ<Fq>::infinity();
+  bool acc_inf = true;
+  for (uint32_t i = 0; i < maxlen; i++) {
+    const bool active = i < len;
+    Affine<Fq> p = ldg_pod(pts + (active ? beg + i : 0u));
+    const bool use = active && !p.is_inf();
+    Fq U2 = p.x * acc.ZZ, S2 = p.y * acc.ZZZ;
+    Fq P = U2 - acc.X, R = S2 - acc.Y;
+    const bool special = use && !acc_inf && P.is_zero();
+    Fq PP = P * P, PPP = P * PP, Q = acc.X * PP;
+    Fq X3 = R * R - PPP - Q.dbl();
+    Fq Y3 = R * (Q - X3) - acc.Y * PPP;
+    Fq ZZ3 = acc.ZZ * PP, ZZZ3 = acc.ZZZ * PPP;
+    const bool normal = use && !acc_inf && !special, first = use && acc_inf;
+    acc.X = Fq::select(normal, X3, Fq::select(first, p.x, acc.X));
+    acc.Y = Fq::select(normal, Y3, Fq::select(first, p.y, acc.Y));
+    acc.ZZ = Fq::select(normal, ZZ3, Fq::select(first, Fq::one(), acc.ZZ));
+    acc.ZZZ = Fq::select(normal, ZZZ3, Fq::select(first, Fq::one(), acc.ZZZ));
+    acc_inf = acc_inf && !first;
+    if (__any_sync(0xffffffffu, special)) {
+      if (special) {
+        if (R.is_zero()) { acc = XYZZ<Fq>::dbl_affine(p); }
+        else { acc = XYZZ<Fq>::infinity(); acc_inf = true; }
+      }
+      __syncwarp();
+    }
+  }
+  if (acc_inf) acc = XYZZ<Fq>::infinity();
+  stg_pod(buckets + ((size_t)b * nbuckets + bucket), acc);
+}
+
+cudaError_t MsmAffineWs::alloc(uint32_t n_entries, uint32_t batch_, MsmCfg cfg) {
+  batch = batch_;
+  buckets = cfg.buckets;
+  if (buckets < 1024 || buckets % 1024 || buckets / 1024 > 32) return cudaErrorInvalidValue;
+  cap_a = ((size_t)n_entries + buckets) / 2 + 1;
+  cap_b = (cap_a + buckets) / 2 + 1;
+  const char *lv = getenv("ZKB_AFFINE_LEVELS");
+  if (lv && atoi(lv) >= 1 && atoi(lv) <= MAX_LEVELS) levels = atoi(lv);
+  const char *gr = getenv("ZKB_AFFINE_GROUP");   // "512" or "512,256,128"
+  if (gr) {
+    uint32_t last = 512;
+    for (int l = 0; l < MAX_LEVELS; l++) {
+      if (gr && *gr) { last = (uint32_t)atoi(gr); gr = strchr(gr, ','); if (gr) gr++; }
+      group[l] = last >= 8 ? last : 8;
+    }
+  }
+  CK(cudaMalloc(&pa, (size_t)batch * cap_a * sizeof(Affine<Fq>)));
+  CK(cudaMalloc(&pb, (size_t)batch * cap_b * sizeof(Affine<Fq>)));
+  CK(cudaMalloc(&park, (size_t)batch * cap_a * sizeof(Fq)));
+  CK(cudaMalloc(&lvl_off, (size_t)MAX_LEVELS * batch * (buckets + 1) * 4));
+  CK(cudaMalloc(&d_adds, 16));
+  return cudaSuccess;
+}
+void MsmAffineWs::free_all() {
+  cudaFree(pa); cudaFree(pb); cudaFree(park); cudaFree(lvl_off); cudaFree(d_adds);
+  pa = pb = nullptr; park = nullptr; lvl_off = nullptr; d_adds = nullptr;
+}
+int msm_affine_launches(const MsmAffineWs &ws) { return 1 + ws.levels + 1; }
+
+cudaError_t msm_accumulate_affine(const MsmSort &sort, const MsmTable<Fq> &table, uint32_t nbatch, MsmWork<Fq> &work,
+                                  uint32_t slot0, MsmAffineWs &ws, cudaStream_t st, size_t tab_batch_stride,
+                                  uint32_t tab_mod) {
+  if (tab_mod == 0) tab_mod = nbatch;
+  if (nbatch > ws.batch || slot0 + nbatch > work.slots || ws.buckets != sort.cfg.buckets) return cudaErrorInvalidValue;
+  if (table.n != sort.n || table.cfg.c != sort.cfg.c || work.cfg.c != sort.cfg.c) return cudaErrorInvalidValue;
+  const uint32_t nb = sort.cfg.buckets;
+  const size_t ent_stride = (size_t)sort.n * sort.cfg.windows, lstride = (size_t)ws.batch * (nb + 1);
+  k_affine_scans<<<nbatch, 1024, 0, st>>>(sort.offsets, ws.lvl_off, nb, ws.batch, ws.levels);
+  size_t cap_in = ent_stride;
+  for (int l = 0; l < ws.levels; l++) {
+    const uint32_t *off_in = l ? ws.lvl_off + (size_t)(l - 1) * lstride : sort.offsets;
+    const uint32_t *off_out = ws.lvl_off + (size_t)l * lstride;
+    const Affine<Fq> *pin = (l & 1) ? ws.pa : ws.pb;
+    Affine<Fq> *pout = (l & 1) ? ws.pb : ws.pa;
+    const size_t pin_stride = (l & 1) ? ws.cap_a : ws.cap_b, pout_stride = (l & 1) ? ws.cap_b : ws.cap_a;
+    const size_t cap_out = (cap_in + nb) / 2 + 1;           // upper bound of this level's outputs per item
+    const uint32_t g = ws.group[l];
+    dim3 grid((unsigned)((cap_out + (size_t)g * 128 - 1) / ((size_t)g * 128)), nbatch);
+    if (l == 0)
+      k_affine_level<true><<<grid, 128, 0, st>>>(table.tab, tab_batch_stride, tab_mod, sort.entries, ent_stride, nullptr, 0,
+                                                  off_in, off_out, pout, pout_stride, ws.park, ws.cap_a, nb, g);
+    else
+      k_affine_level<false><<<grid, 128, 0, st>>>(nullptr, 0, 1, nullptr, 0, pin, pin_stride, off_in, off_out, pout,
+                                                   pout_stride, ws.park, ws.cap_a, nb, g);
+    cap_in = cap_out;
+  }
+  const int last = ws.levels - 1;
+  const Affine<Fq> *pts = (last & 1) ? ws.pb : ws.pa;
+  const size_t pts_stride = (last & 1) ? ws.cap_b : ws.cap_a;
+  k_accumulate_pts<128, 4><<<dim3(nb / 128, nbatch), 128, 0, st>>>(pts, pts_stride, ws.lvl_off + (size_t)last * lstride,
+                                                                  sort.order, nb, work.buckets + (size_t)slot0 * nb);
+  return cudaGetLastError();
+}
+
+// executed work of the pair tree over the current sort: affine additions = sum over levels and buckets of
+// floor(len_l / 2); tail mixed additions = sum over buckets of (len_levels - 1)+
+__global__ void k_affine_counts(const uint32_t *offsets, uint32_t nbuckets, int levels, unsigned long long *out) {
+  const uint32_t bucket = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
+  uint32_t len = off[bucket + 1] - off[bucket];
+  unsigned long long adds = 0;
+  for (int l = 0; l < levels; l++) { adds += len >> 1; len = (len + 1) >> 1; }
+  atomicAdd(out, adds);
+  if (len > 1) atomicAdd(out + 1, (unsigned long long)(len - 1));
+}
+cudaError_t msm_affine_counts(const MsmSort &sort, const MsmAffineWs &ws, uint32_t nbatch, unsigned long long *out2,
+                              cudaStream_t st) {
+  CK(cudaMemsetAsync(ws.d_adds, 0, 16, st));
+  k_affine_counts<<<dim3(sort.cfg.buckets / 128, nbatch), 128, 0, st>>>(sort.offsets, sort.cfg.buckets, ws.levels, ws.d_adds);
+  CK(cudaMemcpyAsync(out2, ws.d_adds, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -24,6 +24,7 @@
 #include <cerrno>
 #include <memory>
 #include <atomic>
+#include <thread>
 #include <algorithm>
 #include <cstdlib>
 #include "common.h"
@@ -290,6 +291,7 @@ struct Lane {
   cudaEvent_t e_fork = nullptr, e_sortW = nullptr, e_W = nullptr, e_2 = nullptr;
   Fr *abc = nullptr, *hs = nullptr, *dw = nullptr, *stage = nullptr;
   MsmSort sortW, sortH;
+  MsmAffineWs affH;               // batched-affine pair tree of the H MSM (batch shape only)
   MsmWork<Fq> work1, workH;
   MsmWork<Fq2> work2;
   XYZZ<Fq> *g1out = nullptr, *g1raw = nullptr;   // g1raw / g2raw: per point-range sums before the fold (large keys)
@@ -304,6 +306,7 @@ struct Lane {
     if (work1.buckets) work1.free_all();
     if (workH.buckets) workH.free_all();
     if (work2.buckets) work2.free_all();
+    if (affH.pa) affH.free_all();
   }
 };
 static constexpr int MAX_LANES = 8;
@@ -333,6 +336,7 @@ struct Circuit {
   // dense: the proof-independent-wire shortcut is off - every SMT level is hashed and the four witness
   // MSMs run over the full witness, as snarkjs / rapidsnark do (measurement aid: zkb_load_circuit_ex flag 1)
   bool dense = false;
+  bool affine = true;              // H MSM bucket lists through the batched-affine pair tree (ZKB_AFFINE=0: XYZZ only)
   // batch workspace
   uint32_t cap = 0;                // proofs resident at once (witness group)
   uint32_t chunk = 0;              // proofs per NTT/MSM chunk
@@ -360,6 +364,7 @@ struct Circuit {
   int *h_status = nullptr;         // pinned
   std::mutex mu;
   uint32_t last_chunk_m = 0;
+  bool last_affine = false;
   int last_lane = 0;
   OsRandom rng;
   // stage timing of the last device pass (ms)
@@ -379,6 +384,9 @@ static bool random_fr(OsRandom &g, uint32_t out[8]) {
     }
   }
 }
+
+// the pair tree pays off when a launch has enough lists to fill the GPU; a single proof keeps the XYZZ kernel
+static constexpr uint32_t AFFINE_MIN_ITEMS = 16;
 
 static uint32_t env_u32(const char *name, uint32_t dflt) {
   const char *v = getenv(name);
@@ -455,6 +463,8 @@ static int alloc_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
     CKR(cudaMalloc(&ln.fin_scratch, (size_t)chunk * 30 * sizeof(XYZZ<Fq>)), "alloc finalize scratch");
     CKR(ln.sortW.alloc(c->nsubW, chunk * c->subW, c->cfgW), "alloc sortW");
     CKR(ln.sortH.alloc(c->nsubH, chunk * c->subH, c->cfgH), "alloc sortH");
+    if (c->affine && chunk * c->subH >= AFFINE_MIN_ITEMS)
+      CKR(ln.affH.alloc(c->nsubH * (uint32_t)c->cfgH.windows, chunk * c->subH, c->cfgH), "alloc H pair tree");
     CKR(ln.work1.alloc(chunk * c->subW * 3, c->cfgW), "alloc msm work g1");
     CKR(ln.workH.alloc(chunk * c->subH, c->cfgH), "alloc msm work g1 (H)");
     CKR(ln.work2.alloc(chunk * c->subW, c->cfgW), "alloc msm work g2");
@@ -497,6 +507,9 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
   XYZZ<Fq2> *out2 = splitW ? ln.g2raw : ln.g2out;
   dim3 g1((c->domain + 127) / 128, m);
   dim3 g2((c->domain + 255) / 256, m);
+  const bool affineH = ln.affH.pa != nullptr && m * sH >= AFFINE_MIN_ITEMS;
+  c->last_affine = affineH;
+  if (affineH) g_launches += msm_affine_launches(ln.affH) - 2;   // instead of the two XYZZ accumulate kernels of the H MSM
   static const uint32_t fork_max = env_u32("ZKB_FORK_MAX", 32);
   if (!ev && m <= fork_max) {
     // Latency shape: after the witness, three independent pipelines.  st: A/B/C vectors -> coset transforms -> h ->
@@ -524,7 +537,8 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
     CKR(c->ntt.dit(ln.abc, 3 * m, c->domain, false, st), "ntt dit");
     k_join<<<g2, 256, 0, st>>>(ln.abc, ln.hs, c->domain);
     CKR(ln.sortH.run(ln.hs + (size_t)c->loH * c->nsubH, c->nsubH, m * sH, st), "sort h digits");
-    CKR(msm_accumulate<Fq>(ln.sortH, &c->tabH, 1, m * sH, ln.workH, 0, st, strH, sH), "msm accumulate g1 (H)");
+    if (affineH) CKR(msm_accumulate_affine(ln.sortH, c->tabH, m * sH, ln.workH, 0, ln.affH, st, strH, sH), "msm accumulate g1 (H, pair tree)");
+    else CKR(msm_accumulate<Fq>(ln.sortH, &c->tabH, 1, m * sH, ln.workH, 0, st, strH, sH), "msm accumulate g1 (H)");
     CKR(msm_reduce<Fq>(ln.workH, 0, m * sH, outH, st), "msm reduce g1 (H)");
     if (splitH) CKR(msm_fold_subs<Fq>(outH, ln.g1out + (size_t)3 * c->chunk, m, sH, 1, st), "fold g1 (H) ranges");
     cudaStreamWaitEvent(st, ln.e_W, 0);
@@ -548,7 +562,8 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
     if (ev) cudaEventRecord(ev[4], st);
     // bucket sums: G1 over the witness difference (A, B1, C share one sort), H over h, G2 (B2) over the witness difference
     CKR(msm_accumulate<Fq>(ln.sortW, tabs, 3, m * sW, ln.work1, 0, st, strW, sW), "msm accumulate g1 (A,B1,C)");
-    CKR(msm_accumulate<Fq>(ln.sortH, &c->tabH, 1, m * sH, ln.workH, 0, st, strH, sH), "msm accumulate g1 (H)");
+    if (affineH) CKR(msm_accumulate_affine(ln.sortH, c->tabH, m * sH, ln.workH, 0, ln.affH, st, strH, sH), "msm accumulate g1 (H, pair tree)");
+    else CKR(msm_accumulate<Fq>(ln.sortH, &c->tabH, 1, m * sH, ln.workH, 0, st, strH, sH), "msm accumulate g1 (H)");
     if (ev) cudaEventRecord(ev[5], st);
     CKR(msm_accumulate<Fq2>(ln.sortW, &c->tabB2, 1, m * sW, ln.work2, 0, st, strW, sW), "msm accumulate g2 (B2)");
     if (ev) cudaEventRecord(ev[6], st);
@@ -693,6 +708,7 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
   c->ctx = ctx;
   c->n_vars = z.n_vars; c->n_public = z.n_public; c->domain = z.domain; c->power = z.power;
   c->dense = (flags & 1u) != 0 || env_u32("ZKB_DENSE", 0) != 0;
+  { const char *a = getenv("ZKB_AFFINE"); c->affine = !(a && a[0] == '0'); }
   cudaStream_t st = ctx->stream;
   memset(&c->L, 0, sizeof c->L);
 
@@ -1151,7 +1167,20 @@ int zkb_work_counters(zkb_circuit *h, uint64_t *out) {
   CKR(msm_count_madds<Fq>(ln.sortW, c->tabA, m, &t[0], st), "count");
   CKR(msm_count_madds<Fq>(ln.sortW, c->tabB1, m, &t[1], st), "count");
   CKR(msm_count_madds<Fq>(ln.sortW, c->tabC, m, &t[2], st), "count");
-  CKR(msm_count_madds<Fq>(ln.sortH, c->tabH, m, &t[3], st), "count");
+  unsigned long long aff[2] = {0, 0}, inversions = 0;
+  if (c->last_affine) {
+    CKR(msm_affine_counts(ln.sortH, ln.affH, m, aff, st), "count");
+    t[3] = aff[1];
+    const uint32_t nb = c->cfgH.buckets;
+    for (int l = 0; l < ln.affH.levels; l++)
+      for (uint32_t b = 0; b < m; b++) {
+        uint32_t tot;
+        CKR(cudaMemcpy(&tot, ln.affH.lvl_off + ((size_t)l * ln.affH.batch + b) * (nb + 1) + nb, 4, cudaMemcpyDeviceToHost), "d2h");
+        inversions += (tot + ln.affH.group[l] - 1) / ln.affH.group[l];
+      }
+  } else {
+    CKR(msm_count_madds<Fq>(ln.sortH, c->tabH, m, &t[3], st), "count");
+  }
   CKR(msm_count_madds<Fq2>(ln.sortW, c->tabB2, m, &t[4], st), "count");
   out[0] = t[0] + t[1] + t[2] + t[3];
   out[1] = t[4];
@@ -1164,6 +1193,7 @@ int zkb_work_counters(zkb_circuit *h, uint64_t *out) {
     eh += v;
   }
   out[2] = ew; out[3] = eh; out[4] = m; out[5] = c->chunk;
+  out[6] = aff[0]; out[7] = inversions;
   return ZKB_OK;
 }
 
@@ -1227,38 +1257,100 @@ int zkb_poseidon_hash(zkb_circuit *h, int arity, int n, const void *in, void *ou
   return ZKB_OK;
 }
 
+}  // extern "C"
+
 // ---- reference-shaped entry points ---------------------------------------------------------------
-// n inputs.json documents -> n proof.json / public.json strings (NUL terminated) at the given strides.
-// status[i]: 0 ok, 1 malformed inputs, 4 circuit assert failed.  Returns 0 unless the batch as a whole failed.
-int zkb_fullprove_batch(zkb_circuit *h, int n, const char *const *inputs_json, const size_t *inputs_len, char *proofs,
-                        size_t proof_stride, char *publics, size_t public_stride, int *status) {
-  Circuit *c = h->c;
-  if (!c->consts) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
-  if (n <= 0) return ZKB_OK;
-  std::lock_guard<std::mutex> g(c->mu);
-  CKR(cudaSetDevice(c->ctx->device), "set device");
-  uint32_t chunk = default_chunk(c), group = env_u32("ZKB_GROUP", 1024);
-  uint32_t cap = (uint32_t)n < group ? (uint32_t)n : group;
-  int rc = ensure_workspace(c, cap > c->cap ? cap : c->cap, chunk);
-  if (rc) return rc;
-  for (uint32_t first = 0; first < (uint32_t)n; first += c->cap) {
-    uint32_t m = (uint32_t)n - first < c->cap ? (uint32_t)n - first : c->cap;
-    std::vector<int> bad(m, 0);
-    std::vector<std::string> errs(m);
-#pragma omp parallel for schedule(dynamic, 8)
-    for (int i = 0; i < (int)m; i++) {
-      uint32_t *dst = c->h_inputs[(size_t)i * c->L.n_inputs].v;
-      memset(dst, 0, (size_t)c->L.n_inputs * 32);
-      if (pack_inputs(c, inputs_json[first + i], inputs_len[first + i], dst, errs[i])) bad[i] = 1;
+// Host threads of the JSON stages.  Not OpenMP: a caller's OMP_NUM_THREADS (torchrun exports 1) must not serialise
+// the parsing of a thousand documents.  ZKB_HOST_THREADS overrides; default min(hardware threads, 16).
+static unsigned host_threads() {
+  static const unsigned n = []() {
+    unsigned e = env_u32("ZKB_HOST_THREADS", 0);
+    if (e) return e;
+    unsigned h = std::thread::hardware_concurrency();
+    if (!h) h = 4;
+    return h > 16 ? 16u : h;
+  }();
+  return n;
+}
+template <class F>
+static void parallel_for(uint32_t n, unsigned nthreads, F fn) {
+  if (!n) return;
+  const unsigned t = nthreads < n ? nthreads : n;
+  if (t <= 1) { for (uint32_t i = 0; i < n; i++) fn(i); return; }
+  std::atomic<uint32_t> next{0};
+  auto body = [&]() { for (;;) { uint32_t i = next.fetch_add(1); if (i >= n) break; fn(i); } };
+  std::vector<std::thread> th;
+  for (unsigned k = 1; k < t; k++) th.emplace_back(body);
+  body();
+  for (auto &x : th) x.join();
+}
+
+// One group of m <= cap documents, host and device overlapped chunk by chunk: worker threads parse the documents in
+// order while this thread, as soon as a chunk's documents are parsed, queues that chunk's H2D copy, proving pipeline
+// and D2H copy on its lane; the proofs of a chunk are formatted as soon as its lane reports it done, while later
+// chunks are still on the GPU.  (Round 1 ran parse -> H2D -> prove -> D2H -> format strictly in sequence.)
+static int fullprove_group(Circuit *c, uint32_t m, const char *const *docs, const size_t *lens, char *proofs,
+                           size_t proof_stride, char *publics, size_t public_stride, int *status) {
+  cudaStream_t st = c->ctx->stream;
+  const uint32_t chunk = c->chunk, nchunks = (m + chunk - 1) / chunk, n_in = c->L.n_inputs;
+  std::vector<int> bad(m, 0);
+  std::vector<std::string> errs(m);
+  if (!fill_blinding(c, m)) return ZKB_ERROR;
+  CKR(cudaMemcpyAsync(c->rs, c->h_rs, (size_t)m * 64, cudaMemcpyHostToDevice, st), "h2d rs");
+  struct EvBag {
+    std::vector<cudaEvent_t> v;
+    ~EvBag() { for (auto e : v) cudaEventDestroy(e); }
+  } bag;
+  bag.v.resize(nchunks + 1);
+  for (auto &e : bag.v) CKR(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
+  cudaEvent_t ev_rs = bag.v[nchunks];
+  CKR(cudaEventRecord(ev_rs, st), "event record");
+  std::unique_ptr<std::atomic<uint32_t>[]> parsed(new std::atomic<uint32_t>[nchunks]);
+  for (uint32_t k = 0; k < nchunks; k++) parsed[k].store(0);
+  std::atomic<uint32_t> next{0};
+  auto parse_body = [&]() {
+    for (;;) {
+      const uint32_t i = next.fetch_add(1);
+      if (i >= m) break;
+      uint32_t *dst = c->h_inputs[(size_t)i * n_in].v;
+      memset(dst, 0, (size_t)n_in * 32);
+      if (pack_inputs(c, docs[i], lens[i], dst, errs[i])) bad[i] = 1;
+      parsed[i / chunk].fetch_add(1, std::memory_order_release);
     }
-    rc = prove_group(c, m, true, nullptr);
-    if (rc) return rc;
-#pragma omp parallel for schedule(dynamic, 8)
-    for (int i = 0; i < (int)m; i++) {
+  };
+  const unsigned nt = m >= 16 ? host_threads() : 1;
+  std::vector<std::thread> workers;
+  if (nt <= 1) parse_body();
+  else for (unsigned k = 0; k + 1 < nt; k++) workers.emplace_back(parse_body);
+  int rc = ZKB_OK;
+  for (uint32_t k = 0; k < nchunks && rc == ZKB_OK; k++) {
+    const uint32_t first = k * chunk, mk = m - first < chunk ? m - first : chunk;
+    while (parsed[k].load(std::memory_order_acquire) < mk) std::this_thread::yield();
+    Lane &ln = c->lanes[k % (uint32_t)c->n_lanes];
+    cudaStreamWaitEvent(ln.st, ev_rs, 0);
+    cudaError_t e = cudaMemcpyAsync(c->inputs + (size_t)first * n_in, c->h_inputs + (size_t)first * n_in, (size_t)mk * n_in * 32,
+                                    cudaMemcpyHostToDevice, ln.st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "h2d inputs"); break; }
+    rc = run_prove_chunk(c, ln, first, mk, true, nullptr);
+    if (rc) break;
+    c->last_chunk_m = mk;
+    c->last_lane = (int)(k % (uint32_t)c->n_lanes);
+    cudaMemcpyAsync(c->h_out + (size_t)first * c->out_stride(), c->out + (size_t)first * c->out_stride(),
+                    (size_t)mk * c->out_stride(), cudaMemcpyDeviceToHost, ln.st);
+    cudaMemcpyAsync(c->h_status + first, c->status + first, (size_t)mk * 4, cudaMemcpyDeviceToHost, ln.st);
+    cudaEventRecord(bag.v[k], ln.st);
+  }
+  for (auto &w : workers) w.join();
+  if (rc) { cudaDeviceSynchronize(); return rc; }
+  for (uint32_t k = 0; k < nchunks; k++) {
+    const uint32_t first = k * chunk, mk = m - first < chunk ? m - first : chunk;
+    CKR(cudaEventSynchronize(bag.v[k]), "prove");
+    parallel_for(mk, nt, [&](uint32_t q) {
+      const uint32_t i = first + q;
       const uint8_t *o = c->h_out + (size_t)i * c->out_stride();
       int stt = bad[i] ? ZKB_ERROR : c->h_status[i];
-      status[first + i] = stt;
-      char *pb = proofs + (size_t)(first + i) * proof_stride, *qb = publics + (size_t)(first + i) * public_stride;
+      status[i] = stt;
+      char *pb = proofs + (size_t)i * proof_stride, *qb = publics + (size_t)i * public_stride;
       pb[0] = 0;
       qb[0] = 0;
       if (stt == 0) {
@@ -1267,12 +1359,38 @@ int zkb_fullprove_batch(zkb_circuit *h, int n, const char *const *inputs_json, c
           memcpy(pb, pj.c_str(), pj.size() + 1);
           memcpy(qb, sj.c_str(), sj.size() + 1);
         } else {
-          status[first + i] = ZKB_SHORT_BUFFER;
+          status[i] = ZKB_SHORT_BUFFER;
         }
       }
-    }
-    for (uint32_t i = 0; i < m; i++)
-      if (bad[i]) set_error(errs[i]);
+    });
+  }
+  for (uint32_t i = 0; i < m; i++)
+    if (bad[i]) set_error(errs[i]);
+  return ZKB_OK;
+}
+
+extern "C" {
+
+// n inputs.json documents -> n proof.json / public.json strings (NUL terminated) at the given strides.
+// status[i]: 0 ok, 1 malformed inputs, 4 circuit assert failed.  Returns 0 unless the batch as a whole failed.
+int zkb_fullprove_batch(zkb_circuit *h, int n, const char *const *inputs_json, const size_t *inputs_len, char *proofs,
+                        size_t proof_stride, char *publics, size_t public_stride, int *status) {
+  if (!h || (n > 0 && (!inputs_json || !inputs_len || !proofs || !publics || !status))) { set_error("null argument"); return ZKB_ERROR; }
+  Circuit *c = h->c;
+  if (!c->consts) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
+  if (n <= 0) return ZKB_OK;
+  if (proof_stride < 1 || public_stride < 1) { set_error("zero output stride"); return ZKB_ERROR; }
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  uint32_t chunk = default_chunk(c), group = env_u32("ZKB_GROUP", 1024);
+  uint32_t cap = (uint32_t)n < group ? (uint32_t)n : group;
+  int rc = ensure_workspace(c, cap > c->cap ? cap : c->cap, chunk);
+  if (rc) return rc;
+  for (uint32_t first = 0; first < (uint32_t)n; first += c->cap) {
+    uint32_t m = (uint32_t)n - first < c->cap ? (uint32_t)n - first : c->cap;
+    rc = fullprove_group(c, m, inputs_json + first, inputs_len + first, proofs + (size_t)first * proof_stride, proof_stride,
+                         publics + (size_t)first * public_stride, public_stride, status + first);
+    if (rc) return rc;
   }
   return ZKB_OK;
 }

@@ -108,7 +108,7 @@ using namespace zkb;
 
 template <class F>
 static int raw_msm(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
-                   float *table_ms) {
+                   float *table_ms, uint32_t flags = 0) {
   if (require_device()) return ZKB_ERROR;
   const char *ce = getenv("ZKB_RAW_MSM_C");
   int cw = ce ? atoi(ce) : 16;
@@ -139,6 +139,21 @@ static int raw_msm(const void *bases, size_t n, const void *scalars, int nbatch,
   for (int r = 0; r < reps; r++) {
     cudaEventRecord(e1);
     CKR(sort.run(ds.as<Fr>(), n, nbatch, 0), "sort");
+    if constexpr (sizeof(F) == 32) {
+      if (flags & 1u) {                      // bucket lists through the batched-affine pair tree
+        MsmAffineWs ws;
+        CKR(ws.alloc((uint32_t)n * (uint32_t)cfg.windows, nbatch, cfg), "pair tree alloc");
+        if ((flags >> 8) & 15u) ws.levels = (int)((flags >> 8) & 15u) > MsmAffineWs::MAX_LEVELS ? MsmAffineWs::MAX_LEVELS : (int)((flags >> 8) & 15u);
+        if (flags >> 16) for (int l = 0; l < MsmAffineWs::MAX_LEVELS; l++) ws.group[l] = flags >> 16;
+        CKR(msm_accumulate_affine(sort, tab, nbatch, work, 0, ws, 0), "msm (pair tree)");
+        CKR(msm_reduce<F>(work, 0, nbatch, dout.as<XYZZ<F>>(), 0), "msm reduce");
+        CKR(cudaDeviceSynchronize(), "msm (pair tree)");
+        ws.free_all();
+        cudaEventRecord(e2);
+        CKR(cudaEventSynchronize(e2), "msm run");
+        continue;
+      }
+    }
     CKR(msm_run<F>(sort, &tab, 1, nbatch, work, dout.as<XYZZ<F>>(), 0), "msm");
     cudaEventRecord(e2);
     CKR(cudaEventSynchronize(e2), "msm run");
@@ -269,6 +284,12 @@ int zkb_raw_coset_ntt(void *data, int logn, int nvec) {
 int zkb_raw_msm_g1(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
                    float *table_ms) {
   return raw_msm<Fq>(bases, n, scalars, nbatch, out, kernel_ms, table_ms);
+}
+// flags bit 0: sum the bucket lists with the batched-affine pair tree (the H MSM's batch path); bits 8-11: tree levels
+// (0 = default 3); bits 16-31: additions per field inversion (0 = default 512)
+int zkb_raw_msm_g1_ex(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
+                      float *table_ms, uint32_t flags) {
+  return raw_msm<Fq>(bases, n, scalars, nbatch, out, kernel_ms, table_ms, flags);
 }
 // G2: points are (x.c0, x.c1, y.c0, y.c1), 128 B each.
 int zkb_raw_msm_g2(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,

@@ -218,7 +218,8 @@ class Circuit:
         m = int(o[4])
         return {"g1_madds_per_proof": float(o[0]) / m, "g2_madds_per_proof": float(o[1]) / m,
                 "witness_digit_entries_per_proof": float(o[2]) / m, "h_digit_entries_per_proof": float(o[3]) / m,
-                "chunk": int(o[5])}
+                "chunk": int(o[5]), "g1_affine_adds_per_proof": float(o[6]) / m,
+                "g1_inversions_per_proof": float(o[7]) / m}
 
     def get_results(self, n=None):
         n = n or self._resident
