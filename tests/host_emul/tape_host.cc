@@ -1,0 +1,63 @@
+// Host build of the generic witness path (csrc/wasm_symexec.cc + csrc/tape_ops.cuh): extracts the witness program from
+// a circom wasm and evaluates it on the CPU with the SAME operation semantics tape_eval.cu runs per lane on the GPU.
+// Test infrastructure for machines without a GPU; the product evaluates tapes on the device only.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../zk_franchise_proof_circuit_b200/csrc/wasm_symexec.cc"
+#include "../../zk_franchise_proof_circuit_b200/csrc/tape_ops.cuh"
+
+using namespace zkb;
+
+static WitnessProgram g_prog;
+static bool g_have = false;
+
+extern "C" {
+
+// info[8] = n_inputs, n_wires, n_slots, tape length, levels, consts, asserts, selects
+int tape_host_build(const uint8_t *wasm, size_t len, uint32_t *info, char *err, size_t errmax) {
+  std::string e;
+  g_prog = WitnessProgram();
+  g_have = build_witness_program(wasm, len, g_prog, e);
+  if (!g_have) { snprintf(err, errmax, "%s", e.c_str()); return 1; }
+  info[0] = g_prog.n_inputs; info[1] = g_prog.n_wires; info[2] = g_prog.n_slots; info[3] = (uint32_t)g_prog.tape.size();
+  info[4] = (uint32_t)g_prog.level_start.size() - 1; info[5] = (uint32_t)(g_prog.consts.size() / 8);
+  info[6] = g_prog.n_asserts; info[7] = g_prog.n_selects;
+  return 0;
+}
+
+// position of the input named `name` in the flat input vector (-1 if unknown); *size = its element count
+int tape_host_input(const char *name, uint32_t *size) {
+  const uint64_t h = fnv1a64_name(name);
+  for (auto &in : g_prog.inputs)
+    if (in.hash == h) { *size = in.size; return (int)(in.pos - g_prog.first_input_signal); }
+  return -1;
+}
+
+// inputs: n_inputs x 32 B canonical; witness: n_wires x 32 B canonical.  returns 0, or 4 when an assert failed
+int tape_host_eval(const uint8_t *inputs, uint8_t *witness) {
+  if (!g_have) return 1;
+  const WitnessProgram &p = g_prog;
+  std::vector<Fr> slot(p.n_slots, Fr::zero()), cst(p.consts.size() / 8);
+  for (size_t i = 0; i < cst.size(); i++) { Fr c; memcpy(c.v, &p.consts[8 * i], 32); cst[i] = c.to_mont(); }
+  for (uint32_t i = 0; i < p.n_inputs; i++) { Fr x; memcpy(x.v, inputs + 32 * i, 32); slot[i] = x.to_mont(); }
+  auto get = [&](uint32_t ref) -> Fr { return (ref & 1u) ? cst[ref >> 1] : slot[ref >> 1]; };
+  bool failed = false;
+  // level by level, results of a level written after all its operands were read (as the GPU lanes do)
+  for (size_t l = 0; l + 1 < p.level_start.size(); l++) {
+    std::vector<Fr> res(p.level_start[l + 1] - p.level_start[l]);
+    for (uint32_t i = p.level_start[l]; i < p.level_start[l + 1]; i++) {
+      const TapeOp &o = p.tape[i];
+      res[i - p.level_start[l]] = tape_apply(o.op, get(o.a), get(o.b), get(o.c), &failed);
+    }
+    for (uint32_t i = p.level_start[l]; i < p.level_start[l + 1]; i++) {
+      const TapeOp &o = p.tape[i];
+      if (o.op != T_ASSERT_TRUE && o.op != T_ASSERT_FALSE) slot[o.dst >> 1] = res[i - p.level_start[l]];
+    }
+  }
+  for (uint32_t w = 0; w < p.n_wires; w++) { Fr x = get(p.wire_ref[w]).from_mont(); memcpy(witness + 32 * w, x.v, 32); }
+  return failed ? 4 : 0;
+}
+
+}  // extern "C"
