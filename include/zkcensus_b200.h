@@ -48,13 +48,19 @@ void *zkb_ctx_stream(zkb_ctx *ctx); /* cudaStream_t the pipeline runs on (for ex
  * artifacts/<name>/<env>/<nLevels>/{proving_key.zkey,circuit.wasm} (zk_census_test.go:81-84) and makes the
  * key device-resident (fixed-base MSM tables, CSR coefficients, NTT twiddles, Poseidon constants,
  * witness template).  wasm may be NULL: then only zkb_prove_wtns / groth16_prover are available.
- * Returns ZKB_UNSUPPORTED_CIRCUIT when the wasm is not a census.circom witness calculator. */
+ * Witness generation: a wasm recognised as census.circom runs on the hand-written census kernel; any other circom-2
+ * witness calculator is executed once, symbolically, at load time and its field operations become a straight-line
+ * program the GPU evaluates per proof.  Returns ZKB_UNSUPPORTED_CIRCUIT only for programs outside
+ * that extractor's subset (control flow or array indexing that depends on a signal value); zkb_last_error says which. */
 int zkb_load_circuit(zkb_ctx *ctx, const void *zkey, size_t zkey_len, const void *wasm, size_t wasm_len,
                      zkb_circuit **out);
 /* flags bit 0 (ZKB_LOAD_DENSE): switch the proof-independent-wire shortcut off - every SMT level is
  * hashed and the four witness MSMs run over all nVars wires, i.e. the work snarkjs / rapidsnark do.  Measurement aid:
  * bench.py reports this point next to the default so the GPU speed-up can be separated from the algorithmic one. */
 #define ZKB_LOAD_DENSE 1u
+/* flags bit 1 (ZKB_LOAD_GENERIC_WITNESS): use the generic (wasm-extracted) witness program even for the census wasm -
+ * the parity test of the generic path against the reference's own witness calculator. */
+#define ZKB_LOAD_GENERIC_WITNESS 2u
 int zkb_load_circuit_ex(zkb_ctx *ctx, const void *zkey, size_t zkey_len, const void *wasm, size_t wasm_len,
                         uint32_t flags, zkb_circuit **out);
 void zkb_circuit_destroy(zkb_circuit *c);

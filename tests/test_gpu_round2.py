@@ -202,3 +202,65 @@ def test_verify_runs_on_the_current_device(files):
         finally:
             cuda.cudaSetDevice(0)
     prover.verify(vk, pub, pf)
+
+
+# ---- generic witness path -------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def generic_circuit(files):
+    """the census key with ZKB_LOAD_GENERIC_WITNESS: the witness program is extracted from circuit.wasm by symbolic
+    execution at load time; nothing census-specific runs"""
+    from zk_franchise_proof_circuit_b200 import prover
+    return prover.load(files[0], files[1], generic=True)
+
+
+def test_generic_witness_gpu_bit_exact(generic_circuit):
+    c = generic_circuit
+    assert (c.n_vars, c.n_inputs) == (82754, 334)
+    inp = H.fixture_inputs()
+    w = H.wtns_payload(c.witness(json.dumps(inp)), c.n_vars)
+    assert H.sha(w.tobytes()) == H.WITNESS_SHA256                      # golden KAT of the reference wasm
+    for v in list(H.voters(2)) + [H.deep_voters()[0]]:
+        code, ref = _ref_witness(v)
+        assert code == 0
+        assert np.array_equal(H.wtns_payload(c.witness(json.dumps(v)), c.n_vars), ref)
+
+
+def test_generic_witness_proofs_match_oracle_and_asserts(generic_circuit, files):
+    from zk_franchise_proof_circuit_b200 import prover
+    c = generic_circuit
+    vs = list(H.voters(40))
+    bad = dict(vs[3], voteWeight="11")                                   # fails LessEqThan: the wasm raises exception 4
+    docs = [json.dumps(v) for v in vs[:3]] + [json.dumps(bad)] + [json.dumps(v) for v in vs[4:]]
+    c.set_blinding(H.R_FIXED, H.S_FIXED)
+    try:
+        proofs, pubs, status = c.fullprove_batch(docs)
+    finally:
+        c.set_blinding(None, None)
+    assert status == [0, 0, 0, 4] + [0] * 36
+    ok = prover.verify_batch(files[2], [q for i, q in enumerate(pubs) if i != 3], [p for i, p in enumerate(proofs) if i != 3])
+    assert ok == [1] * 39
+    for i in (0, 17, 39):
+        code, w = _ref_witness(vs[i])
+        assert O.proof_bin(json.loads(proofs[i])) == H.zkey_ref().prove(w, H.R_FIXED, H.S_FIXED), f"voter {i}"
+    # unknown / missing input names are errors of that document only
+    from zk_franchise_proof_circuit_b200.prover import NativeError
+    with pytest.raises(NativeError):
+        c.fullprove(json.dumps(dict(vs[0], extra="1")))
+    miss = dict(vs[0])
+    del miss["password"]
+    with pytest.raises(NativeError):
+        c.fullprove(json.dumps(miss))
+
+
+def test_non_circom_wasm_is_reported_not_crashed(files):
+    """a wasm that is not a circom witness calculator: ZKB_UNSUPPORTED_CIRCUIT with a message, no crash"""
+    from zk_franchise_proof_circuit_b200 import prover
+    from zk_franchise_proof_circuit_b200.prover import NativeError, UNSUPPORTED_CIRCUIT
+    junk = b"\0asm\x01\0\0\0" + bytes(64)
+    with pytest.raises(NativeError) as ei:
+        prover.Circuit(prover._context(None), files[0], junk)
+    assert ei.value.code in (UNSUPPORTED_CIRCUIT, 1)
+    trunc = files[1][:200000]
+    with pytest.raises(NativeError):
+        prover.Circuit(prover._context(None), files[0], trunc)

@@ -33,6 +33,8 @@
 #include "census_witness.cuh"
 #include "finalize_kernels.h"
 #include "wasm_circuit.h"
+#include "wasm_symexec.h"
+#include "tape_eval.cuh"
 #include "zkey.h"
 #include "json_io.h"
 
@@ -336,6 +338,12 @@ struct Circuit {
   // dense: the proof-independent-wire shortcut is off - every SMT level is hashed and the four witness
   // MSMs run over the full witness, as snarkjs / rapidsnark do (measurement aid: zkb_load_circuit_ex flag 1)
   bool dense = false;
+  // generic witness path: a wasm that is not the census program (or ZKB_LOAD_GENERIC_WITNESS) runs as
+  // a tape extracted from the wasm itself by symbolic execution; has_witness = the circuit can make witnesses at all
+  bool has_witness = false, generic = false;
+  TapeDev tape;
+  std::vector<WitnessProgram::Input> gen_inputs;
+  uint32_t gen_first_signal = 0;
   bool affine = true;              // H MSM bucket lists through the batched-affine pair tree (ZKB_AFFINE=0: XYZZ only)
   // batch workspace
   uint32_t cap = 0;                // proofs resident at once (witness group)
@@ -457,7 +465,8 @@ static int alloc_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
     CKR(cudaMalloc(&ln.hs, (size_t)chunk * c->domain * 32), "alloc h");
     CKR(cudaMalloc(&ln.dw, (size_t)chunk * c->n_pad * 32), "alloc witness diff");
     CKR(cudaMemset(ln.dw, 0, (size_t)chunk * c->n_pad * 32), "clear witness diff");   // the padding stays zero
-    if (c->consts) CKR(cudaMalloc(&ln.stage, (size_t)chunk * c->L.n_signals * 32), "alloc witness staging");
+    if (c->has_witness)
+      CKR(cudaMalloc(&ln.stage, (size_t)chunk * (c->generic ? c->tape.n_slots : c->L.n_signals) * 32), "alloc witness staging");
     CKR(cudaMalloc(&ln.g1out, (size_t)chunk * 4 * sizeof(XYZZ<Fq>)), "alloc g1out");
     CKR(cudaMalloc(&ln.g2out, (size_t)chunk * sizeof(XYZZ<Fq2>)), "alloc g2out");
     CKR(cudaMalloc(&ln.fin_scratch, (size_t)chunk * 30 * sizeof(XYZZ<Fq>)), "alloc finalize scratch");
@@ -479,6 +488,12 @@ static int alloc_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
 // witness for proofs [first, first + n) of c->inputs, n <= chunk, staged in lane ln
 static int run_witness(Circuit *c, Lane &ln, uint32_t first, uint32_t n, cudaStream_t st) {
   CKR(cudaMemsetAsync(c->status + first, 0, (size_t)n * 4, st), "memset status");
+  if (c->generic) {
+    CKR(tape_eval(c->tape, c->inputs + (size_t)first * c->L.n_inputs, ln.stage, c->wtns + (size_t)first * c->n_vars,
+                  c->status + first, n, st), "generic witness (tape)");
+    g_launches += 2;
+    return ZKB_OK;
+  }
   CKR(cudaMemsetAsync(ln.stage, 0, (size_t)n * c->L.n_signals * 32, st), "memset staging");
   k_witness<<<dim3((n * COOP_LANES + 31) / 32, WITNESS_TASKS), 32, 0, st>>>(c->L, c->consts, c->hc,
                                                                c->inputs + (size_t)first * c->L.n_inputs, ln.stage,
@@ -679,6 +694,19 @@ static int pack_inputs(const Circuit *c, const char *json, size_t len, uint32_t 
   std::map<std::string, std::vector<uint32_t>> m;
   if (!parse_inputs_json(json, len, m, err)) return ZKB_ERROR;
   size_t total = 0;
+  if (c->generic) {                 // names resolved through the wasm's own input hashmap (FNV-1a-64 of the name)
+    for (auto &kv : m) {
+      const uint64_t h = fnv1a64_name(kv.first);
+      const WitnessProgram::Input *in = nullptr;
+      for (auto &g : c->gen_inputs) if (g.hash == h) in = &g;
+      if (!in) { err = "inputs: unexpected signal (not an input of the circuit): " + kv.first; return ZKB_ERROR; }
+      if (kv.second.size() != (size_t)in->size * 8) { err = "inputs: wrong number of values for " + kv.first; return ZKB_ERROR; }
+      memcpy(dst + (size_t)(in->pos - c->gen_first_signal) * 8, kv.second.data(), kv.second.size() * 4);
+      total += in->size;
+    }
+    if (m.size() != c->gen_inputs.size() || total != c->L.n_inputs) { err = "inputs: signal not found (an input of the circuit is missing)"; return ZKB_ERROR; }
+    return ZKB_OK;
+  }
   for (int k = 0; k < 12; k++) {
     auto it = m.find(INPUT_NAMES[k]);
     if (it == m.end()) { err = std::string("inputs: signal not found: ") + INPUT_NAMES[k]; return ZKB_ERROR; }
@@ -712,30 +740,33 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
   cudaStream_t st = ctx->stream;
   memset(&c->L, 0, sizeof c->L);
 
-  if (wasm) {
+  // Which witness generator: the hand-written census kernel when the wasm is recognised as census.circom (layout
+  // and input map checked below), the generic tape otherwise (or when flag 2 / ZKB_GENERIC_WITNESS asks for it).
+  bool want_generic = wasm && ((flags & 2u) != 0 || env_u32("ZKB_GENERIC_WITNESS", 0) != 0);
+  std::string census_why;
+  if (wasm && !want_generic) {
     WasmCircuit w;
-    if (!parse_circom_wasm(wasm, wasm_len, w, err)) { set_error(err); return ZKB_UNSUPPORTED_CIRCUIT; }
-    uint32_t pos = 0, size = 0;
-    if (!wasm_input_lookup(w, "censusSiblings", pos, size) || size < 4) { set_error("wasm is not the census circuit (censusSiblings missing)"); return ZKB_UNSUPPORTED_CIRCUIT; }
-    if (!census_layout_build(c->L, size)) { set_error("unsupported number of levels"); return ZKB_UNSUPPORTED_CIRCUIT; }
-    c->L.n_wires = w.n_wires;
-    const uint32_t expect_pos[12] = {c->L.electionId, c->L.nullifier, c->L.voteHash, c->L.sikRoot, c->L.censusRoot,
-                                     c->L.voteWeight, c->L.availableWeight, c->L.address, c->L.password,
-                                     c->L.signature, c->L.censusSiblings, c->L.sikSiblings};
-    const uint32_t expect_size[12] = {2, 1, 2, 1, 1, 1, 1, 1, 1, 1, size, size};
-    for (int k = 0; k < 12; k++) {
-      if (!wasm_input_lookup(w, INPUT_NAMES[k], c->in_pos[k], c->in_size[k]) || c->in_pos[k] != expect_pos[k] ||
-          c->in_size[k] != expect_size[k]) {
-        set_error(std::string("wasm is not the census circuit (input ") + INPUT_NAMES[k] + ")");
-        return ZKB_UNSUPPORTED_CIRCUIT;
-      }
-    }
-    if (w.n_inputs != c->L.n_inputs || w.witness_map.back() >= c->L.n_signals || w.witness_map[0] != 0) {
-      set_error("wasm is not the census circuit (signal layout mismatch)");
-      return ZKB_UNSUPPORTED_CIRCUIT;
-    }
+    auto is_census = [&]() -> bool {
+      if (!parse_circom_wasm(wasm, wasm_len, w, census_why)) return false;
+      uint32_t pos = 0, size = 0;
+      if (!wasm_input_lookup(w, "censusSiblings", pos, size) || size < 4) { census_why = "censusSiblings missing"; return false; }
+      if (!census_layout_build(c->L, size)) { census_why = "unsupported number of levels"; return false; }
+      c->L.n_wires = w.n_wires;
+      const uint32_t expect_pos[12] = {c->L.electionId, c->L.nullifier, c->L.voteHash, c->L.sikRoot, c->L.censusRoot,
+                                       c->L.voteWeight, c->L.availableWeight, c->L.address, c->L.password,
+                                       c->L.signature, c->L.censusSiblings, c->L.sikSiblings};
+      const uint32_t expect_size[12] = {2, 1, 2, 1, 1, 1, 1, 1, 1, 1, size, size};
+      for (int k = 0; k < 12; k++)
+        if (!wasm_input_lookup(w, INPUT_NAMES[k], c->in_pos[k], c->in_size[k]) || c->in_pos[k] != expect_pos[k] ||
+            c->in_size[k] != expect_size[k]) { census_why = std::string("input ") + INPUT_NAMES[k]; return false; }
+      if (w.n_inputs != c->L.n_inputs || w.witness_map.back() >= c->L.n_signals || w.witness_map[0] != 0) { census_why = "signal layout mismatch"; return false; }
+      if (z.n_public != 8) { census_why = "census circuit has 8 public signals; zkey says otherwise"; return false; }
+      return true;
+    };
+    if (!is_census()) { want_generic = true; memset(&c->L, 0, sizeof c->L); }
+    else {
     if (w.n_wires != z.n_vars) { set_error("zkey and wasm disagree on the number of wires"); return ZKB_INVALID_WITNESS_LENGTH; }
-    if (z.n_public != 8) { set_error("census circuit has 8 public signals; zkey says otherwise"); return ZKB_UNSUPPORTED_CIRCUIT; }
+    c->has_witness = true;
     // constants
     std::vector<uint32_t> cbuf;
     std::vector<int> forms;
@@ -771,6 +802,22 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
     CKR(cudaStreamSynchronize(st), "witness template");
     cudaFree(zstage);
     cudaFree(zin); cudaFree(zst); cudaFree(dforms);
+    }
+  }
+  if (want_generic) {
+    WitnessProgram prog;
+    if (!build_witness_program(wasm, wasm_len, prog, err)) {
+      set_error(err + (census_why.empty() ? "" : " (not recognised as census.circom either: " + census_why + ")"));
+      return ZKB_UNSUPPORTED_CIRCUIT;
+    }
+    if (prog.n_wires != z.n_vars) { set_error("zkey and wasm disagree on the number of wires"); return ZKB_INVALID_WITNESS_LENGTH; }
+    CKR(c->tape.upload(prog, st), "upload witness program");
+    c->generic = true;
+    c->has_witness = true;
+    c->gen_inputs = prog.inputs;
+    c->gen_first_signal = prog.first_input_signal;
+    c->L.n_inputs = prog.n_inputs;
+    c->L.n_wires = prog.n_wires;
   }
 
   // coefficient matrices (CSR by row)
@@ -917,6 +964,7 @@ static void destroy_circuit(Circuit *c) {
   cudaFree(c->consts); cudaFree(c->hc); cudaFree(c->tmpl); cudaFree(c->wmap); cudaFree(c->csr_buf); cudaFree(c->row_order);
   cudaFree(c->csr_val); cudaFree(c->fix1); cudaFree(c->fix2); cudaFree(c->d1tab); cudaFree(c->d2tab);
   cudaFree(c->tconst1); cudaFree(c->tconst2);
+  c->tape.free_all();
   if (c->root_is_ipc) cudaIpcCloseMemHandle(c->root_x);
   cudaFree(c->xbuf);
   cudaFree(c->tabA.tab); cudaFree(c->tabB1.tab); cudaFree(c->tabC.tab); cudaFree(c->tabH.tab); cudaFree(c->tabB2.tab);
@@ -1095,7 +1143,7 @@ int zkb_set_blinding(zkb_circuit *h, const uint8_t *r32, const uint8_t *s32) {
 int zkb_batch_set_inputs(zkb_circuit *h, int n, const void *inputs) {
   if (!h || !inputs || n <= 0) { set_error("batch_set_inputs: null handle / inputs or n <= 0"); return ZKB_ERROR; }
   Circuit *c = h->c;
-  if (!c->consts) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
+  if (!c->has_witness) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
   std::lock_guard<std::mutex> g(c->mu);
   CKR(cudaSetDevice(c->ctx->device), "set device");
   uint32_t chunk = default_chunk(c);
@@ -1377,7 +1425,7 @@ int zkb_fullprove_batch(zkb_circuit *h, int n, const char *const *inputs_json, c
                         size_t proof_stride, char *publics, size_t public_stride, int *status) {
   if (!h || (n > 0 && (!inputs_json || !inputs_len || !proofs || !publics || !status))) { set_error("null argument"); return ZKB_ERROR; }
   Circuit *c = h->c;
-  if (!c->consts) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
+  if (!c->has_witness) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
   if (n <= 0) return ZKB_OK;
   if (proof_stride < 1 || public_stride < 1) { set_error("zero output stride"); return ZKB_ERROR; }
   std::lock_guard<std::mutex> g(c->mu);
@@ -1421,7 +1469,7 @@ int zkb_fullprove(zkb_circuit *h, const char *inputs_json, size_t inputs_len, ch
 // .wtns (snarkjs/circom binary witness) for one inputs.json; *wtns_len in = capacity, out = size
 int zkb_witness(zkb_circuit *h, const char *inputs_json, size_t inputs_len, void *wtns_out, size_t *wtns_len) {
   Circuit *c = h->c;
-  if (!c->consts) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
+  if (!c->has_witness) { set_error("circuit was loaded without a wasm: no witness generator"); return ZKB_ERROR; }
   std::lock_guard<std::mutex> g(c->mu);
   CKR(cudaSetDevice(c->ctx->device), "set device");
   size_t need = 4 + 4 + 4 + 12 + (4 + 32 + 4) + 12 + (size_t)c->n_vars * 32;

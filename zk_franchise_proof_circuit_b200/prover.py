@@ -93,9 +93,10 @@ class Context:
 class Circuit:
     """A proving key + witness calculator loaded onto the GPU (zkb_load_circuit)."""
 
-    def __init__(self, ctx: Context, zkey: bytes, wasm: bytes = None, shard=None, dense=False):
+    def __init__(self, ctx: Context, zkey: bytes, wasm: bytes = None, shard=None, dense=False, generic=False):
         """shard = (rank, nranks): keep only this rank's point ranges of the key (zkb_load_circuit_shard).
-        dense = True: ZKB_LOAD_DENSE, the proof-independent-wire shortcut is off (measurement aid)."""
+        dense = True: ZKB_LOAD_DENSE, the proof-independent-wire shortcut is off (measurement aid).
+        generic = True: ZKB_LOAD_GENERIC_WITNESS, witness by the program extracted from the wasm (any circom circuit)."""
         self.ctx = ctx
         self.dense = dense
         self.h = _vp()
@@ -108,7 +109,7 @@ class Circuit:
         else:
             _native.check(_lib().zkb_load_circuit_ex(ctx.h, ctypes.addressof(zb), len(zkey),
                                                      ctypes.addressof(wb) if wasm else None, len(wasm) if wasm else 0,
-                                                     1 if dense else 0, ctypes.byref(self.h)))
+                                                     (1 if dense else 0) | (2 if generic else 0), ctypes.byref(self.h)))
         info = np.zeros(8, dtype=np.uint32)
         _lib().zkb_circuit_info(self.h, info.ctypes.data)
         self.n_vars, self.n_public, self.domain, self.n_inputs, self.n_levels1 = (int(x) for x in info[:5])
@@ -289,11 +290,11 @@ def _context(device=None):
     return _ctx[device]
 
 
-def load(zkey: bytes, wasm: bytes = None, device=None, dense=False) -> Circuit:
+def load(zkey: bytes, wasm: bytes = None, device=None, dense=False, generic=False) -> Circuit:
     """Cached zkb_load_circuit."""
-    key = (hashlib.sha256(zkey).digest(), hashlib.sha256(wasm).digest() if wasm else None, device, dense)
+    key = (hashlib.sha256(zkey).digest(), hashlib.sha256(wasm).digest() if wasm else None, device, dense, generic)
     if key not in _circuits:
-        _circuits[key] = Circuit(_context(device), zkey, wasm, dense=dense)
+        _circuits[key] = Circuit(_context(device), zkey, wasm, dense=dense, generic=generic)
     return _circuits[key]
 
 
