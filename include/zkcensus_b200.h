@@ -139,6 +139,11 @@ int zkb_verify_batch(const char *vkey_json, size_t vkey_len, int n, const char *
 /* The same check on binary results (the layout of zkb_batch_get_results): proofs256 = n x 256 B, publics = n x nPublic x 32 B. */
 int zkb_verify_batch_bin(const char *vkey_json, size_t vkey_len, int n, const void *publics, const void *proofs256, int *ok);
 
+/* `snarkjs zkey export verificationkey` (circuit/circuit-compiler.sh:128-134): the verification_key.json of a proving
+ * key, the exact text snarkjs writes (incl. vk_alphabeta_12 in ffjavascript's convention).  *out_len: capacity in,
+ * bytes written (or needed, with ZKB_SHORT_BUFFER) out.  Host arithmetic only (one pairing); needs no GPU. */
+int zkb_export_vkey(const void *zkey, size_t zkey_len, char *out, size_t *out_len);
+
 /* Batched Poseidon with the circuit's constants (arity 2..4): the hash function of the census and SIK trees
  * (arbo.HashFunctionPoseidon, internal/helpers.go:45-49; circomlibjs in ts_inputs/src/inputs.ts:16,33).
  * in: n x arity canonical 32-byte values, out: n x 32 bytes. */

@@ -158,3 +158,19 @@ def test_host_build_of_pairing_verifies_reference_fixture(tmp_path):
     pf2 = json.loads(json.dumps(pf))
     pf2["pi_c"] = pf["pi_a"]
     assert call(pub, pf2) == 0
+
+
+def test_export_vkey_matches_setup_vkeys(art_dir):
+    """zkb_export_vkey == `snarkjs zkey export verificationkey` (circuit/circuit-compiler.sh:128-134): byte-identical to
+    the verification keys the dev setup wrote for the census key and the chain key (whose vk_alphabeta_12 computation is
+    pinned against the REFERENCE's verification_key.json by test_vk_alphabeta_12_reproduced).  Host arithmetic: runs
+    without a GPU."""
+    from zk_franchise_proof_circuit_b200 import prover
+    for d in (art_dir, os.path.join(H.ROOT, "artifacts", "chain600")):
+        if not os.path.exists(os.path.join(d, "proving_key.zkey")):
+            continue
+        got = prover.export_vkey(open(os.path.join(d, "proving_key.zkey"), "rb").read())
+        assert got == open(os.path.join(d, "verification_key.json"), "rb").read()
+    from zk_franchise_proof_circuit_b200._native import NativeError
+    with pytest.raises(NativeError):
+        prover.export_vkey(b"zkey" + bytes(100))

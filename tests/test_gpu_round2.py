@@ -264,3 +264,26 @@ def test_non_circom_wasm_is_reported_not_crashed(files):
     trunc = files[1][:200000]
     with pytest.raises(NativeError):
         prover.Circuit(prover._context(None), files[0], trunc)
+
+
+def test_rlc_batch_verification(circuit, files):
+    """n >= 8 proofs are checked with one random-linear-combination pairing product; a batch with an
+    invalid proof falls back to per-proof checks and names exactly the bad ones."""
+    from zk_franchise_proof_circuit_b200 import prover
+    vs = H.voters(24)
+    packed = np.stack([prover.pack_inputs(v) for v in vs])
+    circuit.set_inputs(packed)
+    circuit.prove_resident()
+    proofs, pubs, status = circuit.get_results()
+    assert (status == 0).all()
+    assert list(prover.verify_batch_bin(files[2], pubs, proofs)) == [1] * 24
+    bad = proofs.copy()
+    bad[5, 64:128] = proofs[6, 64:128]                   # B.x of another proof: a valid curve point? no - x without its y
+    bad[17] = proofs[16]                                 # a valid proof of ANOTHER statement
+    pb = pubs.copy()
+    pb[20, 7, 0] ^= 1                                    # voteWeight changed
+    got = list(prover.verify_batch_bin(files[2], pb, bad))
+    want = [1] * 24
+    want[5] = want[17] = want[20] = 0
+    assert got == want
+    assert O.verify_many(H.dev_vkey(), pubs[:8].tobytes(), proofs[:8].tobytes(), 8).all()

@@ -350,6 +350,19 @@ def verify_batch_bin(vkey: bytes, publics: np.ndarray, proofs256: np.ndarray) ->
     return ok
 
 
+def export_vkey(zkey: bytes) -> bytes:
+    """`snarkjs zkey export verificationkey` (circuit/circuit-compiler.sh:128-134): verification_key.json of a proving
+    key, the exact text snarkjs writes (zkb_export_vkey; host arithmetic, no GPU needed)."""
+    L = _native.lib()
+    L.zkb_export_vkey.argtypes = [_vp, _sz, _vp, ctypes.POINTER(_sz)]
+    zb = (ctypes.c_char * len(zkey)).from_buffer_copy(zkey)
+    n = _sz(0)
+    L.zkb_export_vkey(ctypes.addressof(zb), len(zkey), None, ctypes.byref(n))
+    buf = ctypes.create_string_buffer(n.value)
+    _native.check(L.zkb_export_vkey(ctypes.addressof(zb), len(zkey), buf, ctypes.byref(n)))
+    return buf.raw[:n.value]
+
+
 # ---- snarkjs-shaped API -------------------------------------------------------------------------------
 
 class groth16:  # noqa: N801  (mirrors `import { groth16 } from "snarkjs"`)
