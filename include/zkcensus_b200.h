@@ -108,6 +108,13 @@ int zkb_load_circuit_shard(zkb_ctx *ctx, const void *zkey, size_t zkey_len, int 
 int zkb_shard_export(zkb_circuit *c, void *handle64);
 int zkb_shard_attach(zkb_circuit *c, const void *handle64);
 int zkb_shard_attach_local(zkb_circuit *c, zkb_circuit *root);
+/* Witness-slice exchange of a sharded key (optional; without it every rank uploads the whole .wtns): every rank exports
+ * the buffer that holds ITS slice of the witness (values [nVars r / G, nVars (r+1) / G)) and attaches the others'.
+ * Once all G - 1 peers are attached, zkb_prove_wtns on rank r checks and uploads only that slice and gathers the rest
+ * from the peers over NVLink (P2P loads through the IPC mappings, flag-synchronised). */
+int zkb_shard_export_witness(zkb_circuit *c, void *handle64);
+int zkb_shard_attach_witness(zkb_circuit *c, int peer_rank, const void *handle64);
+int zkb_shard_attach_witness_local(zkb_circuit *c, int peer_rank, zkb_circuit *peer);
 
 /* rapidsnark prover.h, same symbol and signature, so go-rapidsnark's cgo wrapper links unchanged
  * (go.mod:30 github.com/iden3/go-rapidsnark/prover v0.0.9).  Returns 0 / 1 / 2. */

@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_accumulate_g2pair(TablePtrs<F
     Fq2 pc = ldg_pod(reinterpret_cast<const Fq2 *>(tab + (x & 0x7fffffffu)) + (h ? 1 : 0));
     if (SMB) B = getB();
     const bool myzero = pc.is_zero();
-    const bool p_inf = myzero && __shfl_xor_sync(0xffffffffu, (int)myzero, 1);
+    const int other_zero = __shfl_xor_sync(0xffffffffu, (int)myzero, 1);   // (not inside the &&: every lane must shuffle)
+    const bool p_inf = myzero && other_zero != 0;
     const bool use = active && !p_inf;
     pc = Fq2::select(h && (x >> 31) != 0, pc.neg(), pc);
     // step 1

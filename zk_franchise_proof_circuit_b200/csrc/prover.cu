@@ -244,6 +244,41 @@ __global__ void k_shard_combine(ShardSlot *slots, int nranks, uint32_t epoch, XY
   }
 }
 
+// Witness of a sharded proof: rank r uploads only values [n r / G, n (r+1) / G) from the host, then every rank reads
+// the other ranks' slices out of their exchange buffers over NVLink (CUDA IPC mappings) - instead of G processes each
+// pushing the whole witness (134 MB at 2^22 constraints) through the host memory system at the same time.
+struct WitnessPeers { const Fr *slice[SHARD_MAX_RANKS]; const uint32_t *flag[SHARD_MAX_RANKS]; };
+__global__ void k_wt_set_flag(uint32_t *flag, uint32_t epoch) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+__global__ void k_wt_wait(WitnessPeers P, int nranks, uint32_t epoch, int *status) {
+  const int r = threadIdx.x;
+  if (r >= nranks) return;
+  const long long t0 = clock64();
+  uint32_t f;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(P.flag[r]) : "memory");
+    if (f != epoch && clock64() - t0 > 8000000000LL) { atomicMax(status, 7); return; }
+  } while (f != epoch);
+}
+// wtns[i] = slice of the rank that owns i (plain loads: the data was published with a system-scope release)
+__global__ void __launch_bounds__(256) k_wt_gather(WitnessPeers P, int nranks, uint32_t n, Fr *wtns) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int r = (int)(((uint64_t)i * nranks) / n);
+  while ((uint32_t)(((uint64_t)n * r) / nranks) > i) r--;
+  while ((uint32_t)(((uint64_t)n * (r + 1)) / nranks) <= i) r++;
+  const uint32_t lo = (uint32_t)(((uint64_t)n * r) / nranks);
+  const uint4 *src = reinterpret_cast<const uint4 *>(P.slice[r] + (i - lo));
+  uint4 a, b;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(src));
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(src + 1));
+  uint4 *dst = reinterpret_cast<uint4 *>(wtns + i);
+  dst[0] = a;
+  dst[1] = b;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host objects
 // ---------------------------------------------------------------------------------------------
@@ -364,6 +399,14 @@ struct Circuit {
   ShardSlot *root_x = nullptr;     // where this rank publishes
   bool root_is_ipc = false;
   uint32_t epoch = 0;
+  // witness slices of a sharded proof (see k_wt_gather): own slice buffer (+ flag word behind it), the peers' mappings
+  uint8_t *wt_buf = nullptr;
+  size_t wt_flag_off = 0;
+  uint8_t *h_wt = nullptr;         // pinned staging of the own slice
+  const uint8_t *wt_peer[SHARD_MAX_RANKS] = {};
+  bool wt_peer_ipc[SHARD_MAX_RANKS] = {};
+  int wt_attached = 0;
+  uint32_t wt_epoch = 0;
   MsmCfg cfgW, cfgH;              // window sizes: witness MSMs (sparse after the template difference), H MSM (dense)
   uint8_t *out = nullptr;          // device results
   uint8_t *h_out = nullptr;        // pinned
@@ -886,6 +929,14 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
       c->cntW = (uint32_t)((uint64_t)c->subW * (shard_rank + 1) / shard_n) - c->loW;
       c->loH = (uint32_t)((uint64_t)c->subH * shard_rank / shard_n);
       c->cntH = (uint32_t)((uint64_t)c->subH * (shard_rank + 1) / shard_n) - c->loH;
+      {
+        const size_t max_slice = ((size_t)z.n_vars + shard_n - 1) / shard_n + 1;
+        c->wt_flag_off = (max_slice * 32 + 255) / 256 * 256;
+        CKR(cudaMalloc(&c->wt_buf, c->wt_flag_off + 256), "alloc witness slice");
+        CKR(cudaMemsetAsync(c->wt_buf + c->wt_flag_off, 0, 256, st), "memset");
+        CKR(cudaMallocHost(&c->h_wt, max_slice * 32), "alloc pinned witness slice");
+        c->wt_peer[shard_rank] = c->wt_buf;
+      }
       CKR(cudaMalloc(&c->xbuf, SHARD_MAX_RANKS * sizeof(ShardSlot)), "alloc shard exchange");
       CKR(cudaMemsetAsync(c->xbuf, 0, SHARD_MAX_RANKS * sizeof(ShardSlot), st), "memset");
       c->root_x = c->xbuf;
@@ -966,6 +1017,10 @@ static void destroy_circuit(Circuit *c) {
   cudaFree(c->tconst1); cudaFree(c->tconst2);
   c->tape.free_all();
   if (c->root_is_ipc) cudaIpcCloseMemHandle(c->root_x);
+  for (int r = 0; r < SHARD_MAX_RANKS; r++)
+    if (c->wt_peer_ipc[r]) cudaIpcCloseMemHandle(const_cast<uint8_t *>(c->wt_peer[r]));
+  cudaFree(c->wt_buf);
+  if (c->h_wt) cudaFreeHost(c->h_wt);
   cudaFree(c->xbuf);
   cudaFree(c->tabA.tab); cudaFree(c->tabB1.tab); cudaFree(c->tabC.tab); cudaFree(c->tabH.tab); cudaFree(c->tabB2.tab);
   c->ntt.destroy();
@@ -1107,6 +1162,57 @@ int zkb_shard_attach_local(zkb_circuit *h, zkb_circuit *root) {
     cudaGetLastError();
   }
   c->root_x = r->xbuf;
+  return ZKB_OK;
+}
+
+// Witness-slice exchange of a sharded key: every rank exports its slice buffer and maps the others'.  Once all
+// nranks - 1 peers are attached, zkb_prove_wtns uploads only this rank's slice of the witness and gathers the rest
+// over NVLink; until then every rank uploads the whole witness.
+int zkb_shard_export_witness(zkb_circuit *h, void *handle64) {
+  if (!h || !handle64) { set_error("null argument"); return ZKB_ERROR; }
+  Circuit *c = h->c;
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  if (!c->wt_buf) { set_error("not a sharded key"); return ZKB_ERROR; }
+  cudaIpcMemHandle_t mh;
+  CKR(cudaIpcGetMemHandle(&mh, c->wt_buf), "ipc export");
+  memcpy(handle64, &mh, 64);
+  return ZKB_OK;
+}
+int zkb_shard_attach_witness(zkb_circuit *h, int peer_rank, const void *handle64) {
+  if (!h || !handle64) { set_error("null argument"); return ZKB_ERROR; }
+  Circuit *c = h->c;
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  if (!c->wt_buf || peer_rank < 0 || peer_rank >= c->shard_n || peer_rank == c->shard_rank || c->wt_peer[peer_rank]) {
+    set_error("bad peer rank for the witness exchange");
+    return ZKB_ERROR;
+  }
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, handle64, 64);
+  void *p = nullptr;
+  CKR(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess), "ipc open (peer witness slice)");
+  c->wt_peer[peer_rank] = (const uint8_t *)p;
+  c->wt_peer_ipc[peer_rank] = true;
+  c->wt_attached++;
+  return ZKB_OK;
+}
+int zkb_shard_attach_witness_local(zkb_circuit *h, int peer_rank, zkb_circuit *peer) {
+  if (!h || !peer) { set_error("null argument"); return ZKB_ERROR; }
+  Circuit *c = h->c, *q = peer->c;
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  if (!c->wt_buf || !q->wt_buf || peer_rank != q->shard_rank || peer_rank == c->shard_rank || c->wt_peer[peer_rank]) {
+    set_error("bad peer for the witness exchange");
+    return ZKB_ERROR;
+  }
+  if (c->ctx->device != q->ctx->device) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, c->ctx->device, q->ctx->device);
+    if (!can) { set_error("no peer access between the two GPUs"); return ZKB_ERROR; }
+    cudaError_t e = cudaDeviceEnablePeerAccess(q->ctx->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "enable peer access");
+    cudaGetLastError();
+  }
+  c->wt_peer[peer_rank] = q->wt_buf;
+  c->wt_attached++;
   return ZKB_OK;
 }
 
@@ -1562,27 +1668,61 @@ int zkb_prove_wtns_stages(zkb_circuit *h, const void *wtns, size_t wtns_size, ch
   if (!data) { set_error("wtns: no data section"); return ZKB_ERROR; }
   if (nw != c->n_vars) { set_error("wtns: witness length does not match the zkey"); return ZKB_INVALID_WITNESS_LENGTH; }
   if (data_sz < (uint64_t)nw * 32) { set_error("wtns: data section shorter than nVars x 32 bytes"); return ZKB_INVALID_WITNESS_LENGTH; }
-  for (uint32_t i = 0; i < nw; i++) {          // canonical values only: they feed Montgomery products and MSM digits
-    uint32_t top;
-    memcpy(&top, data + (size_t)i * 32 + 28, 4);
-    if (top < RMOD[7]) continue;
-    uint32_t v[8];
-    memcpy(v, data + (size_t)i * 32, 32);
-    bool lt = false;
-    for (int k = 7; k >= 0; k--) { if (v[k] != RMOD[k]) { lt = v[k] < RMOD[k]; break; } }
-    if (!lt) { set_error("wtns: value not in [0, r)"); return ZKB_ERROR; }
-  }
+  // canonical values only (they feed Montgomery products and MSM digits); a sharded key with its peers attached
+  // checks and uploads only its own slice, the rest arrives over NVLink
+  const bool slices = c->shard_n > 1 && c->wt_attached == c->shard_n - 1;
+  const uint32_t lo = slices ? (uint32_t)(((uint64_t)nw * c->shard_rank) / c->shard_n) : 0;
+  const uint32_t hi = slices ? (uint32_t)(((uint64_t)nw * (c->shard_rank + 1)) / c->shard_n) : nw;
+  std::atomic<int> bad_value{0};
+  const uint32_t piece = 1u << 15;
+  parallel_for((hi - lo + piece - 1) / piece, nw >= (1u << 18) ? host_threads() : 1, [&](uint32_t q) {
+    const uint32_t a = lo + q * piece, b = std::min(hi, a + piece);
+    for (uint32_t i = a; i < b; i++) {
+      uint32_t top;
+      memcpy(&top, data + (size_t)i * 32 + 28, 4);
+      if (top < RMOD[7]) continue;
+      uint32_t v[8];
+      memcpy(v, data + (size_t)i * 32, 32);
+      bool lt = false;
+      for (int k = 7; k >= 0; k--) { if (v[k] != RMOD[k]) { lt = v[k] < RMOD[k]; break; } }
+      if (!lt) bad_value.store(1);
+    }
+    if (slices) memcpy(c->h_wt + (size_t)(a - lo) * 32, data + (size_t)a * 32, (size_t)(b - a) * 32);   // pinned staging
+  });
+  if (bad_value.load()) { set_error("wtns: value not in [0, r)"); return ZKB_ERROR; }
   std::lock_guard<std::mutex> g(c->mu);
   CKR(cudaSetDevice(c->ctx->device), "set device");
   int rc = ensure_workspace(c, c->cap ? c->cap : 1, c->chunk ? c->chunk : default_chunk(c));
   if (rc) return rc;
-  CKR(cudaMemcpyAsync(c->wtns, data, (size_t)nw * 32, cudaMemcpyHostToDevice, c->ctx->stream), "h2d witness");
+  int *wt_status = reinterpret_cast<int *>(c->wt_buf + c->wt_flag_off + 64);   // set to 7 when a peer's slice never arrives
+  if (slices) {
+    cudaStream_t st = c->ctx->stream;
+    c->wt_epoch++;
+    CKR(cudaMemsetAsync(wt_status, 0, 4, st), "memset");
+    CKR(cudaMemcpyAsync(c->wt_buf, c->h_wt, (size_t)(hi - lo) * 32, cudaMemcpyHostToDevice, st), "h2d witness slice");
+    k_wt_set_flag<<<1, 1, 0, st>>>(reinterpret_cast<uint32_t *>(c->wt_buf + c->wt_flag_off), c->wt_epoch);
+    WitnessPeers P;
+    for (int r = 0; r < SHARD_MAX_RANKS; r++) {
+      P.slice[r] = reinterpret_cast<const Fr *>(c->wt_peer[r]);
+      P.flag[r] = c->wt_peer[r] ? reinterpret_cast<const uint32_t *>(c->wt_peer[r] + c->wt_flag_off) : nullptr;
+    }
+    k_wt_wait<<<1, 32, 0, st>>>(P, c->shard_n, c->wt_epoch, wt_status);
+    k_wt_gather<<<(nw + 255) / 256, 256, 0, st>>>(P, c->shard_n, nw, c->wtns);
+    g_launches += 3;
+    CKR(cudaGetLastError(), "witness slice exchange");
+  } else {
+    CKR(cudaMemcpyAsync(c->wtns, data, (size_t)nw * 32, cudaMemcpyHostToDevice, c->ctx->stream), "h2d witness");
+  }
   if (c->shard_n > 1) CKR(cudaMemsetAsync(c->status, 0, 4, c->ctx->stream), "memset status");
   if ((rc = prove_group(c, 1, false, stage_ms))) return rc;
   if (c->shard_n > 1) {
     int stt = 0;
     CKR(cudaMemcpy(&stt, c->status, 4, cudaMemcpyDeviceToHost), "d2h status");
     if (stt == 7) { set_error("sharded prove: timed out waiting for a peer's partial sums"); return ZKB_ERROR; }
+    if (slices) {
+      CKR(cudaMemcpy(&stt, wt_status, 4, cudaMemcpyDeviceToHost), "d2h status");
+      if (stt == 7) { set_error("sharded prove: timed out waiting for a peer's witness slice"); return ZKB_ERROR; }
+    }
     if (c->shard_rank != 0) {                            // only rank 0 assembles and returns the proof
       if (proof_size) *proof_size = 0;
       if (public_size) *public_size = 0;

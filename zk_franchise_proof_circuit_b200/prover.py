@@ -41,6 +41,9 @@ def _lib():
         L.zkb_shard_export.argtypes = [_vp, _vp]
         L.zkb_shard_attach.argtypes = [_vp, _vp]
         L.zkb_shard_attach_local.argtypes = [_vp, _vp]
+        L.zkb_shard_export_witness.argtypes = [_vp, _vp]
+        L.zkb_shard_attach_witness.argtypes = [_vp, _i32, _vp]
+        L.zkb_shard_attach_witness_local.argtypes = [_vp, _i32, _vp]
         L.zkb_circuit_destroy.argtypes = [_vp]
         L.zkb_circuit_info.argtypes = [_vp, _vp]
         L.zkb_set_blinding.argtypes = [_vp, _vp, _vp]
@@ -124,6 +127,17 @@ class Circuit:
 
     def shard_attach_local(self, root: "Circuit"):
         _native.check(_lib().zkb_shard_attach_local(self.h, root.h))
+
+    def shard_export_witness(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        _native.check(_lib().zkb_shard_export_witness(self.h, buf))
+        return buf.raw
+
+    def shard_attach_witness(self, peer_rank: int, handle: bytes):
+        _native.check(_lib().zkb_shard_attach_witness(self.h, peer_rank, ctypes.create_string_buffer(handle, 64)))
+
+    def shard_attach_witness_local(self, peer_rank: int, peer: "Circuit"):
+        _native.check(_lib().zkb_shard_attach_witness_local(self.h, peer_rank, peer.h))
 
     def close(self):
         if self.h:
