@@ -332,6 +332,10 @@ def multi_gpu_selfcheck(rank, world, local_rank, dist, torch):
         h = bcast(c.shard_export() if rank == 0 else None)
         if rank != 0:
             c.shard_attach(h)
+        whs = gather(c.shard_export_witness())               # witness slices: each rank uploads 1 / N of the .wtns
+        for g in range(world):
+            if g != rank:
+                c.shard_attach_witness(g, whs[g])
         c.set_blinding(kat["r"], kat["s"])
         barrier()
         c.prove_wtns(wtns)                                   # warm-up: allocates the workspace
@@ -597,6 +601,8 @@ def run_ours(args, rank, world, local_rank):
             pts.append({"tree_depth": depth, "proofs_per_s": rate, "g1_madds_per_proof": w["g1_madds_per_proof"],
                         "g2_madds_per_proof": w["g2_madds_per_proof"],
                         "witness_digit_entries_per_proof": w["witness_digit_entries_per_proof"]})
+        c.close()                                   # the dense circuit needs the HBM the default one's workspace holds
+        prover._circuits.clear()
         cd = prover.load(zkey, wasm, device=local_rank, dense=True)
         rate_dense = timed_resident(cd, packed[:64], nd, 1, stream, torch)
         wd = cd.work_counters()

@@ -156,6 +156,13 @@ int zkb_export_vkey(const void *zkey, size_t zkey_len, char *out, size_t *out_le
  * in: n x arity canonical 32-byte values, out: n x 32 bytes. */
 int zkb_poseidon_hash(zkb_circuit *c, int arity, int n, const void *in, void *out);
 
+/* Poseidon sparse Merkle tree of a census (arbo semantics of internal/helpers.go:36-85 GenTree /
+ * GenProof): n distinct 32-byte little-endian keys with their values -> root and, per key, its nLevels + 1 siblings
+ * (zero padded: what MockInputs puts into censusSiblings / sikSiblings, internal/inputs.go:44-72).  The trie is laid
+ * out on the host (C++), all hashing runs on the GPU (one batched launch per tree level).  siblings may be NULL. */
+int zkb_census_tree(zkb_circuit *c, int n_keys, const void *keys32, const void *values32, int n_levels, void *root32,
+                    void *siblings);
+
 /* --- resident-input batch path (inputs already in HBM; what bench.py times as `value`) -------------- */
 
 /* inputs: n x nInputs canonical 32-byte little-endian values in the circuit's main-signal order

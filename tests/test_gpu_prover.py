@@ -279,12 +279,37 @@ def test_generic_circuit_chain_bit_exact(tmp_path, links):
     c.close()
 
 
-def _sharded_proof(zkey, wtns, nranks, devices):
+def _sharded_proof(zkey, wtns, nranks, devices, slices=False):
     from zk_franchise_proof_circuit_b200 import prover
     cs = [prover.load_shard(zkey, r, nranks, device=devices[r % len(devices)]) for r in range(nranks)]
     for c in cs[1:]:
         c.shard_attach_local(cs[0])
     cs[0].set_blinding(H.R_FIXED, H.S_FIXED)
+    if slices:
+        # witness-slice exchange: the ranks wait for each other's slices on the device, so each rank needs its own
+        # host thread (as in a multi-process run); ctypes releases the GIL during the call
+        import threading
+        for a in cs:
+            for b in cs:
+                if a is not b:
+                    a.shard_attach_witness_local(b.shard[0], b)
+        outs = []
+        for _ in range(2):                 # two proofs: two epochs
+            res = [None] * nranks
+
+            def work(r):
+                res[r] = cs[r].prove_wtns(wtns)
+            ts = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            assert all(res[r] == (b"", b"") for r in range(1, nranks))
+            outs.append(res[0])
+        assert outs[0] == outs[1]
+        for c in cs:
+            c.close()
+        return outs[0]
     for c in cs[1:]:                       # single thread: the peers publish first, then rank 0 combines
         assert c.prove_wtns(wtns) == (b"", b"")
     pj, sj = cs[0].prove_wtns(wtns)
@@ -310,8 +335,22 @@ def test_sharded_key_matches_oracle(tmp_path):
         pj, sj = _sharded_proof(zkey, wtns, nranks, [0])
         assert O.proof_bin(json.loads(pj)) == exp
         prover.verify(vkey, sj, pj)
+    # more ranks than 2^17-point ranges: the key is cut into finer ranges (8 ranks -> 2^15 points each)
+    pj, sj = _sharded_proof(zkey, wtns, 8, [0], slices=True)
+    assert O.proof_bin(json.loads(pj)) == exp
     with pytest.raises(Exception):
-        prover.load_shard(zkey, 0, 8)       # 3 witness ranges cannot feed 8 ranks
+        prover.load_shard(zkey, 0, 17)      # more than SHARD_MAX_RANKS
+
+
+def test_sharded_key_witness_slices(tmp_path):
+    """Every rank uploads only its slice of the .wtns and gathers the rest from the peers' buffers (here: contexts of
+    one GPU, one host thread per rank as in a multi-process run): same proof as the CPU oracle."""
+    n_wires, _, _ = O.chain_artifacts(600, 7, str(tmp_path), check=False)
+    zkey = open(tmp_path / "proving_key.zkey", "rb").read()
+    wtns = open(tmp_path / "witness.wtns", "rb").read()
+    exp = O.ZKeyRef(zkey).prove(H.wtns_payload(wtns, n_wires), H.R_FIXED, H.S_FIXED)
+    pj, sj = _sharded_proof(zkey, wtns, 3, [0], slices=True)
+    assert O.proof_bin(json.loads(pj)) == exp
 
 
 def test_sharded_key_two_gpus(tmp_path):
@@ -323,6 +362,8 @@ def test_sharded_key_two_gpus(tmp_path):
     wtns = open(tmp_path / "witness.wtns", "rb").read()
     exp = O.ZKeyRef(zkey).prove(H.wtns_payload(wtns, n_wires), H.R_FIXED, H.S_FIXED)
     pj, sj = _sharded_proof(zkey, wtns, 2, [0, 1])
+    assert O.proof_bin(json.loads(pj)) == exp
+    pj, sj = _sharded_proof(zkey, wtns, 2, [0, 1], slices=True)      # witness slices over NVLink
     assert O.proof_bin(json.loads(pj)) == exp
 
 

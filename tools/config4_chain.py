@@ -58,6 +58,11 @@ def main():
         dist.broadcast_object_list(box, src=0)
         if rank != 0:
             c.shard_attach(box[0])
+        hs = [None] * world
+        dist.all_gather_object(hs, c.shard_export_witness())   # witness slices: each rank uploads 1 / N of the .wtns
+        for g in range(world):
+            if g != rank:
+                c.shard_attach_witness(g, hs[g])
     else:
         c = prover.load(zkey, None, device=local)
     t_load = time.perf_counter() - t0

@@ -31,7 +31,9 @@ class _Node:
 
 
 class SparseMerkleTree:
-    """arbo-style tree over {key: value}; all hashing goes through `hasher(rows) -> ints` in per-depth batches."""
+    """arbo-style tree over {key: value}; all hashing goes through `hasher(rows) -> ints` in per-depth batches.
+    Python statement of the tree semantics, kept as the cross-check of the library's builder (Circuit.census_tree,
+    zkb_census_tree), which gen_census uses."""
 
     def __init__(self, hasher, leaves: dict):
         self.leaves = leaves
@@ -98,8 +100,17 @@ def gen_census(circuit, n_voters, seed=0xC0FFEE, n_levels=160, available_weight=
         sigs.append(int.from_bytes(sig, "big") % R_MOD)
     siks = H([(a, password, s) for a, s in zip(addrs, sigs)])
     nulls = H([(s, password, election[0], election[1]) for s in sigs])
-    census = SparseMerkleTree(H, {a: available_weight for a in addrs})
-    siktree = SparseMerkleTree(H, dict(zip(addrs, siks)))
+    # both trees by the library's builder (zkb_census_tree: trie layout in C++, hashing on the GPU)
+    census_root, census_sibs = circuit.census_tree({a: available_weight for a in addrs}, n_levels)
+    sik_root, sik_sibs = circuit.census_tree(dict(zip(addrs, siks)), n_levels)
+
+    class _T:
+        def __init__(self, root, sibs):
+            self.root, self._s = root, sibs
+
+        def siblings(self, key):
+            return self._s[key]
+    census, siktree = _T(census_root, census_sibs), _T(sik_root, sik_sibs)
     out = []
     pad = lambda s: [str(x) for x in s] + ["0"] * (n_levels + 1 - len(s))
     for a, s, nul in zip(addrs, sigs, nulls):

@@ -14,6 +14,7 @@
 #include "ec_coop.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace zkb {
 
@@ -606,7 +607,7 @@ __device__ __forceinline__ Fq pair_divisor(const PairSrc &s, int &kind) {
 // thread = `group` consecutive outputs of level l + 1 of batch item blockIdx.y
 template <bool FIRST>
 __global__ void __launch_bounds__(128) k_affine_level(const Affine<Fq> *tab, size_t tab_batch_stride, uint32_t tab_mod,
-                                                      const uint32_t *__restrict__ entries, size_t ent_stride,
+                                                      uint32_t item0, const uint32_t *__restrict__ entries, size_t ent_stride,
                                                       const Affine<Fq> *pin, size_t pin_stride,
                                                       const uint32_t *__restrict__ off_in_all,
                                                       const uint32_t *__restrict__ off_out_all, Affine<Fq> *pout_all,
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(128) k_affine_level(const Affine<Fq> *tab, siz
   const uint32_t o0 = (blockIdx.x * 128u + threadIdx.x) * group;
   if (o0 >= total) return;
   const uint32_t cnt = min(group, total - o0);
-  const Affine<Fq> *tb = FIRST ? tab + (size_t)(b % tab_mod) * tab_batch_stride : nullptr;
+  const Affine<Fq> *tb = FIRST ? tab + (size_t)((item0 + b) % tab_mod) * tab_batch_stride : nullptr;
   const uint32_t *ent = FIRST ? entries + (size_t)b * ent_stride : nullptr;
   const Affine<Fq> *pi = FIRST ? nullptr : pin + (size_t)b * pin_stride;
   Affine<Fq> *pout = pout_all + (size_t)b * pout_stride;
@@ -764,68 +765,83 @@ cudaError_t MsmAffineWs::alloc(uint32_t n_entries, uint32_t batch_, MsmCfg cfg) 
   CK(cudaMalloc(&pb, (size_t)batch * cap_b * sizeof(Affine<Fq>)));
   CK(cudaMalloc(&park, (size_t)batch * cap_a * sizeof(Fq)));
   CK(cudaMalloc(&lvl_off, (size_t)MAX_LEVELS * batch * (buckets + 1) * 4));
-  CK(cudaMalloc(&d_adds, 16));
   return cudaSuccess;
 }
 void MsmAffineWs::free_all() {
-  cudaFree(pa); cudaFree(pb); cudaFree(park); cudaFree(lvl_off); cudaFree(d_adds);
-  pa = pb = nullptr; park = nullptr; lvl_off = nullptr; d_adds = nullptr;
+  cudaFree(pa); cudaFree(pb); cudaFree(park); cudaFree(lvl_off);
+  pa = pb = nullptr; park = nullptr; lvl_off = nullptr;
 }
-int msm_affine_launches(const MsmAffineWs &ws) { return 1 + ws.levels + 1; }
+int msm_affine_launches(const MsmAffineWs &ws, uint32_t nbatch) {
+  const uint32_t subs = ws.batch ? (nbatch + ws.batch - 1) / ws.batch : 1;
+  return (int)subs * (1 + ws.levels + 1);
+}
 
 cudaError_t msm_accumulate_affine(const MsmSort &sort, const MsmTable<Fq> &table, uint32_t nbatch, MsmWork<Fq> &work,
                                   uint32_t slot0, MsmAffineWs &ws, cudaStream_t st, size_t tab_batch_stride,
                                   uint32_t tab_mod) {
   if (tab_mod == 0) tab_mod = nbatch;
-  if (nbatch > ws.batch || slot0 + nbatch > work.slots || ws.buckets != sort.cfg.buckets) return cudaErrorInvalidValue;
+  if (!ws.batch || slot0 + nbatch > work.slots || ws.buckets != sort.cfg.buckets) return cudaErrorInvalidValue;
   if (table.n != sort.n || table.cfg.c != sort.cfg.c || work.cfg.c != sort.cfg.c) return cudaErrorInvalidValue;
   const uint32_t nb = sort.cfg.buckets;
   const size_t ent_stride = (size_t)sort.n * sort.cfg.windows, lstride = (size_t)ws.batch * (nb + 1);
-  k_affine_scans<<<nbatch, 1024, 0, st>>>(sort.offsets, ws.lvl_off, nb, ws.batch, ws.levels);
-  size_t cap_in = ent_stride;
-  for (int l = 0; l < ws.levels; l++) {
-    const uint32_t *off_in = l ? ws.lvl_off + (size_t)(l - 1) * lstride : sort.offsets;
-    const uint32_t *off_out = ws.lvl_off + (size_t)l * lstride;
-    const Affine<Fq> *pin = (l & 1) ? ws.pa : ws.pb;
-    Affine<Fq> *pout = (l & 1) ? ws.pb : ws.pa;
-    const size_t pin_stride = (l & 1) ? ws.cap_a : ws.cap_b, pout_stride = (l & 1) ? ws.cap_b : ws.cap_a;
-    const size_t cap_out = (cap_in + nb) / 2 + 1;           // upper bound of this level's outputs per item
-    const uint32_t g = ws.group[l];
-    dim3 grid((unsigned)((cap_out + (size_t)g * 128 - 1) / ((size_t)g * 128)), nbatch);
-    if (l == 0)
-      k_affine_level<true><<<grid, 128, 0, st>>>(table.tab, tab_batch_stride, tab_mod, sort.entries, ent_stride, nullptr, 0,
-                                                  off_in, off_out, pout, pout_stride, ws.park, ws.cap_a, nb, g);
-    else
-      k_affine_level<false><<<grid, 128, 0, st>>>(nullptr, 0, 1, nullptr, 0, pin, pin_stride, off_in, off_out, pout,
-                                                   pout_stride, ws.park, ws.cap_a, nb, g);
-    cap_in = cap_out;
+  // the workspace holds ws.batch items: a larger launch runs as consecutive sub-batches on the same stream
+  for (uint32_t b0 = 0; b0 < nbatch; b0 += ws.batch) {
+    const uint32_t cnt = nbatch - b0 < ws.batch ? nbatch - b0 : ws.batch;
+    const uint32_t *offs = sort.offsets + (size_t)b0 * (nb + 1);
+    k_affine_scans<<<cnt, 1024, 0, st>>>(offs, ws.lvl_off, nb, ws.batch, ws.levels);
+    size_t cap_in = ent_stride;
+    for (int l = 0; l < ws.levels; l++) {
+      const uint32_t *off_in = l ? ws.lvl_off + (size_t)(l - 1) * lstride : offs;
+      const size_t off_in_stride = nb + 1;
+      (void)off_in_stride;
+      const uint32_t *off_out = ws.lvl_off + (size_t)l * lstride;
+      const Affine<Fq> *pin = (l & 1) ? ws.pa : ws.pb;
+      Affine<Fq> *pout = (l & 1) ? ws.pb : ws.pa;
+      const size_t pin_stride = (l & 1) ? ws.cap_a : ws.cap_b, pout_stride = (l & 1) ? ws.cap_b : ws.cap_a;
+      const size_t cap_out = (cap_in + nb) / 2 + 1;           // upper bound of this level's outputs per item
+      const uint32_t g = ws.group[l];
+      dim3 grid((unsigned)((cap_out + (size_t)g * 128 - 1) / ((size_t)g * 128)), cnt);
+      if (l == 0)
+        k_affine_level<true><<<grid, 128, 0, st>>>(table.tab, tab_batch_stride, tab_mod, b0, sort.entries + (size_t)b0 * ent_stride,
+                                                    ent_stride, nullptr, 0, off_in, off_out, pout, pout_stride,
+                                                    reinterpret_cast<Fq *>(ws.pb), ws.cap_b * 2, nb, g);
+      else
+        k_affine_level<false><<<grid, 128, 0, st>>>(nullptr, 0, 1, 0, nullptr, 0, pin, pin_stride, off_in, off_out, pout,
+                                                     pout_stride, ws.park, ws.cap_b, nb, g);
+      cap_in = cap_out;
+    }
+    const int last = ws.levels - 1;
+    const Affine<Fq> *pts = (last & 1) ? ws.pb : ws.pa;
+    const size_t pts_stride = (last & 1) ? ws.cap_b : ws.cap_a;
+    k_accumulate_pts<128, 4><<<dim3(nb / 128, cnt), 128, 0, st>>>(pts, pts_stride, ws.lvl_off + (size_t)last * lstride,
+                                                                 sort.order + (size_t)b0 * nb, nb,
+                                                                 work.buckets + ((size_t)slot0 + b0) * nb);
   }
-  const int last = ws.levels - 1;
-  const Affine<Fq> *pts = (last & 1) ? ws.pb : ws.pa;
-  const size_t pts_stride = (last & 1) ? ws.cap_b : ws.cap_a;
-  k_accumulate_pts<128, 4><<<dim3(nb / 128, nbatch), 128, 0, st>>>(pts, pts_stride, ws.lvl_off + (size_t)last * lstride,
-                                                                  sort.order, nb, work.buckets + (size_t)slot0 * nb);
   return cudaGetLastError();
 }
 
-// executed work of the pair tree over the current sort: affine additions = sum over levels and buckets of
-// floor(len_l / 2); tail mixed additions = sum over buckets of (len_levels - 1)+
-__global__ void k_affine_counts(const uint32_t *offsets, uint32_t nbuckets, int levels, unsigned long long *out) {
-  const uint32_t bucket = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  const uint32_t *off = offsets + (size_t)b * (nbuckets + 1);
-  uint32_t len = off[bucket + 1] - off[bucket];
-  unsigned long long adds = 0;
-  for (int l = 0; l < levels; l++) { adds += len >> 1; len = (len + 1) >> 1; }
-  atomicAdd(out, adds);
-  if (len > 1) atomicAdd(out + 1, (unsigned long long)(len - 1));
-}
-cudaError_t msm_affine_counts(const MsmSort &sort, const MsmAffineWs &ws, uint32_t nbatch, unsigned long long *out2,
+// executed work of the pair tree over the current sort (measurement aid, host arithmetic over the downloaded bucket
+// offsets): out[0] = affine additions = sum over levels and buckets of floor(len_l / 2); out[1] = mixed additions of the
+// XYZZ tail = sum over buckets of (len_levels - 1)+; out[2] = field inversions = threads of the level kernels
+cudaError_t msm_affine_counts(const MsmSort &sort, const MsmAffineWs &ws, uint32_t nbatch, unsigned long long *out3,
                               cudaStream_t st) {
-  CK(cudaMemsetAsync(ws.d_adds, 0, 16, st));
-  k_affine_counts<<<dim3(sort.cfg.buckets / 128, nbatch), 128, 0, st>>>(sort.offsets, sort.cfg.buckets, ws.levels, ws.d_adds);
-  CK(cudaMemcpyAsync(out2, ws.d_adds, 16, cudaMemcpyDeviceToHost, st));
+  const uint32_t nb = sort.cfg.buckets;
+  std::vector<uint32_t> off((size_t)nbatch * (nb + 1));
+  CK(cudaMemcpyAsync(off.data(), sort.offsets, off.size() * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  return cudaGetLastError();
+  unsigned long long adds = 0, tail = 0, inv = 0;
+  for (uint32_t b = 0; b < nbatch; b++) {
+    const uint32_t *o = off.data() + (size_t)b * (nb + 1);
+    unsigned long long total[MsmAffineWs::MAX_LEVELS] = {};
+    for (uint32_t k = 0; k < nb; k++) {
+      uint32_t len = o[k + 1] - o[k];
+      for (int l = 0; l < ws.levels; l++) { adds += len >> 1; len = (len + 1) >> 1; total[l] += len; }
+      if (len > 1) tail += len - 1;
+    }
+    for (int l = 0; l < ws.levels; l++) inv += (total[l] + ws.group[l] - 1) / ws.group[l];
+  }
+  out3[0] = adds; out3[1] = tail; out3[2] = inv;
+  return cudaSuccess;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -69,14 +69,13 @@ struct MsmWork {
 // summed by the XYZZ kernel.  pa / pb ping-pong the level outputs.
 struct MsmAffineWs {
   static constexpr int MAX_LEVELS = 4;
-  uint32_t batch = 0, buckets = 0;
+  uint32_t batch = 0, buckets = 0;   // batch: items the workspace holds at once (larger launches run in sub-batches)
   size_t cap_a = 0, cap_b = 0;       // points per batch item in pa (levels 1, 3) and pb (levels 2, 4)
   int levels = 3;
   uint32_t group[MAX_LEVELS] = {512, 512, 512, 512};
   Affine<Fq> *pa = nullptr, *pb = nullptr;
-  Fq *park = nullptr;                // [batch][cap_a] parked prefix products
+  Fq *park = nullptr;                // [batch][cap_b] parked prefix products of levels >= 1 (level 0 parks in pb)
   uint32_t *lvl_off = nullptr;       // [MAX_LEVELS][batch][buckets + 1] exclusive scans of the per-level list lengths
-  unsigned long long *d_adds = nullptr;   // executed affine additions of the last run (measurement aid)
   cudaError_t alloc(uint32_t n_entries, uint32_t batch, MsmCfg cfg);
   void free_all();
 };
@@ -84,9 +83,10 @@ struct MsmAffineWs {
 cudaError_t msm_accumulate_affine(const MsmSort &sort, const MsmTable<Fq> &table, uint32_t nbatch, MsmWork<Fq> &work,
                                   uint32_t slot0, MsmAffineWs &ws, cudaStream_t st, size_t tab_batch_stride = 0,
                                   uint32_t tab_mod = 0);
-int msm_affine_launches(const MsmAffineWs &ws);
-// executed work of the last msm_accumulate_affine run: out[0] = affine additions, out[1] = XYZZ mixed additions of the tail
-cudaError_t msm_affine_counts(const MsmSort &sort, const MsmAffineWs &ws, uint32_t nbatch, unsigned long long *out2,
+int msm_affine_launches(const MsmAffineWs &ws, uint32_t nbatch);
+// executed work of the pair tree over `sort`: out[0] = affine additions, out[1] = XYZZ mixed additions of the tail,
+// out[2] = field inversions
+cudaError_t msm_affine_counts(const MsmSort &sort, const MsmAffineWs &ws, uint32_t nbatch, unsigned long long *out3,
                               cudaStream_t st);
 
 // build the window table from n affine bases (Montgomery form, zkey layout; (0,0) = infinity).  subs > 1: `bases`

@@ -437,7 +437,7 @@ static bool random_fr(OsRandom &g, uint32_t out[8]) {
 }
 
 // the pair tree pays off when a launch has enough lists to fill the GPU; a single proof keeps the XYZZ kernel
-static constexpr uint32_t AFFINE_MIN_ITEMS = 16;
+static constexpr uint32_t AFFINE_MIN_ITEMS = 16, AFFINE_BATCH = 64;
 
 static uint32_t env_u32(const char *name, uint32_t dflt) {
   const char *v = getenv(name);
@@ -473,7 +473,7 @@ static int ensure_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
   if (c->cap >= cap && c->chunk >= chunk) return ZKB_OK;
   free_workspace(c);
   int rc = alloc_workspace(c, cap, chunk);
-  if (rc) { free_workspace(c); return rc; }
+  if (rc) { free_workspace(c); cudaGetLastError(); return rc; }   // (clears the allocation error: it is reported through rc)
   c->cap = cap;
   c->chunk = chunk;
   return ZKB_OK;
@@ -515,8 +515,7 @@ static int alloc_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
     CKR(cudaMalloc(&ln.fin_scratch, (size_t)chunk * 30 * sizeof(XYZZ<Fq>)), "alloc finalize scratch");
     CKR(ln.sortW.alloc(c->nsubW, chunk * c->subW, c->cfgW), "alloc sortW");
     CKR(ln.sortH.alloc(c->nsubH, chunk * c->subH, c->cfgH), "alloc sortH");
-    if (c->affine && chunk * c->subH >= AFFINE_MIN_ITEMS)
-      CKR(ln.affH.alloc(c->nsubH * (uint32_t)c->cfgH.windows, chunk * c->subH, c->cfgH), "alloc H pair tree");
+    // (the pair tree's workspace is allocated on first use, see run_prove_chunk)
     CKR(ln.work1.alloc(chunk * c->subW * 3, c->cfgW), "alloc msm work g1");
     CKR(ln.workH.alloc(chunk * c->subH, c->cfgH), "alloc msm work g1 (H)");
     CKR(ln.work2.alloc(chunk * c->subW, c->cfgW), "alloc msm work g2");
@@ -544,7 +543,8 @@ static int run_witness(Circuit *c, Lane &ln, uint32_t first, uint32_t n, cudaStr
   k_witness_gather<<<dim3((c->n_vars + 255) / 256, n), 256, 0, st>>>(ln.stage, c->L.n_signals, c->wmap, c->tmpl,
                                                                      c->wtns + (size_t)first * c->n_vars, c->n_vars);
   g_launches += 2;
-  return cudaGetLastError() == cudaSuccess ? ZKB_OK : cuda_fail(cudaGetLastError(), "witness launch");
+  const cudaError_t le = cudaGetLastError();
+  return le == cudaSuccess ? ZKB_OK : cuda_fail(le, "witness launch");
 }
 
 // witness (optional) + Groth16 for proofs [first, first + m), m <= chunk, on lane ln
@@ -565,9 +565,16 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
   XYZZ<Fq2> *out2 = splitW ? ln.g2raw : ln.g2out;
   dim3 g1((c->domain + 127) / 128, m);
   dim3 g2((c->domain + 255) / 256, m);
-  const bool affineH = ln.affH.pa != nullptr && m * sH >= AFFINE_MIN_ITEMS;
+  const bool affineH = c->affine && m * sH >= AFFINE_MIN_ITEMS;
+  if (affineH && !ln.affH.pa) {
+    // first batch-shaped chunk on this lane: the pair tree's workspace, AFFINE_BATCH items at a time (7.6 GB at 2^17
+    // points per item; a chunk of 128 proofs runs as two sub-batches)
+    const uint32_t items = c->chunk * c->subH < AFFINE_BATCH ? c->chunk * c->subH : AFFINE_BATCH;
+    cudaError_t e = ln.affH.alloc(c->nsubH * (uint32_t)c->cfgH.windows, items, c->cfgH);
+    if (e != cudaSuccess) { ln.affH.free_all(); cudaGetLastError(); return cuda_fail(e, "alloc H pair tree"); }
+  }
   c->last_affine = affineH;
-  if (affineH) g_launches += msm_affine_launches(ln.affH) - 2;   // instead of the two XYZZ accumulate kernels of the H MSM
+  if (affineH) g_launches += msm_affine_launches(ln.affH, m * sH) - 2;   // instead of the two XYZZ accumulate kernels of the H MSM
   static const uint32_t fork_max = env_u32("ZKB_FORK_MAX", 32);
   if (!ev && m <= fork_max) {
     // Latency shape: after the witness, three independent pipelines.  st: A/B/C vectors -> coset transforms -> h ->
@@ -1321,17 +1328,11 @@ int zkb_work_counters(zkb_circuit *h, uint64_t *out) {
   CKR(msm_count_madds<Fq>(ln.sortW, c->tabA, m, &t[0], st), "count");
   CKR(msm_count_madds<Fq>(ln.sortW, c->tabB1, m, &t[1], st), "count");
   CKR(msm_count_madds<Fq>(ln.sortW, c->tabC, m, &t[2], st), "count");
-  unsigned long long aff[2] = {0, 0}, inversions = 0;
+  unsigned long long aff[3] = {0, 0, 0}, inversions = 0;
   if (c->last_affine) {
     CKR(msm_affine_counts(ln.sortH, ln.affH, m, aff, st), "count");
     t[3] = aff[1];
-    const uint32_t nb = c->cfgH.buckets;
-    for (int l = 0; l < ln.affH.levels; l++)
-      for (uint32_t b = 0; b < m; b++) {
-        uint32_t tot;
-        CKR(cudaMemcpy(&tot, ln.affH.lvl_off + ((size_t)l * ln.affH.batch + b) * (nb + 1) + nb, 4, cudaMemcpyDeviceToHost), "d2h");
-        inversions += (tot + ln.affH.group[l] - 1) / ln.affH.group[l];
-      }
+    inversions = aff[2];
   } else {
     CKR(msm_count_madds<Fq>(ln.sortH, c->tabH, m, &t[3], st), "count");
   }
@@ -1412,6 +1413,130 @@ int zkb_poseidon_hash(zkb_circuit *h, int arity, int n, const void *in, void *ou
 }
 
 }  // extern "C"
+
+// ---- census / SIK tree builder ----------------------------------------------------------------
+// arbo semantics (internal/helpers.go:36-85, GenTree + GenProof): the path of a key is its bits LSB first; an empty
+// subtree hashes to 0, a subtree with one key is the leaf H(key, value, 1), any other node is H(left, right); the
+// siblings of a key are the other branch at every depth until the key is alone.  The structure (a trie over the
+// bit-reversed keys) is laid out on the host in one sort + one pass; every hash runs on the GPU, one batched Poseidon
+// launch for all leaves and one per tree level, deepest first.
+static int poseidon_device(Circuit *c, int arity, uint32_t n, const Fr *din, Fr *dout, cudaStream_t st) {
+  const unsigned grid = (n + 63) / 64;
+  if (arity == 2) k_poseidon_batch<3><<<grid, 64, 0, st>>>(c->L, c->consts, din, dout, n);
+  else if (arity == 3) k_poseidon_batch<4><<<grid, 64, 0, st>>>(c->L, c->consts, din, dout, n);
+  else k_poseidon_batch<5><<<grid, 64, 0, st>>>(c->L, c->consts, din, dout, n);
+  const cudaError_t le = cudaGetLastError();
+  return le == cudaSuccess ? ZKB_OK : cuda_fail(le, "poseidon launch");
+}
+
+extern "C" int zkb_census_tree(zkb_circuit *h, int n_keys, const void *keys32, const void *values32, int n_levels,
+                               void *root32, void *siblings) {
+  if (!h || n_keys <= 0 || !keys32 || !values32 || !root32 || n_levels < 1 || n_levels > 255) { set_error("census_tree: bad argument"); return ZKB_ERROR; }
+  Circuit *c = h->c;
+  if (!c->consts) { set_error("circuit was loaded without the census wasm: no Poseidon constants"); return ZKB_ERROR; }
+  const uint32_t n = (uint32_t)n_keys;
+  const uint8_t *K = (const uint8_t *)keys32, *V = (const uint8_t *)values32;
+  auto bit = [&](uint32_t i, int d) -> int { return (K[(size_t)i * 32 + (d >> 3)] >> (d & 7)) & 1; };
+  // order the keys by their LSB-first bit string
+  std::vector<uint32_t> ord(n);
+  for (uint32_t i = 0; i < n; i++) ord[i] = i;
+  std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
+    for (int byte = 0; byte < 32; byte++) {
+      uint8_t x = K[(size_t)a * 32 + byte], y = K[(size_t)b * 32 + byte];
+      if (x != y) {
+        const uint8_t diff = x ^ y, low = diff & (uint8_t)(-(int8_t)diff);     // lowest differing bit decides
+        return (x & low) == 0;
+      }
+    }
+    return false;
+  });
+  for (uint32_t i = 1; i < n; i++)
+    if (memcmp(K + (size_t)ord[i] * 32, K + (size_t)ord[i - 1] * 32, 32) == 0) { set_error("census_tree: duplicate key"); return ZKB_ERROR; }
+  struct Node { uint32_t lo, hi; int depth; int left, right; };          // children: node index, -1 = empty
+  std::vector<Node> nodes;
+  std::vector<std::pair<int, int>> stack;                                 // iterative build (node index, unused)
+  nodes.push_back({0, n, 0, -1, -1});
+  int max_depth = 0;
+  for (size_t q = 0; q < nodes.size(); q++) {
+    Node nd = nodes[q];
+    if (nd.hi - nd.lo <= 1) continue;
+    if (nd.depth >= n_levels) { set_error("census_tree: two keys share their first nLevels bits"); return ZKB_ERROR; }
+    uint32_t mid = nd.lo;
+    while (mid < nd.hi && !bit(ord[mid], nd.depth)) mid++;                // keys with bit `depth` = 0 come first
+    if (mid > nd.lo) { nodes[q].left = (int)nodes.size(); nodes.push_back({nd.lo, mid, nd.depth + 1, -1, -1}); }
+    if (mid < nd.hi) { nodes[q].right = (int)nodes.size(); nodes.push_back({mid, nd.hi, nd.depth + 1, -1, -1}); }
+    max_depth = std::max(max_depth, nd.depth + 1);
+  }
+  std::lock_guard<std::mutex> g(c->mu);
+  CKR(cudaSetDevice(c->ctx->device), "set device");
+  cudaStream_t st = c->ctx->stream;
+  const size_t nn = nodes.size();
+  std::vector<Fr> hash(nn, Fr::zero());
+  Fr *din = nullptr, *dout = nullptr;
+  CKR(cudaMalloc(&din, (size_t)std::max<size_t>(nn, n) * 3 * 32), "alloc");
+  CKR(cudaMalloc(&dout, (size_t)std::max<size_t>(nn, n) * 32), "alloc");
+  std::vector<Fr> in, out;
+  auto run = [&](int arity, uint32_t cnt) -> int {
+    out.resize(cnt);
+    CKR(cudaMemcpyAsync(din, in.data(), (size_t)cnt * arity * 32, cudaMemcpyHostToDevice, st), "h2d");
+    int rc = poseidon_device(c, arity, cnt, din, dout, st);
+    if (rc) return rc;
+    CKR(cudaMemcpyAsync(out.data(), dout, (size_t)cnt * 32, cudaMemcpyDeviceToHost, st), "d2h");
+    CKR(cudaStreamSynchronize(st), "sync");
+    return ZKB_OK;
+  };
+  // leaves: H(key, value, 1)
+  {
+    std::vector<size_t> idx;
+    in.clear();
+    for (size_t q = 0; q < nn; q++)
+      if (nodes[q].hi - nodes[q].lo == 1) {
+        idx.push_back(q);
+        Fr k, v, one = Fr::zero();
+        memcpy(k.v, K + (size_t)ord[nodes[q].lo] * 32, 32);
+        memcpy(v.v, V + (size_t)ord[nodes[q].lo] * 32, 32);
+        one.v[0] = 1;
+        in.push_back(k); in.push_back(v); in.push_back(one);
+      }
+    int rc = run(3, (uint32_t)idx.size());
+    if (rc) { cudaFree(din); cudaFree(dout); return rc; }
+    for (size_t t = 0; t < idx.size(); t++) hash[idx[t]] = out[t];
+  }
+  // internal nodes, deepest level first
+  std::vector<std::vector<size_t>> by_depth(max_depth + 1);
+  for (size_t q = 0; q < nn; q++)
+    if (nodes[q].hi - nodes[q].lo > 1) by_depth[nodes[q].depth].push_back(q);
+  for (int d = max_depth; d >= 0; d--) {
+    if (by_depth[d].empty()) continue;
+    in.clear();
+    for (size_t q : by_depth[d]) {
+      in.push_back(nodes[q].left >= 0 ? hash[nodes[q].left] : Fr::zero());
+      in.push_back(nodes[q].right >= 0 ? hash[nodes[q].right] : Fr::zero());
+    }
+    int rc = run(2, (uint32_t)by_depth[d].size());
+    if (rc) { cudaFree(din); cudaFree(dout); return rc; }
+    for (size_t t = 0; t < by_depth[d].size(); t++) hash[by_depth[d][t]] = out[t];
+  }
+  cudaFree(din); cudaFree(dout);
+  memcpy(root32, hash[0].v, 32);
+  if (siblings) {
+    uint8_t *S = (uint8_t *)siblings;
+    const size_t stride = (size_t)(n_levels + 1) * 32;
+    memset(S, 0, (size_t)n * stride);
+    // walk every node once: the sibling of all keys under a child is the other child's hash
+    for (size_t q = 0; q < nn; q++) {
+      const Node &nd = nodes[q];
+      if (nd.hi - nd.lo <= 1) continue;
+      for (int side = 0; side < 2; side++) {
+        const int ch = side ? nd.right : nd.left, other = side ? nd.left : nd.right;
+        if (ch < 0) continue;
+        const Fr sib = other >= 0 ? hash[other] : Fr::zero();
+        for (uint32_t t = nodes[ch].lo; t < nodes[ch].hi; t++) memcpy(S + (size_t)ord[t] * stride + (size_t)nd.depth * 32, sib.v, 32);
+      }
+    }
+  }
+  return ZKB_OK;
+}
 
 // ---- reference-shaped entry points ---------------------------------------------------------------
 // Host threads of the JSON stages.  Not OpenMP: a caller's OMP_NUM_THREADS (torchrun exports 1) must not serialise

@@ -212,6 +212,26 @@ class Circuit:
         _native.check(_lib().zkb_poseidon_hash(self.h, arity, n, buf.ctypes.data, out.ctypes.data))
         return [int.from_bytes(out[i].tobytes(), "little") for i in range(n)]
 
+    def census_tree(self, leaves: dict, n_levels=160):
+        """arbo-style Poseidon sparse Merkle tree of {key: value} built by the library (zkb_census_tree: structure in
+        C++, hashing on the GPU).  Returns (root, {key: [siblings, without the zero padding]})."""
+        keys = list(leaves)
+        n = len(keys)
+        kb = np.frombuffer(b"".join(int(k).to_bytes(32, "little") for k in keys), dtype=np.uint8)
+        vb = np.frombuffer(b"".join(int(leaves[k] % R_MOD).to_bytes(32, "little") for k in keys), dtype=np.uint8)
+        root = np.zeros(32, dtype=np.uint8)
+        sib = np.zeros((n, n_levels + 1, 32), dtype=np.uint8)
+        L = _lib()
+        L.zkb_census_tree.argtypes = [_vp, _i32, _vp, _vp, _i32, _vp, _vp]
+        _native.check(L.zkb_census_tree(self.h, n, kb.ctypes.data, vb.ctypes.data, n_levels, root.ctypes.data, sib.ctypes.data))
+        out = {}
+        for i, k in enumerate(keys):
+            row = [int.from_bytes(sib[i, j].tobytes(), "little") for j in range(n_levels + 1)]
+            while row and row[-1] == 0:
+                row.pop()
+            out[k] = row
+        return int.from_bytes(root.tobytes(), "little"), out
+
     # ---- resident path (inputs already in HBM; used for device-only timing) ---------------------
     def set_inputs(self, packed: np.ndarray):
         """packed: uint8[n, n_inputs, 32] canonical values in main-signal order (see pack_inputs)."""
