@@ -12,3 +12,9 @@ export function fullProve(
   wasmPath: string,
   zkeyPath: string
 ): Promise<{ proof: Groth16Proof; publicSignals: string[] }>;
+/** snarkjs groth16.verify(vKey, publicSignals, proof): objects or JSON strings; resolves false for an invalid proof */
+export function verify(
+  vKey: Record<string, unknown> | string,
+  publicSignals: string[] | string,
+  proof: Groth16Proof | Record<string, unknown> | string
+): Promise<boolean>;
