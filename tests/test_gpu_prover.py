@@ -294,21 +294,27 @@ def _sharded_proof(zkey, wtns, nranks, devices, slices=False):
                 if a is not b:
                     a.shard_attach_witness_local(b.shard[0], b)
         outs = []
-        for _ in range(2):                 # two proofs: two epochs
-            res = [None] * nranks
+        try:
+            for _ in range(2):                 # two proofs: two epochs
+                res = [None] * nranks
 
-            def work(r):
-                res[r] = cs[r].prove_wtns(wtns)
-            ts = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
-            assert all(res[r] == (b"", b"") for r in range(1, nranks))
-            outs.append(res[0])
-        assert outs[0] == outs[1]
-        for c in cs:
-            c.close()
+                def work(r):
+                    try:
+                        res[r] = cs[r].prove_wtns(wtns)
+                    except Exception as e:      # noqa: BLE001
+                        res[r] = e
+                ts = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+                for t in ts:
+                    t.start()
+                for t in ts:
+                    t.join()
+                assert all(res[r] == (b"", b"") for r in range(1, nranks)), res[1:]
+                assert not isinstance(res[0], Exception), res[0]
+                outs.append(res[0])
+            assert outs[0] == outs[1]
+        finally:
+            for c in cs:
+                c.close()
         return outs[0]
     for c in cs[1:]:                       # single thread: the peers publish first, then rank 0 combines
         assert c.prove_wtns(wtns) == (b"", b"")

@@ -287,3 +287,26 @@ def test_rlc_batch_verification(circuit, files):
     want[5] = want[17] = want[20] = 0
     assert got == want
     assert O.verify_many(H.dev_vkey(), pubs[:8].tobytes(), proofs[:8].tobytes(), 8).all()
+
+
+def test_pair_tree_prover_path_matches_oracle(files, monkeypatch):
+    """ZKB_AFFINE=1: the H MSM of a batch runs through the batched-affine pair tree (opt-in):
+    same proofs, bit for bit, and the work counters show where the additions went."""
+    from zk_franchise_proof_circuit_b200 import prover
+    monkeypatch.setenv("ZKB_AFFINE", "1")
+    c = prover.Circuit(prover._context(None), files[0], files[1])
+    try:
+        vs = H.voters(40)
+        c.set_blinding(H.R_FIXED, H.S_FIXED)
+        c.set_inputs(np.stack([prover.pack_inputs(v) for v in vs]))
+        c.prove_resident()
+        proofs, pubs, status = c.get_results()
+        assert (status == 0).all()
+        wc = c.work_counters()
+        assert wc["g1_affine_adds_per_proof"] > 1.5e6 and wc["g1_inversions_per_proof"] > 0
+        assert prover.verify_batch_bin(files[2], pubs, proofs).sum() == 40
+        for i in (0, 21, 39):
+            code, w = _ref_witness(vs[i])
+            assert proofs[i].tobytes() == H.zkey_ref().prove(w, H.R_FIXED, H.S_FIXED), f"voter {i}"
+    finally:
+        c.close()
