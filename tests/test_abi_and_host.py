@@ -174,3 +174,14 @@ def test_export_vkey_matches_setup_vkeys(art_dir):
     from zk_franchise_proof_circuit_b200._native import NativeError
     with pytest.raises(NativeError):
         prover.export_vkey(b"zkey" + bytes(100))
+
+
+def test_json_formatter_under_address_sanitizer(tmp_path):
+    """u256_to_dec overflowed its stack buffer for values >= 10^72.  csrc/json_io.cc built with
+    -fsanitize=address,undefined formats r-1, q-1, 2^256-1, 0, 1 and a proof / public-signal document."""
+    src = os.path.join(H.ROOT, "tests", "host_emul", "json_asan.cc")
+    exe = str(tmp_path / "json_asan")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                           "-o", exe, src])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "json_asan ok" in out.stdout, out.stdout + out.stderr
