@@ -342,20 +342,23 @@ def test_sharded_key_matches_oracle(tmp_path):
         assert O.proof_bin(json.loads(pj)) == exp
         prover.verify(vkey, sj, pj)
     # more ranks than 2^17-point ranges: the key is cut into finer ranges (8 ranks -> 2^15 points each)
-    pj, sj = _sharded_proof(zkey, wtns, 8, [0], slices=True)
+    pj, sj = _sharded_proof(zkey, wtns, 8, [0])
     assert O.proof_bin(json.loads(pj)) == exp
     with pytest.raises(Exception):
         prover.load_shard(zkey, 0, 17)      # more than SHARD_MAX_RANKS
 
 
 def test_sharded_key_witness_slices(tmp_path):
-    """Every rank uploads only its slice of the .wtns and gathers the rest from the peers' buffers (here: contexts of
-    one GPU, one host thread per rank as in a multi-process run): same proof as the CPU oracle."""
+    """Every rank uploads only its slice of the .wtns and gathers the rest from the peers' buffers (here: two contexts
+    of one GPU, one host thread per rank as in a multi-process run): same proof as the CPU oracle.  Two ranks only: the
+    ranks wait for each other's slices with a spinning kernel, which needs the ranks' streams on distinct hardware
+    queues - guaranteed with one process per GPU (bench.py --gpus N, test_sharded_key_two_gpus), not with many contexts
+    on one device."""
     n_wires, _, _ = O.chain_artifacts(600, 7, str(tmp_path), check=False)
     zkey = open(tmp_path / "proving_key.zkey", "rb").read()
     wtns = open(tmp_path / "witness.wtns", "rb").read()
     exp = O.ZKeyRef(zkey).prove(H.wtns_payload(wtns, n_wires), H.R_FIXED, H.S_FIXED)
-    pj, sj = _sharded_proof(zkey, wtns, 3, [0], slices=True)
+    pj, sj = _sharded_proof(zkey, wtns, 2, [0], slices=True)
     assert O.proof_bin(json.loads(pj)) == exp
 
 
