@@ -326,12 +326,6 @@ struct Lane {
   // small batches (latency): the witness-side MSMs run on two side streams beside the H pipeline
   cudaStream_t sW = nullptr, s2 = nullptr;
   cudaEvent_t e_fork = nullptr, e_sortW = nullptr, e_W = nullptr, e_2 = nullptr;
-  // batch shape: the latency-bound kernels of a chunk (witness, digit sorts, bucket reduction, proof assembly) run on
-  // a HIGH-PRIORITY stream, the IMAD-bound ones (A/B/C vectors, transforms, bucket accumulation) on `st`.  The
-  // accumulation kernels fill every SM's register file; without the priority a sort of another lane waits behind
-  // thousands of queued accumulation CTAs instead of slipping in as CTAs retire.
-  cudaStream_t stHi = nullptr;
-  cudaEvent_t e_start = nullptr, e_w = nullptr, e_abc = nullptr, e_sort = nullptr, e_acc = nullptr, e_fin = nullptr;
   Fr *abc = nullptr, *hs = nullptr, *dw = nullptr, *stage = nullptr;
   MsmSort sortW, sortH;
   MsmAffineWs affH;               // batched-affine pair tree of the H MSM (batch shape only)
@@ -510,11 +504,8 @@ static int alloc_workspace(Circuit *c, uint32_t cap, uint32_t chunk) {
       CKR(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming), "lane event");
       CKR(cudaStreamCreateWithFlags(&ln.sW, cudaStreamNonBlocking), "lane side stream");
       CKR(cudaStreamCreateWithFlags(&ln.s2, cudaStreamNonBlocking), "lane side stream");
-      for (cudaEvent_t *e : {&ln.e_fork, &ln.e_sortW, &ln.e_W, &ln.e_2, &ln.e_start, &ln.e_w, &ln.e_abc, &ln.e_sort, &ln.e_acc, &ln.e_fin})
+      for (cudaEvent_t *e : {&ln.e_fork, &ln.e_sortW, &ln.e_W, &ln.e_2})
         CKR(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "lane event");
-      int prio_least = 0, prio_greatest = 0;
-      cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-      CKR(cudaStreamCreateWithPriority(&ln.stHi, cudaStreamNonBlocking, prio_greatest), "lane priority stream");
     }
     CKR(cudaMalloc(&ln.abc, (size_t)chunk * 3 * c->domain * 32), "alloc abc");
     CKR(cudaMalloc(&ln.hs, (size_t)chunk * c->domain * 32), "alloc h");
@@ -562,14 +553,7 @@ static int run_witness(Circuit *c, Lane &ln, uint32_t first, uint32_t n, cudaStr
 // witness (optional) + Groth16 for proofs [first, first + m), m <= chunk, on lane ln
 static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, bool with_witness, cudaEvent_t *ev) {
   cudaStream_t st = ln.st;
-  static const uint32_t fork_max = env_u32("ZKB_FORK_MAX", 32);
-  static const bool prio_split = env_u32("ZKB_PRIO_SPLIT", 1) != 0;
-  // batch shape with several lanes in flight: latency-bound kernels on the lane's high-priority stream (see Lane)
-  const bool split = !ev && m > fork_max && prio_split && c->n_lanes > 1 && ln.stHi;
-  cudaStream_t hi = split ? ln.stHi : st;
-  if (split) { cudaEventRecord(ln.e_start, st); cudaStreamWaitEvent(hi, ln.e_start, 0); }
-  if (with_witness) { int rc = run_witness(c, ln, first, m, hi); if (rc) return rc; }
-  if (split) { cudaEventRecord(ln.e_w, hi); cudaStreamWaitEvent(st, ln.e_w, 0); }
+  if (with_witness) { int rc = run_witness(c, ln, first, m, st); if (rc) return rc; }
   if (ev) cudaEventRecord(ev[1], st);
   const Fr *w = c->wtns + (size_t)first * c->n_vars;
   // batch item p * sub + s = point range s of proof p (sub = 1: one item per proof)
@@ -594,6 +578,7 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
   }
   c->last_affine = affineH;
   if (affineH) g_launches += msm_affine_launches(ln.affH, m * sH) - 2;   // instead of the two XYZZ accumulate kernels of the H MSM
+  static const uint32_t fork_max = env_u32("ZKB_FORK_MAX", 32);
   if (!ev && m <= fork_max) {
     // Latency shape: after the witness, three independent pipelines.  st: A/B/C vectors -> coset transforms -> h ->
     // H MSM.  sW: witness difference -> digit sort -> A, B1, C sums.  s2: (after that sort) the G2 sum.
@@ -638,13 +623,10 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
     CKR(c->ntt.dit(ln.abc, 3 * m, c->domain, false, st), "ntt dit");
     k_join<<<g2, 256, 0, st>>>(ln.abc, ln.hs, c->domain);
     if (ev) cudaEventRecord(ev[3], st);
-    if (split) cudaEventRecord(ln.e_abc, st);
-    k_witness_diff<<<dim3((c->n_vars + 255) / 256, m), 256, 0, hi>>>(w, c->n_vars, c->tconst1 ? c->tmpl : nullptr, ln.dw, c->n_pad, c->n_vars);
+    k_witness_diff<<<dim3((c->n_vars + 255) / 256, m), 256, 0, st>>>(w, c->n_vars, c->tconst1 ? c->tmpl : nullptr, ln.dw, c->n_pad, c->n_vars);
     g_launches += 1;
-    CKR(ln.sortW.run(ln.dw + (size_t)c->loW * c->nsubW, c->nsubW, m * sW, hi), "sort witness digits");
-    if (split) cudaStreamWaitEvent(hi, ln.e_abc, 0);
-    CKR(ln.sortH.run(ln.hs + (size_t)c->loH * c->nsubH, c->nsubH, m * sH, hi), "sort h digits");
-    if (split) { cudaEventRecord(ln.e_sort, hi); cudaStreamWaitEvent(st, ln.e_sort, 0); }
+    CKR(ln.sortW.run(ln.dw + (size_t)c->loW * c->nsubW, c->nsubW, m * sW, st), "sort witness digits");
+    CKR(ln.sortH.run(ln.hs + (size_t)c->loH * c->nsubH, c->nsubH, m * sH, st), "sort h digits");
     if (ev) cudaEventRecord(ev[4], st);
     // bucket sums: G1 over the witness difference (A, B1, C share one sort), H over h, G2 (B2) over the witness difference
     CKR(msm_accumulate<Fq>(ln.sortW, tabs, 3, m * sW, ln.work1, 0, st, strW, sW), "msm accumulate g1 (A,B1,C)");
@@ -653,17 +635,16 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
     if (ev) cudaEventRecord(ev[5], st);
     CKR(msm_accumulate<Fq2>(ln.sortW, &c->tabB2, 1, m * sW, ln.work2, 0, st, strW, sW), "msm accumulate g2 (B2)");
     if (ev) cudaEventRecord(ev[6], st);
-    if (split) { cudaEventRecord(ln.e_acc, st); cudaStreamWaitEvent(hi, ln.e_acc, 0); }
-    CKR(msm_reduce<Fq>(ln.work1, 0, 3 * m * sW, outW, hi), "msm reduce g1");
-    CKR(msm_reduce<Fq>(ln.workH, 0, m * sH, outH, hi), "msm reduce g1 (H)");
-    CKR(msm_reduce<Fq2>(ln.work2, 0, m * sW, out2, hi), "msm reduce g2");
+    CKR(msm_reduce<Fq>(ln.work1, 0, 3 * m * sW, outW, st), "msm reduce g1");
+    CKR(msm_reduce<Fq>(ln.workH, 0, m * sH, outH, st), "msm reduce g1 (H)");
+    CKR(msm_reduce<Fq2>(ln.work2, 0, m * sW, out2, st), "msm reduce g2");
     if (splitW) {
-      CKR(msm_fold_subs<Fq>(outW, ln.g1out, m, sW, 3, hi), "fold g1 ranges");
-      CKR(msm_fold_subs<Fq2>(out2, ln.g2out, m, sW, 1, hi), "fold g2 ranges");
+      CKR(msm_fold_subs<Fq>(outW, ln.g1out, m, sW, 3, st), "fold g1 ranges");
+      CKR(msm_fold_subs<Fq2>(out2, ln.g2out, m, sW, 1, st), "fold g2 ranges");
       g_launches += 2;
     }
     if (splitH) {
-      CKR(msm_fold_subs<Fq>(outH, ln.g1out + (size_t)3 * c->chunk, m, sH, 1, hi), "fold g1 (H) ranges");
+      CKR(msm_fold_subs<Fq>(outH, ln.g1out + (size_t)3 * c->chunk, m, sH, 1, st), "fold g1 (H) ranges");
       g_launches += 1;
     }
   }
@@ -671,13 +652,12 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
     c->epoch++;
     g_launches += 1;
     if (c->shard_rank != 0) {
-      k_shard_publish<<<1, 256, 0, hi>>>(c->root_x + c->shard_rank, ln.g1out, ln.g1out + (size_t)3 * c->chunk, ln.g2out, c->epoch);
+      k_shard_publish<<<1, 256, 0, st>>>(c->root_x + c->shard_rank, ln.g1out, ln.g1out + (size_t)3 * c->chunk, ln.g2out, c->epoch);
       if (ev) { cudaEventRecord(ev[7], st); cudaEventRecord(ev[8], st); }
-      if (split) { cudaEventRecord(ln.e_fin, hi); cudaStreamWaitEvent(st, ln.e_fin, 0); }
       CKR(cudaGetLastError(), "shard publish");
       return ZKB_OK;                                     // rank 0 assembles the proof
     }
-    k_shard_combine<<<1, 32, 0, hi>>>(c->xbuf, c->shard_n, c->epoch, ln.g1out, ln.g1out + (size_t)3 * c->chunk, ln.g2out,
+    k_shard_combine<<<1, 32, 0, st>>>(c->xbuf, c->shard_n, c->epoch, ln.g1out, ln.g1out + (size_t)3 * c->chunk, ln.g2out,
                                       c->status + first);
   }
   if (ev) cudaEventRecord(ev[7], st);
@@ -700,8 +680,7 @@ static int run_prove_chunk(Circuit *c, Lane &ln, uint32_t first, uint32_t m, boo
   P.out = c->out + (size_t)first * c->out_stride();
   P.n_public = c->n_public;
   P.n = m;
-  CKR(launch_finalize(P, hi), "finalize");
-  if (split) { cudaEventRecord(ln.e_fin, hi); cudaStreamWaitEvent(st, ln.e_fin, 0); }
+  CKR(launch_finalize(P, st), "finalize");
   g_launches += 1;
   if (ev) cudaEventRecord(ev[8], st);
   CKR(cudaGetLastError(), "prove chunk launch");
@@ -1064,8 +1043,8 @@ static void destroy_circuit(Circuit *c) {
     c->lanes[i].free_all();
     if (c->lanes[i].st) {
       Lane &ln = c->lanes[i];
-      cudaStreamDestroy(ln.st); cudaStreamDestroy(ln.sW); cudaStreamDestroy(ln.s2); cudaStreamDestroy(ln.stHi);
-      for (cudaEvent_t e : {ln.done, ln.e_fork, ln.e_sortW, ln.e_W, ln.e_2, ln.e_start, ln.e_w, ln.e_abc, ln.e_sort, ln.e_acc, ln.e_fin}) cudaEventDestroy(e);
+      cudaStreamDestroy(ln.st); cudaStreamDestroy(ln.sW); cudaStreamDestroy(ln.s2);
+      for (cudaEvent_t e : {ln.done, ln.e_fork, ln.e_sortW, ln.e_W, ln.e_2}) cudaEventDestroy(e);
     }
   }
   delete c;
