@@ -199,7 +199,8 @@ int zkb_raw_msm_g1(const void *bases, size_t n, const void *scalars, int nbatch,
                    float *table_ms);
 int zkb_raw_msm_g2(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
                    float *table_ms);
-/* flags bit 0: bucket lists summed by the batched-affine pair tree (what the prover's H MSM uses in batch shape);
+/* flags bit 1: variable-base MSM (no window table; one bucket set per window, window sums combined by Horner's rule);
+ * flags bit 0: bucket lists summed by the batched-affine pair tree (opt-in path of the prover's H MSM in batch shape);
  * bits 8-11: tree levels (0 = 3), bits 16-31: additions sharing one field inversion (0 = 512) */
 int zkb_raw_msm_g1_ex(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
                       float *table_ms, uint32_t flags);
@@ -213,6 +214,7 @@ int zkb_raw_msm_g1_ex(const void *bases, size_t n, const void *scalars, int nbat
  * other ranks attach to it, then each step every rank calls run() (asynchronous; its last kernel writes the rank's
  * partial sum into rank 0's memory and releases a flag) and rank 0 calls combine(). */
 typedef struct zkb_msm_session zkb_msm_session;
+/* window_bits: 12..16, + 0x100 for the variable-base form (no window table: the bases are used as they are) */
 int zkb_msm_session_create(int device, int logn, int rank, int nranks, uint64_t seed, int window_bits,
                            zkb_msm_session **out);
 void zkb_msm_session_destroy(zkb_msm_session *s);

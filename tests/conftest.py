@@ -2,10 +2,6 @@ import os
 import sys
 import pytest
 
-# several contexts of one GPU stand in for several ranks in the single-GPU tests of the sharded paths: give their streams
-# separate hardware queues (must be set before CUDA initialises)
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -165,6 +165,24 @@ def test_msm_g1_pair_tree_matches_oracle(levels, group, monkeypatch):
         assert out[b].tobytes() == O.msm_g1(bases, sc[b]), f"batch item {b}"
 
 
+@pytest.mark.parametrize("window", [16, 12])
+def test_msm_g1_variable_base_matches_oracle(window, monkeypatch):
+    """No window table: one bucket set per window, window sums combined by Horner's rule.  Same degenerate inputs as the
+    fixed-base test (infinity, repeated bases, signed-digit boundary scalars)."""
+    from zk_franchise_proof_circuit_b200 import raw
+    monkeypatch.setenv("ZKB_RAW_MSM_C", str(window))
+    n = 700
+    bases = _g1_points(n, 1)
+    bases[10] = 0
+    bases[11] = bases[12]
+    rng = np.random.default_rng(5)
+    sc = _scalars(rng, (3, n))
+    sc[1, 11] = sc[1, 12]
+    out = raw.msm_g1(bases, sc, variable_base=True)
+    for b in range(3):
+        assert out[b].tobytes() == O.msm_g1(bases, sc[b]), f"batch item {b}"
+
+
 def test_msm_g1_pair_tree_dense_buckets(monkeypatch):
     """H-MSM shape scaled down: 2^14 random scalars, c = 12 -> ~180 entries per bucket, default tree (3 levels, 512)."""
     from zk_franchise_proof_circuit_b200 import raw

@@ -44,6 +44,27 @@ def test_session_four_ranks_one_device_matches_oracle():
     assert point1 == point
 
 
+def test_session_variable_base_matches_fixed_base():
+    """The variable-base form of the session (no window table) gives the same point as the fixed-base one, on one rank
+    and split over four; and the oracle's at 2^12."""
+    from zk_franchise_proof_circuit_b200 import raw
+    def run(logn, nranks, vb):
+        ss = [raw.MsmSession(logn, r, nranks, device=0, seed=1, window=16, variable_base=vb) for r in range(nranks)]
+        for s in ss[1:]:
+            s.attach_local(ss[0])
+        for s in ss:
+            s.run()
+        point, _ = ss[0].combine(nranks)
+        return ss, point
+    ss, p_vb = run(12, 1, True)
+    bases, scalars = ss[0].read()
+    assert p_vb == O.msm_g1(bases, scalars)
+    _, p_fixed = run(20, 1, False)
+    _, p_vb1 = run(20, 1, True)
+    _, p_vb4 = run(20, 4, True)
+    assert p_fixed == p_vb1 == p_vb4 and p_fixed != bytes(64)
+
+
 def test_session_split_invariance_large():
     """2^20 points: 8 sub-MSMs of 2^17 on one rank == 2 ranks x 4 sub-MSMs == 16 ranks of 2^16 (no oracle at this size)."""
     _, p1, _ = _run_group(20, 1, [0])

@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--nccl-compare", action="store_true",
                     help="also time the NCCL collectives the P2P exchanges replace (all_gather of one 128-byte partial "
                          "sum; all_to_all of the NTT columns), same GPUs, CUDA events")
+    ap.add_argument("--variable-base", action="store_true",
+                    help="also run every MSM size without a window table (bases used as they are, one bucket set per "
+                         "window, Horner combination): the column for bases that are not key material")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -70,8 +73,8 @@ def main():
             print(json.dumps(d), flush=True)
             lines.append(d)
 
-    for logn in [int(x) for x in args.msm.split(",") if x]:
-        s = raw.MsmSession(logn, rank, world, device=local, seed=1, window=16)
+    for logn, vb in [(int(x), v) for x in args.msm.split(",") if x for v in ((False, True) if args.variable_base else (False,))]:
+        s = raw.MsmSession(logn, rank, world, device=local, seed=1, window=16, variable_base=vb)
         if world > 1:
             box = [s.export_handle() if rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
@@ -91,7 +94,7 @@ def main():
                 times.append(reduce_max(ms))
         madds = reduce_sum(float(s.madds()))
         t = sorted(times)[len(times) // 2] * 1e-3
-        emit({"kind": "msm_g1", "logn": logn, "n_gpus": world, "ms": t * 1e3, "points_per_s": (1 << logn) / t,
+        emit({"kind": "msm_g1_variable_base" if vb else "msm_g1", "logn": logn, "n_gpus": world, "ms": t * 1e3, "points_per_s": (1 << logn) / t,
               "madds": madds, "gmodmul_per_s": madds * 10 / t / 1e9, "peak_gmodmul_per_s": peak * world / 1e9,
               "frac_of_imad_peak": madds * 10 / t / (peak * world), "window_bits": 16, "sub_msm_points": s.sub_size,
               "sub_msms_per_gpu": s.subs, "table_build_ms_rank0": s.table_ms, "gen_ms_rank0": s.gen_ms,

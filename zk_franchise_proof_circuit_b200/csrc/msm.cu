@@ -108,6 +108,57 @@ __global__ void k_digits(const Fr *scalars, size_t scalar_stride, uint32_t n, in
   }
 }
 
+// Variable-base form (no window table): batch item j * nsets + s holds window j of scalar set s, i.e. every scalar files
+// ONE entry per item (its digit j, index k into the set's bases), so each window has its own bucket set and the window
+// sums are combined afterwards by Horner's rule (k_horner).  Same signed digits as k_digits.
+template <bool SCATTER>
+__global__ void k_digits_vb(const Fr *scalars, size_t scalar_stride, uint32_t n, int c, int windows, uint32_t buckets,
+                            uint32_t nsets, uint32_t *counts_or_cursor, uint32_t *entries) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t sset = blockIdx.y;
+  if (k >= n) return;
+  const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + (size_t)sset * scalar_stride + k);
+  uint4 lo = sp[0], hi = sp[1];
+  uint32_t w[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0u};
+  if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) return;
+  const uint32_t mask = (1u << c) - 1, full = 1u << c;
+  uint32_t carry = 0;
+  for (int j = 0; j < windows; j++) {
+    int bit = j * c, wd = bit >> 5, sh = bit & 31;
+    uint64_t two = (uint64_t)w[wd] | ((uint64_t)(wd < 8 ? w[wd + 1] : 0u) << 32);
+    uint32_t v = ((uint32_t)(two >> sh) & mask) + carry;
+    uint32_t neg = v > buckets;
+    uint32_t mag = neg ? full - v : v;
+    carry = neg;
+    if (mag) {
+      const size_t item = (size_t)j * nsets + sset;
+      uint32_t *cc = counts_or_cursor + item * buckets;
+      if (SCATTER) {
+        uint32_t pos = atomicAdd(cc + (mag - 1), 1u);
+        entries[item * n + pos] = k | (neg << 31);
+      } else {
+        atomicAdd(cc + (mag - 1), 1u);
+      }
+    }
+  }
+}
+
+// out[s] = sum_j 2^(c j) * sum_t in[j * nsets * fold + s * fold + t]   (one thread per set; fold = sub-ranges per set)
+__global__ void k_horner(const XYZZ<Fq> *in, XYZZ<Fq> *out, uint32_t nsets, uint32_t fold, int windows, int c) {
+  uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= nsets) return;
+  XYZZ<Fq> acc = XYZZ<Fq>::infinity();
+  for (int j = windows - 1; j >= 0; j--) {
+    for (int i = 0; i < c; i++) xyzz_dbl_ni(&acc);
+    for (uint32_t t = 0; t < fold; t++) xyzz_add_ni(&acc, in + ((size_t)j * nsets * fold + (size_t)sidx * fold + t));
+  }
+  stg_pod(out + sidx, acc);
+}
+cudaError_t msm_horner(const XYZZ<Fq> *in, XYZZ<Fq> *out, uint32_t nsets, uint32_t fold, int windows, int c, cudaStream_t st) {
+  k_horner<<<(nsets + 31) / 32, 32, 0, st>>>(in, out, nsets, fold, windows, c);
+  return cudaGetLastError();
+}
+
 // offsets[b][0..buckets] = exclusive scan of counts[b]; cursor[b] = offsets[b][0..buckets).  One CTA of 1024
 // threads per batch item, each thread owning buckets/1024 consecutive counters (<= 32).
 __global__ void __launch_bounds__(1024) k_scan(const uint32_t *counts, uint32_t *offsets, uint32_t *cursor,
@@ -217,6 +268,23 @@ void MsmSort::free_all() {
   cudaFree(counts); cudaFree(offsets); cudaFree(cursor); cudaFree(entries); cudaFree(order); cudaFree(n_long);
   counts = offsets = cursor = entries = order = n_long = nullptr;
 }
+// variable-base digits: nsets scalar sets -> nsets * windows batch items (item j * nsets + s = window j of set s);
+// this sort's cfg must have windows == 1 (one entry per scalar per item)
+cudaError_t MsmSort::run_vb(const Fr *scalars, size_t scalar_stride, uint32_t nsets, int windows, cudaStream_t st) {
+  const uint32_t nitems = nsets * (uint32_t)windows;
+  if (nitems > batch || cfg.windows != 1) return cudaErrorInvalidValue;
+  CK(cudaMemsetAsync(counts, 0, (size_t)nitems * cfg.buckets * 4, st));
+  dim3 grid((n + 255) / 256, nsets);
+  k_digits_vb<false><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cfg.c, windows, cfg.buckets, nsets, counts, nullptr);
+  k_scan<<<nitems, 1024, 0, st>>>(counts, offsets, cursor, cfg.buckets);
+  const bool lat = (uint64_t)nitems * cfg.buckets < 262144;
+  max_long = lat ? MAX_LONG_LAT : MAX_LONG;
+  if (max_long > cfg.buckets / 2) max_long = cfg.buckets / 2;
+  k_order<<<nitems, 1024, 0, st>>>(counts, order, n_long, cfg.buckets, lat ? LONG_BUCKET_LAT : LONG_BUCKET, max_long);
+  k_digits_vb<true><<<grid, 256, 0, st>>>(scalars, scalar_stride, n, cfg.c, windows, cfg.buckets, nsets, cursor, entries);
+  return cudaGetLastError();
+}
+
 cudaError_t MsmSort::run(const Fr *scalars, size_t scalar_stride, uint32_t nbatch, cudaStream_t st) {
   if (nbatch > batch) return cudaErrorInvalidValue;
   CK(cudaMemsetAsync(counts, 0, (size_t)nbatch * cfg.buckets * 4, st));

@@ -46,9 +46,13 @@ struct MsmSort {
   void free_all();
   // scalars: [batch] vectors of n canonical 256-bit values, `scalar_stride` elements apart
   cudaError_t run(const Fr *scalars, size_t scalar_stride, uint32_t nbatch, cudaStream_t st);
+  // variable-base form: see k_digits_vb in msm.cu
+  cudaError_t run_vb(const Fr *scalars, size_t scalar_stride, uint32_t nsets, int windows, cudaStream_t st);
 };
 
 int msm_sort_launches();   // kernels one MsmSort::run launches
+// window sums of a variable-base MSM -> the MSM: out[s] = sum_j 2^(c j) sum_t in[j * nsets * fold + s * fold + t]
+cudaError_t msm_horner(const XYZZ<Fq> *in, XYZZ<Fq> *out, uint32_t nsets, uint32_t fold, int windows, int c, cudaStream_t st);
 
 // workspace for bucket sums + reduction of `slots` simultaneous (batch item, table) pairs
 template <class F>

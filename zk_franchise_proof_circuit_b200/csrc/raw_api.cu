@@ -140,6 +140,28 @@ static int raw_msm(const void *bases, size_t n, const void *scalars, int nbatch,
     cudaEventRecord(e1);
     CKR(sort.run(ds.as<Fr>(), n, nbatch, 0), "sort");
     if constexpr (sizeof(F) == 32) {
+      if (flags & 2u) {                      // variable-base: no window table, one bucket set per window, Horner at the end
+        MsmCfg c1 = cfg;
+        c1.windows = 1;
+        MsmSort vs;
+        MsmWork<F> vw;
+        MsmTable<F> bt;
+        bt.tab = db.as<Affine<F>>(); bt.n = (uint32_t)n; bt.cfg = c1;
+        DevBuf wsum;
+        const uint32_t items = (uint32_t)nbatch * (uint32_t)cfg.windows;
+        CKR(vs.alloc((uint32_t)n, items, c1), "sort alloc");
+        CKR(vw.alloc(items, c1), "work alloc");
+        CKR(wsum.alloc(sizeof(XYZZ<F>) * items), "alloc");
+        CKR(vs.run_vb(ds.as<Fr>(), n, nbatch, cfg.windows, 0), "sort (variable base)");
+        CKR(msm_accumulate<F>(vs, &bt, 1, items, vw, 0, 0, 0, items), "accumulate (variable base)");
+        CKR(msm_reduce<F>(vw, 0, items, wsum.as<XYZZ<F>>(), 0), "reduce (variable base)");
+        CKR(msm_horner(wsum.as<XYZZ<F>>(), dout.as<XYZZ<F>>(), nbatch, 1, cfg.windows, cfg.c, 0), "horner");
+        cudaEventRecord(e2);
+        CKR(cudaEventSynchronize(e2), "msm run");
+        vs.free_all();
+        vw.free_all();
+        continue;
+      }
       if (flags & 1u) {                      // bucket lists through the batched-affine pair tree
         MsmAffineWs ws;
         CKR(ws.alloc((uint32_t)n * (uint32_t)cfg.windows, nbatch > 2 ? 2 : nbatch, cfg), "pair tree alloc");   // 3 items: two sub-batches
@@ -285,6 +307,7 @@ int zkb_raw_msm_g1(const void *bases, size_t n, const void *scalars, int nbatch,
                    float *table_ms) {
   return raw_msm<Fq>(bases, n, scalars, nbatch, out, kernel_ms, table_ms);
 }
+// flags bit 1: variable-base MSM (no window table: one bucket set per window, window sums combined by Horner's rule)
 // flags bit 0: sum the bucket lists with the batched-affine pair tree (the H MSM's batch path); bits 8-11: tree levels
 // (0 = default 3); bits 16-31: additions per field inversion (0 = default 512)
 int zkb_raw_msm_g1_ex(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,

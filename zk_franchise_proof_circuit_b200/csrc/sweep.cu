@@ -149,6 +149,9 @@ struct MsmSession {
   int device = 0;
   cudaStream_t st = nullptr;
   uint32_t n_sub = 0, subs = 0;       // this rank: subs sub-MSMs of n_sub points
+  bool vb = false;                    // variable base: no window table, `windows` bucket sets per sub-MSM, Horner at the end
+  int windows = 0;                    // windows of the digit decomposition (cfg.windows is 1 in the variable-base form)
+  uint32_t items = 0;                 // batch items of one run: subs (fixed base) or subs * windows (variable base)
   uint64_t first = 0, total = 0;      // global index of this rank's first point; points in the whole MSM
   uint64_t seed = 0;
   MsmCfg cfg;
@@ -295,10 +298,12 @@ int zkb_msm_session_create(int device, int logn, int rank, int nranks, uint64_t 
                            zkb_msm_session **out) {
   if (require_device()) return ZKB_ERROR;
   if (logn < 10 || logn > 27 || nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks ||
-      (nranks & (nranks - 1)) || window_bits < 12 || window_bits > 16) {
-    set_error("msm session: logn in [10,27], nranks a power of two <= 16, window in [12,16]");
+      (nranks & (nranks - 1)) || (window_bits & 0xff) < 12 || (window_bits & 0xff) > 16 || (window_bits & ~0x1ff)) {
+    set_error("msm session: logn in [10,27], nranks a power of two <= 16, window in [12,16] (+ 0x100: variable base)");
     return ZKB_ERROR;
   }
+  const bool vb = (window_bits & 0x100) != 0;
+  window_bits &= 0xff;
   CKR(cudaSetDevice(device), "set device");
   MsmSession *s = new MsmSession();
   // any failure below releases what was allocated so far
@@ -306,12 +311,19 @@ int zkb_msm_session_create(int device, int logn, int rank, int nranks, uint64_t 
   s->device = device;
   s->total = 1ull << logn;
   uint64_t mine = s->total / nranks;
-  s->n_sub = (uint32_t)(mine < (1u << 17) ? mine : (1u << 17));
+  // fixed base: sub-MSMs of 2^17 points (16 digits per point land in one bucket set); variable base: every window has
+  // its own bucket set, so a sub-MSM takes 2^20 points to fill 2^15 buckets with ~32 entries each
+  const uint32_t sub_max = vb ? (1u << 20) : (1u << 17);
+  s->n_sub = (uint32_t)(mine < sub_max ? mine : sub_max);
   s->subs = (uint32_t)(mine / s->n_sub);
+  s->vb = vb;
   s->first = mine * rank;
   s->seed = seed;
   s->slot = rank;
   s->cfg = msm_cfg(window_bits);
+  s->windows = s->cfg.windows;
+  if (vb) s->cfg.windows = 1;
+  s->items = vb ? s->subs * (uint32_t)s->windows : s->subs;
   CKS(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking), "stream");
   cudaEventCreate(&s->e0); cudaEventCreate(&s->e1); cudaEventCreate(&s->e2);
   CKS(cudaMalloc(&s->bases, mine * sizeof(Affine<Fq>)), "alloc bases");
@@ -320,11 +332,12 @@ int zkb_msm_session_create(int device, int logn, int rank, int nranks, uint64_t 
   k_gen_points<<<(unsigned)((mine + 127) / 128), 128, 0, s->st>>>(s->bases, s->first, mine, seed);
   k_gen_scalars<<<(unsigned)((mine + 255) / 256), 256, 0, s->st>>>(s->scalars, s->first, mine, seed);
   cudaEventRecord(s->e1, s->st);
-  CKS(msm_build_table<Fq>(s->tab, s->bases, s->n_sub, s->cfg, s->st, s->subs), "build table");
+  if (vb) { s->tab.tab = s->bases; s->tab.n = s->n_sub; s->tab.cfg = s->cfg; }      // the bases ARE the table
+  else CKS(msm_build_table<Fq>(s->tab, s->bases, s->n_sub, s->cfg, s->st, s->subs), "build table");
   cudaEventRecord(s->e2, s->st);
-  CKS(s->sort.alloc(s->n_sub, s->subs, s->cfg), "alloc sort");
-  CKS(s->work.alloc(s->subs, s->cfg), "alloc buckets");
-  CKS(cudaMalloc(&s->sub_out, (size_t)s->subs * sizeof(XYZZ<Fq>)), "alloc");
+  CKS(s->sort.alloc(s->n_sub, s->items, s->cfg), "alloc sort");
+  CKS(s->work.alloc(s->items, s->cfg), "alloc buckets");
+  CKS(cudaMalloc(&s->sub_out, (size_t)s->items * sizeof(XYZZ<Fq>)), "alloc");
   CKS(cudaMalloc(&s->partial, sizeof(XYZZ<Fq>)), "alloc");
   CKS(cudaMalloc(&s->xbuf, MAX_RANKS * sizeof(ExSlot)), "alloc exchange");
   CKS(cudaMemsetAsync(s->xbuf, 0, MAX_RANKS * sizeof(ExSlot), s->st), "memset");
@@ -345,7 +358,8 @@ void zkb_msm_session_destroy(zkb_msm_session *h) {
   cudaSetDevice(s->device);
   if (s->st) cudaStreamSynchronize(s->st);
   if (s->root_is_ipc) cudaIpcCloseMemHandle(s->root_x);
-  cudaFree(s->bases); cudaFree(s->scalars); cudaFree(s->tab.tab); cudaFree(s->sub_out); cudaFree(s->partial);
+  if (!s->vb) cudaFree(s->tab.tab);
+  cudaFree(s->bases); cudaFree(s->scalars); cudaFree(s->sub_out); cudaFree(s->partial);
   cudaFree(s->xbuf); cudaFree(s->result); cudaFree(s->status);
   s->sort.free_all();
   s->work.free_all();
@@ -408,10 +422,18 @@ int zkb_msm_session_run(zkb_msm_session *h, float *ms) {
   CKR(cudaSetDevice(s->device), "set device");
   s->epoch++;
   cudaEventRecord(s->e0, s->st);
-  CKR(s->sort.run(s->scalars, s->n_sub, s->subs, s->st), "sort");
-  CKR(msm_accumulate<Fq>(s->sort, &s->tab, 1, s->subs, s->work, 0, s->st, (size_t)s->cfg.windows * s->n_sub), "accumulate");
-  CKR(msm_reduce<Fq>(s->work, 0, s->subs, s->sub_out, s->st), "reduce");
-  k_fold<<<1, 256, 0, s->st>>>(s->sub_out, s->subs, s->partial);
+  if (s->vb) {
+    // item j * subs + t = window j of sub-MSM t; its bases are block t (items % subs) of the rank's points
+    CKR(s->sort.run_vb(s->scalars, s->n_sub, s->subs, s->windows, s->st), "sort (variable base)");
+    CKR(msm_accumulate<Fq>(s->sort, &s->tab, 1, s->items, s->work, 0, s->st, (size_t)s->n_sub, s->subs), "accumulate");
+    CKR(msm_reduce<Fq>(s->work, 0, s->items, s->sub_out, s->st), "reduce");
+    CKR(msm_horner(s->sub_out, s->partial, 1, s->subs, s->windows, s->cfg.c, s->st), "horner");
+  } else {
+    CKR(s->sort.run(s->scalars, s->n_sub, s->subs, s->st), "sort");
+    CKR(msm_accumulate<Fq>(s->sort, &s->tab, 1, s->subs, s->work, 0, s->st, (size_t)s->cfg.windows * s->n_sub), "accumulate");
+    CKR(msm_reduce<Fq>(s->work, 0, s->subs, s->sub_out, s->st), "reduce");
+    k_fold<<<1, 256, 0, s->st>>>(s->sub_out, s->subs, s->partial);
+  }
   k_publish<<<1, 64, 0, s->st>>>(s->root_x + s->slot, s->partial, s->epoch);
   cudaEventRecord(s->e1, s->st);
   CKR(cudaGetLastError(), "msm session launch");
@@ -445,9 +467,9 @@ int zkb_msm_session_madds(zkb_msm_session *h, uint64_t *madds) {
   CKR(cudaSetDevice(s->device), "set device");
   unsigned long long t = 0;
   // every sub-MSM has its own table block; none of the synthetic bases is infinity, so count entries - buckets used
-  std::vector<uint32_t> off((size_t)s->subs * (s->cfg.buckets + 1));
+  std::vector<uint32_t> off((size_t)s->items * (s->cfg.buckets + 1));
   CKR(cudaMemcpy(off.data(), s->sort.offsets, off.size() * 4, cudaMemcpyDeviceToHost), "d2h");
-  for (uint32_t b = 0; b < s->subs; b++) {
+  for (uint32_t b = 0; b < s->items; b++) {
     const uint32_t *o = off.data() + (size_t)b * (s->cfg.buckets + 1);
     for (uint32_t i = 0; i < s->cfg.buckets; i++) {
       uint32_t len = o[i + 1] - o[i];

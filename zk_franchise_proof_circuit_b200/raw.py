@@ -58,15 +58,15 @@ def _msm(fn, psize, bases, scalars, timing):
     return (out, kms.value, tms.value) if timing else out
 
 
-def msm_g1(bases, scalars, timing=False, pair_tree=False, levels=0, group=0):
+def msm_g1(bases, scalars, timing=False, pair_tree=False, levels=0, group=0, variable_base=False):
     """bases: uint8[n, 64] canonical affine (zeros = infinity); scalars: uint8[(nbatch,) n, 32].
     pair_tree: sum the bucket lists with the batched-affine pair tree (zkb_raw_msm_g1_ex flag 1)."""
-    if not pair_tree:
+    if not pair_tree and not variable_base:
         return _msm(_native.lib().zkb_raw_msm_g1, 64, bases, scalars, timing)
     fn = _native.lib().zkb_raw_msm_g1_ex
     fn.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                    ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_uint32]
-    flags = 1 | (levels << 8) | (group << 16)
+    flags = (2 if variable_base else 1) | (levels << 8) | (group << 16)
     return _msm(lambda *a: fn(*a, flags), 64, bases, scalars, timing)
 
 
@@ -78,10 +78,13 @@ class MsmSession:
     """One rank's share of a 2^logn-point synthetic G1 MSM split by point range (include/zkcensus_b200.h,
     zkb_msm_session_*).  Ranks > 0 push their partial sum into rank 0's exchange buffer over NVLink; rank 0 combines."""
 
-    def __init__(self, logn, rank=0, nranks=1, device=0, seed=1, window=16):
+    def __init__(self, logn, rank=0, nranks=1, device=0, seed=1, window=16, variable_base=False):
+        """variable_base: no precomputed window table (the bases are used as they are): one bucket set per window and a
+        Horner combination at the end - the MSM for bases that are not key material."""
         self.h = ctypes.c_void_p()
         self.rank, self.nranks = rank, nranks
-        _native.check(_native.lib().zkb_msm_session_create(device, logn, rank, nranks, seed, window, ctypes.byref(self.h)))
+        _native.check(_native.lib().zkb_msm_session_create(device, logn, rank, nranks, seed,
+                                                           window | (0x100 if variable_base else 0), ctypes.byref(self.h)))
         info = (ctypes.c_uint64 * 6)()
         _native.check(_native.lib().zkb_msm_session_info(self.h, info))
         self.points, self.sub_size, self.subs, self.window = int(info[0]), int(info[1]), int(info[2]), int(info[3])
