@@ -17,7 +17,7 @@ LIB = os.path.join(H.ROOT, "zk_franchise_proof_circuit_b200", "libzkcensus_b200.
 def _declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(zkb_[a-z0-9_]+|groth16_prover)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(zkb_[a-z0-9_]+|groth16_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -185,3 +185,24 @@ def test_json_formatter_under_address_sanitizer(tmp_path):
                            "-o", exe, src])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "json_asan ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_census_of_chosen_depth_passes_the_reference_wasm(art_dir):
+    """census_tree.gen_census_depth (bench.py's depth sweep) with the oracle's Poseidon as the hasher: tree_depth is
+    what was asked for and the reference wasm accepts the inputs (depth 1, the reference's own 10-leaf shape 4, and
+    the circuit's maximum 160)."""
+    import census_gen as G
+    import ref_witness as RW
+    from zk_franchise_proof_circuit_b200 import census_tree as CT
+    if not RW.available():
+        pytest.skip("oracle/_ref not built")
+
+    class Hasher:
+        P = G.Poseidon(H.poseidon_tables())
+
+        def poseidon(self, rows):
+            return [self.P(list(r)) for r in rows]
+    for depth in (1, 4, 160):
+        v = CT.gen_census_depth(Hasher(), 1, depth, seed=3)[0]
+        assert CT.tree_depth(v) == depth
+        assert RW.witness(v)[0] == 0
