@@ -41,29 +41,36 @@ __global__ void __launch_bounds__(128) k_tape_eval(TapeDev T, const Fr *__restri
   for (uint32_t i = lane; i < T.n_inputs; i += 32) tape_st(slots + i, tape_ld(inputs + (size_t)p * T.n_inputs + i).to_mont());
   __syncwarp();
   bool failed = false;
-  uint32_t beg = T.level_start[0];
-  for (uint32_t l = 0; l < T.n_levels; l++) {
-    const uint32_t end = T.level_start[l + 1];
-    for (uint32_t i = beg + lane; i < end; i += 32) {
-      const TapeOp o = T.tape[i];
-      const Fr a = (o.a & 1u) ? tape_ld(T.consts + (o.a >> 1)) : tape_ld(slots + (o.a >> 1));
-      Fr b = a, c = a;
-      if (o.op <= T_BXOR && o.op != T_NEG && o.op != T_INV && o.op != T_LNOT)
-        b = (o.b & 1u) ? tape_ld(T.consts + (o.b >> 1)) : tape_ld(slots + (o.b >> 1));
-      if (o.op == T_SELECT) {
-        b = (o.b & 1u) ? tape_ld(T.consts + (o.b >> 1)) : tape_ld(slots + (o.b >> 1));
-        c = (o.c & 1u) ? tape_ld(T.consts + (o.c >> 1)) : tape_ld(slots + (o.c >> 1));
-      }
-      Fr r;
-      // the three operations that make up almost all of a circuit stay out of the big switch
-      if (o.op == T_MUL) r = a * b;
-      else if (o.op == T_ADD) r = a + b;
-      else if (o.op == T_SUB) r = a - b;
-      else r = tape_apply(o.op, a, b, c, &failed);
-      if (o.op != T_ASSERT_TRUE && o.op != T_ASSERT_FALSE) tape_st(slots + (o.dst >> 1), r);
+  auto exec = [&](const TapeOp &o) {
+    const Fr a = (o.a & 1u) ? tape_ld(T.consts + (o.a >> 1)) : tape_ld(slots + (o.a >> 1));
+    Fr b = a, c = a;
+    if (o.op <= T_BXOR && o.op != T_NEG && o.op != T_INV && o.op != T_LNOT)
+      b = (o.b & 1u) ? tape_ld(T.consts + (o.b >> 1)) : tape_ld(slots + (o.b >> 1));
+    if (o.op == T_SELECT) {
+      b = (o.b & 1u) ? tape_ld(T.consts + (o.b >> 1)) : tape_ld(slots + (o.b >> 1));
+      c = (o.c & 1u) ? tape_ld(T.consts + (o.c >> 1)) : tape_ld(slots + (o.c >> 1));
     }
+    Fr r;
+    // the three operations that make up almost all of a circuit stay out of the big switch
+    if (o.op == T_MUL) r = a * b;
+    else if (o.op == T_ADD) r = a + b;
+    else if (o.op == T_SUB) r = a - b;
+    else r = tape_apply(o.op, a, b, c, &failed);
+    if (o.op != T_ASSERT_TRUE && o.op != T_ASSERT_FALSE) tape_st(slots + (o.dst >> 1), r);
+  };
+  // The operations of level l + 1 (and the level table two ahead) are fetched while level l computes: a level is a
+  // chain tape entry -> operands -> product -> store, and the first link does not depend on the previous level.
+  uint32_t beg = T.level_start[0], end = T.level_start[1];
+  TapeOp cur = T.tape[min(beg + lane, T.n_ops - 1)];
+  for (uint32_t l = 0; l < T.n_levels; l++) {
+    const uint32_t nend = T.level_start[min(l + 2, T.n_levels)];
+    const TapeOp nxt = T.tape[min(end + lane, T.n_ops - 1)];
+    if (beg + lane < end) exec(cur);
+    for (uint32_t i = beg + lane + 32; i < end; i += 32) exec(T.tape[i]);     // levels wider than a warp (rare)
     __syncwarp();
+    cur = nxt;
     beg = end;
+    end = nend;
   }
   if (__any_sync(0xffffffffu, failed) && lane == 0) atomicMax(status + p, 4);
 }
