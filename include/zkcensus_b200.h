@@ -201,7 +201,6 @@ int zkb_raw_msm_g2(const void *bases, size_t n, const void *scalars, int nbatch,
                    float *table_ms);
 /* flags bit 1: variable-base MSM (no window table; one bucket set per window, window sums combined by Horner's rule);
  * flags bit 0: bucket lists summed by the batched-affine pair tree (opt-in path of the prover's H MSM in batch shape);
- * flags bit 2: the pair tree's second form (separate index / divisor / inverse / add kernels);
  * bits 8-11: tree levels (0 = 3), bits 16-31: additions sharing one field inversion (0 = 512) */
 int zkb_raw_msm_g1_ex(const void *bases, size_t n, const void *scalars, int nbatch, void *out, float *kernel_ms,
                       float *table_ms, uint32_t flags);

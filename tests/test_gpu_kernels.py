@@ -140,9 +140,8 @@ def test_msm_g1_small_matches_oracle(window, monkeypatch):
         assert out[b].tobytes() == O.msm_g1(bases, sc[b])
 
 
-@pytest.mark.parametrize("version", [1, 2])
 @pytest.mark.parametrize("levels,group", [(1, 8), (2, 8), (3, 16), (4, 8), (3, 512)])
-def test_msm_g1_pair_tree_matches_oracle(levels, group, version, monkeypatch):
+def test_msm_g1_pair_tree_matches_oracle(levels, group, monkeypatch):
     """The batched-affine pair tree (the prover's H MSM in batch shape) on degenerate inputs: a base at infinity, equal
     bases with equal digits (P + P inside a bucket -> doubling), equal bases with opposite scalars (P - P -> the
     point at infinity flowing through later levels), tiny inversion groups so that thread ranges straddle buckets."""
@@ -161,7 +160,7 @@ def test_msm_g1_pair_tree_matches_oracle(levels, group, version, monkeypatch):
     sc[1, 21] = np.frombuffer(neg.to_bytes(32, "little"), dtype=np.uint8)     # P - P in every window
     sc[2, 30] = sc[2, 31] = sc[2, 32] = sc[2, 33]          # four equal entries: doubling at two levels
     sc[2, 40:60] = 0
-    out = raw.msm_g1(bases, sc, pair_tree=True, levels=levels, group=group, tree_version=version)
+    out = raw.msm_g1(bases, sc, pair_tree=True, levels=levels, group=group)
     for b in range(3):
         assert out[b].tobytes() == O.msm_g1(bases, sc[b]), f"batch item {b}"
 
@@ -184,8 +183,7 @@ def test_msm_g1_variable_base_matches_oracle(window, monkeypatch):
         assert out[b].tobytes() == O.msm_g1(bases, sc[b]), f"batch item {b}"
 
 
-@pytest.mark.parametrize("version", [1, 2])
-def test_msm_g1_pair_tree_dense_buckets(version, monkeypatch):
+def test_msm_g1_pair_tree_dense_buckets(monkeypatch):
     """H-MSM shape scaled down: 2^14 random scalars, c = 12 -> ~180 entries per bucket, default tree (3 levels, 512)."""
     from zk_franchise_proof_circuit_b200 import raw
     monkeypatch.setenv("ZKB_RAW_MSM_C", "12")
@@ -194,7 +192,7 @@ def test_msm_g1_pair_tree_dense_buckets(version, monkeypatch):
     bases = np.tile(base, (n // 64, 1))                    # 64 distinct points, each 256 times (plenty of doublings)
     rng = np.random.default_rng(6)
     sc = _scalars(rng, (2, n), special=False)
-    out, kms, _ = raw.msm_g1(bases, sc, timing=True, pair_tree=True, tree_version=version)
+    out, kms, _ = raw.msm_g1(bases, sc, timing=True, pair_tree=True)
     ref, kms0, _ = raw.msm_g1(bases, sc, timing=True)
     print(f"pair tree {kms:.3f} ms, XYZZ {kms0:.3f} ms")
     assert np.array_equal(out, ref)

@@ -289,12 +289,11 @@ def test_rlc_batch_verification(circuit, files):
     assert O.verify_many(H.dev_vkey(), pubs[:8].tobytes(), proofs[:8].tobytes(), 8).all()
 
 
-@pytest.mark.parametrize("form", ["1", "2"])
-def test_pair_tree_prover_path_matches_oracle(files, monkeypatch, form):
+def test_pair_tree_prover_path_matches_oracle(files, monkeypatch):
     """ZKB_AFFINE=1: the H MSM of a batch runs through the batched-affine pair tree (opt-in):
     same proofs, bit for bit, and the work counters show where the additions went."""
     from zk_franchise_proof_circuit_b200 import prover
-    monkeypatch.setenv("ZKB_AFFINE", form)     # 1: one thread per group; 2: index / divisor / inverse / add kernels
+    monkeypatch.setenv("ZKB_AFFINE", "1")
     c = prover.Circuit(prover._context(None), files[0], files[1])
     try:
         vs = H.voters(40)

@@ -769,110 +769,6 @@ __global__ void __launch_bounds__(128) k_affine_level(const Affine<Fq> *tab, siz
   (void)j0; (void)k0;
 }
 
-// ---- pair tree, second form: one kernel per step instead of one long-running thread per group ----------------------
-// ncu on the one-kernel form above (profiles/r02_ncu_tree_summary.txt): DRAM at 33 %, multiply pipe at 31 %, stalls
-// dominated by long_scoreboard - every thread walks its 512 outputs serially with two dependent gathers per output
-// inside the product chain, so neither memory nor the multiplier is busy.  Here the gathers are taken out of the chain:
-//   k_tree_index    thread = bucket:  where each output of the level takes its operands
-//   k_tree_div      thread = output:  the divisor x2 - x1 (or 2 y1 / 1 in the degenerate cases)     [pure gather]
-//   k_tree_inverse  thread = group:   divisors -> their inverses in place, Montgomery's trick over      [sequential,
-//                                     `group` CONSECUTIVE array elements                                 streaming]
-//   k_tree_add      thread = output:  lambda, x3, y3                                                   [pure gather]
-// 480 instead of 320 bytes per addition, but all of it either fully parallel or sequential per thread.
-__global__ void __launch_bounds__(128) k_tree_index(const uint32_t *__restrict__ off_in_all,
-                                                    const uint32_t *__restrict__ off_out_all, uint32_t *src_all,
-                                                    size_t src_stride, uint32_t nbuckets) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  if (j >= nbuckets) return;
-  const uint32_t *off_in = off_in_all + (size_t)b * (nbuckets + 1), *off_out = off_out_all + (size_t)b * (nbuckets + 1);
-  const uint32_t in_beg = off_in[j], in_len = off_in[j + 1] - in_beg, out_beg = off_out[j], n_out = off_out[j + 1] - out_beg;
-  uint32_t *src = src_all + (size_t)b * src_stride;
-  for (uint32_t k = 0; k < n_out; k++) src[out_beg + k] = (in_beg + 2 * k) | ((2 * k + 1 < in_len) ? 0x80000000u : 0u);
-}
-
-template <bool FIRST>
-__global__ void __launch_bounds__(256) k_tree_div(const Affine<Fq> *tab, size_t tab_batch_stride, uint32_t tab_mod,
-                                                  uint32_t item0, const uint32_t *__restrict__ entries, size_t ent_stride,
-                                                  const Affine<Fq> *pin, size_t pin_stride,
-                                                  const uint32_t *__restrict__ off_out_all, const uint32_t *__restrict__ src_all,
-                                                  size_t src_stride, Fq *div_all, size_t div_stride, uint32_t nbuckets) {
-  const uint32_t b = blockIdx.y, o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= off_out_all[(size_t)b * (nbuckets + 1) + nbuckets]) return;
-  const uint32_t sidx = src_all[(size_t)b * src_stride + o];
-  const Affine<Fq> *tb = FIRST ? tab + (size_t)((item0 + b) % tab_mod) * tab_batch_stride : nullptr;
-  const PairSrc ps = pair_src<FIRST>(tb, FIRST ? entries + (size_t)b * ent_stride : nullptr,
-                                     FIRST ? nullptr : pin + (size_t)b * pin_stride, sidx & 0x7fffffffu, (sidx >> 31) != 0);
-  int kind;
-  stg_fq(div_all + (size_t)b * div_stride + o, pair_divisor(ps, kind));
-}
-
-__global__ void __launch_bounds__(128) k_tree_inverse(const uint32_t *__restrict__ off_out_all, Fq *div_all, size_t div_stride,
-                                                      Fq *park_all, size_t park_stride, uint32_t nbuckets, uint32_t group) {
-  const uint32_t b = blockIdx.y;
-  const uint32_t total = off_out_all[(size_t)b * (nbuckets + 1) + nbuckets];
-  const uint32_t o0 = (blockIdx.x * 128u + threadIdx.x) * group;
-  if (o0 >= total) return;
-  const uint32_t cnt = min(group, total - o0);
-  Fq *d = div_all + (size_t)b * div_stride + o0, *park = park_all + (size_t)b * park_stride + o0;
-  Fq acc = Fq::one();
-  for (uint32_t i = 0; i < cnt; i++) {
-    acc = acc * d[i];
-    stg_fq(park + i, acc);
-  }
-  Fq inv = acc.inv();
-  for (uint32_t i = cnt; i-- > 0;) {
-    const Fq prev = i ? park[i - 1] : Fq::one();
-    const Fq di = d[i];
-    stg_fq(d + i, inv * prev);
-    inv = inv * di;
-  }
-}
-
-template <bool FIRST>
-__global__ void __launch_bounds__(256) k_tree_add(const Affine<Fq> *tab, size_t tab_batch_stride, uint32_t tab_mod,
-                                                  uint32_t item0, const uint32_t *__restrict__ entries, size_t ent_stride,
-                                                  const Affine<Fq> *pin, size_t pin_stride,
-                                                  const uint32_t *__restrict__ off_out_all, const uint32_t *__restrict__ src_all,
-                                                  size_t src_stride, const Fq *__restrict__ dinv_all, size_t div_stride,
-                                                  Affine<Fq> *pout_all, size_t pout_stride, uint32_t nbuckets) {
-  const uint32_t b = blockIdx.y, o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= off_out_all[(size_t)b * (nbuckets + 1) + nbuckets]) return;
-  const uint32_t sidx = src_all[(size_t)b * src_stride + o];
-  const Affine<Fq> *tb = FIRST ? tab + (size_t)((item0 + b) % tab_mod) * tab_batch_stride : nullptr;
-  const PairSrc s = pair_src<FIRST>(tb, FIRST ? entries + (size_t)b * ent_stride : nullptr,
-                                    FIRST ? nullptr : pin + (size_t)b * pin_stride, sidx & 0x7fffffffu, (sidx >> 31) != 0);
-  int kind;
-  (void)pair_divisor(s, kind);
-  const Fq dinv = ldg_fq(dinv_all + (size_t)b * div_stride + o);
-  Affine<Fq> r;
-  Fq x1 = ldg_fq(&s.p1->x), y1 = ldg_fq(&s.p1->y);
-  if (s.neg1) y1 = y1.neg();
-  if (kind == 0 || kind == 4) {
-    Fq x2, lam;
-    if (kind == 0) {
-      x2 = ldg_fq(&s.p2->x);
-      Fq y2 = ldg_fq(&s.p2->y);
-      if (s.neg2) y2 = y2.neg();
-      lam = (y2 - y1) * dinv;
-    } else {
-      x2 = x1;
-      const Fq xx = x1 * x1;
-      lam = (xx.dbl() + xx) * dinv;
-    }
-    r.x = lam * lam - x1 - x2;
-    r.y = lam * (x1 - r.x) - y1;
-  } else if (kind == 1 || kind == 3) {
-    r.x = x1; r.y = y1;
-  } else if (kind == 2) {
-    r.x = ldg_fq(&s.p2->x);
-    r.y = ldg_fq(&s.p2->y);
-    if (s.neg2) r.y = r.y.neg();
-  } else {
-    r.x = Fq::zero(); r.y = Fq::zero();
-  }
-  stg_pod(pout_all + (size_t)b * pout_stride + o, r);
-}
-
 // XYZZ tail: thread = bucket, summing its remaining affine points (list of the last level)
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_accumulate_pts(const Affine<Fq> *pts_all, size_t pts_stride,
@@ -923,8 +819,6 @@ cudaError_t MsmAffineWs::alloc(uint32_t n_entries, uint32_t batch_, MsmCfg cfg) 
   if (buckets < 1024 || buckets % 1024 || buckets / 1024 > 32) return cudaErrorInvalidValue;
   cap_a = ((size_t)n_entries + buckets) / 2 + 1;
   cap_b = (cap_a + buckets) / 2 + 1;
-  const char *ve = getenv("ZKB_AFFINE");
-  if (ve && ve[0] == '2') version = 2;
   const char *lv = getenv("ZKB_AFFINE_LEVELS");
   if (lv && atoi(lv) >= 1 && atoi(lv) <= MAX_LEVELS) levels = atoi(lv);
   const char *gr = getenv("ZKB_AFFINE_GROUP");   // "512" or "512,256,128"
@@ -939,19 +833,15 @@ cudaError_t MsmAffineWs::alloc(uint32_t n_entries, uint32_t batch_, MsmCfg cfg) 
   CK(cudaMalloc(&pb, (size_t)batch * cap_b * sizeof(Affine<Fq>)));
   CK(cudaMalloc(&park, (size_t)batch * cap_a * sizeof(Fq)));
   CK(cudaMalloc(&lvl_off, (size_t)MAX_LEVELS * batch * (buckets + 1) * 4));
-  if (version == 2) {
-    CK(cudaMalloc(&divs, (size_t)batch * cap_a * sizeof(Fq)));
-    CK(cudaMalloc(&src, (size_t)batch * cap_a * 4));
-  }
   return cudaSuccess;
 }
 void MsmAffineWs::free_all() {
-  cudaFree(pa); cudaFree(pb); cudaFree(park); cudaFree(lvl_off); cudaFree(divs); cudaFree(src);
-  pa = pb = nullptr; park = nullptr; lvl_off = nullptr; divs = nullptr; src = nullptr;
+  cudaFree(pa); cudaFree(pb); cudaFree(park); cudaFree(lvl_off);
+  pa = pb = nullptr; park = nullptr; lvl_off = nullptr;
 }
 int msm_affine_launches(const MsmAffineWs &ws, uint32_t nbatch) {
   const uint32_t subs = ws.batch ? (nbatch + ws.batch - 1) / ws.batch : 1;
-  return (int)subs * (1 + ws.levels * (ws.version == 2 ? 4 : 1) + 1);
+  return (int)subs * (1 + ws.levels + 1);
 }
 
 cudaError_t msm_accumulate_affine(const MsmSort &sort, const MsmTable<Fq> &table, uint32_t nbatch, MsmWork<Fq> &work,
@@ -979,26 +869,7 @@ cudaError_t msm_accumulate_affine(const MsmSort &sort, const MsmTable<Fq> &table
       const size_t cap_out = (cap_in + nb) / 2 + 1;           // upper bound of this level's outputs per item
       const uint32_t g = ws.group[l];
       dim3 grid((unsigned)((cap_out + (size_t)g * 128 - 1) / ((size_t)g * 128)), cnt);
-      if (ws.version == 2) {
-        Fq *park = l == 0 ? reinterpret_cast<Fq *>(ws.pb) : ws.park;
-        const size_t park_stride = l == 0 ? ws.cap_b * 2 : ws.cap_b;
-        const uint32_t *ent = sort.entries + (size_t)b0 * ent_stride;
-        dim3 gout((unsigned)((cap_out + 255) / 256), cnt);
-        k_tree_index<<<dim3((nb + 127) / 128, cnt), 128, 0, st>>>(off_in, off_out, ws.src, ws.cap_a, nb);
-        if (l == 0)
-          k_tree_div<true><<<gout, 256, 0, st>>>(table.tab, tab_batch_stride, tab_mod, b0, ent, ent_stride, nullptr, 0, off_out,
-                                                  ws.src, ws.cap_a, ws.divs, ws.cap_a, nb);
-        else
-          k_tree_div<false><<<gout, 256, 0, st>>>(nullptr, 0, 1, 0, nullptr, 0, pin, pin_stride, off_out, ws.src, ws.cap_a,
-                                                   ws.divs, ws.cap_a, nb);
-        k_tree_inverse<<<grid, 128, 0, st>>>(off_out, ws.divs, ws.cap_a, park, park_stride, nb, g);
-        if (l == 0)
-          k_tree_add<true><<<gout, 256, 0, st>>>(table.tab, tab_batch_stride, tab_mod, b0, ent, ent_stride, nullptr, 0, off_out,
-                                                  ws.src, ws.cap_a, ws.divs, ws.cap_a, pout, pout_stride, nb);
-        else
-          k_tree_add<false><<<gout, 256, 0, st>>>(nullptr, 0, 1, 0, nullptr, 0, pin, pin_stride, off_out, ws.src, ws.cap_a,
-                                                   ws.divs, ws.cap_a, pout, pout_stride, nb);
-      } else if (l == 0)
+      if (l == 0)
         k_affine_level<true><<<grid, 128, 0, st>>>(table.tab, tab_batch_stride, tab_mod, b0, sort.entries + (size_t)b0 * ent_stride,
                                                     ent_stride, nullptr, 0, off_in, off_out, pout, pout_stride,
                                                     reinterpret_cast<Fq *>(ws.pb), ws.cap_b * 2, nb, g);

@@ -80,9 +80,6 @@ struct MsmAffineWs {
   Affine<Fq> *pa = nullptr, *pb = nullptr;
   Fq *park = nullptr;                // [batch][cap_b] parked prefix products of levels >= 1 (level 0 parks in pb)
   uint32_t *lvl_off = nullptr;       // [MAX_LEVELS][batch][buckets + 1] exclusive scans of the per-level list lengths
-  int version = 1;                   // 1: one long-running thread per group; 2: index / divisor / inverse / add kernels
-  Fq *divs = nullptr;                // version 2: [batch][cap_a] divisors, inverted in place
-  uint32_t *src = nullptr;           // version 2: [batch][cap_a] operand position of every output of the level
   cudaError_t alloc(uint32_t n_entries, uint32_t batch, MsmCfg cfg);
   void free_all();
 };

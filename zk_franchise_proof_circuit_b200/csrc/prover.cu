@@ -789,7 +789,7 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
   c->ctx = ctx;
   c->n_vars = z.n_vars; c->n_public = z.n_public; c->domain = z.domain; c->power = z.power;
   c->dense = (flags & 1u) != 0 || env_u32("ZKB_DENSE", 0) != 0;
-  { const char *a = getenv("ZKB_AFFINE"); c->affine = a && (a[0] == '1' || a[0] == '2'); }
+  { const char *a = getenv("ZKB_AFFINE"); c->affine = a && a[0] == '1'; }
   cudaStream_t st = ctx->stream;
   memset(&c->L, 0, sizeof c->L);
 

@@ -164,7 +164,6 @@ static int raw_msm(const void *bases, size_t n, const void *scalars, int nbatch,
       }
       if (flags & 1u) {                      // bucket lists through the batched-affine pair tree
         MsmAffineWs ws;
-        if (flags & 4u) ws.version = 2;
         CKR(ws.alloc((uint32_t)n * (uint32_t)cfg.windows, nbatch > 2 ? 2 : nbatch, cfg), "pair tree alloc");   // 3 items: two sub-batches
         if ((flags >> 8) & 15u) ws.levels = (int)((flags >> 8) & 15u) > MsmAffineWs::MAX_LEVELS ? MsmAffineWs::MAX_LEVELS : (int)((flags >> 8) & 15u);
         if (flags >> 16) for (int l = 0; l < MsmAffineWs::MAX_LEVELS; l++) ws.group[l] = flags >> 16;

@@ -58,7 +58,7 @@ def _msm(fn, psize, bases, scalars, timing):
     return (out, kms.value, tms.value) if timing else out
 
 
-def msm_g1(bases, scalars, timing=False, pair_tree=False, levels=0, group=0, variable_base=False, tree_version=1):
+def msm_g1(bases, scalars, timing=False, pair_tree=False, levels=0, group=0, variable_base=False):
     """bases: uint8[n, 64] canonical affine (zeros = infinity); scalars: uint8[(nbatch,) n, 32].
     pair_tree: sum the bucket lists with the batched-affine pair tree (zkb_raw_msm_g1_ex flag 1)."""
     if not pair_tree and not variable_base:
@@ -66,7 +66,7 @@ def msm_g1(bases, scalars, timing=False, pair_tree=False, levels=0, group=0, var
     fn = _native.lib().zkb_raw_msm_g1_ex
     fn.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                    ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_uint32]
-    flags = (2 if variable_base else 1) | (4 if tree_version == 2 else 0) | (levels << 8) | (group << 16)
+    flags = (2 if variable_base else 1) | (levels << 8) | (group << 16)
     return _msm(lambda *a: fn(*a, flags), 64, bases, scalars, timing)
 
 
