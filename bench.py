@@ -570,8 +570,10 @@ def run_ours(args, rank, world, local_rank):
                 + 462889 + 2 * c.domain                                              # buildABC (nnz) + join
                 + 2 * 32768 * 14 + 3 * 2 * 4096 * 14 + 2 * 4096 * 14 * 3             # bucket reductions: H, A/B1/C, B2 (x3 Fq)
                 + 2.0e4 + 8.0e3)                                                     # witness (levels above the leaf), assembly
-    roofline = {"bound": "imad", "kernel": "G1 bucket accumulation: k_affine_level (H MSM pair tree, batched-affine adds) + "
-                                           "k_accumulate<Fq> / k_accumulate_pts (XYZZ mixed adds)",
+    pair_tree = work["g1_affine_adds_per_proof"] > 0
+    roofline = {"bound": "imad", "kernel": ("G1 bucket accumulation: k_affine_level (H MSM pair tree, batched-affine adds, ZKB_AFFINE=1) + "
+                                           "k_accumulate<Fq> / k_accumulate_pts (XYZZ mixed adds)") if pair_tree else
+                                          "k_accumulate<Fq> (G1 bucket accumulation, XYZZ mixed adds)",
                 "executed_per_proof": {"xyzz_madds": work["g1_madds_per_proof"], "affine_adds": work["g1_affine_adds_per_proof"],
                                        "inversions": work["g1_inversions_per_proof"], "modmul": g1_modmul_per_proof,
                                        "modmul_if_all_xyzz": (work["g1_madds_per_proof"] + work["g1_affine_adds_per_proof"]) * 10},

@@ -1,5 +1,7 @@
 #!/bin/bash
-# round 2, GPU run 6: full suite on one GPU, bench, raw sweep with the variable-base column, ncu launch list + captures
+# Full validation on one B200 (what profiles/r02_* were made with): GPU test suite, bench, raw sweep with the
+# variable-base column, ncu launch list + full captures of the accumulation / NTT kernels.
+#   gpurun --timeout 4200 -- "bash tools/gpu_validate.sh"
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 T="--timeout 240 --timeout-method=thread"
