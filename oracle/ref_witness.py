@@ -62,6 +62,42 @@ def witness(inputs: dict, sanity=True):
     return code, out
 
 
+class RefWasm:
+    """A second transpiled witness calculator beside the census one (oracle/_ref/<sub>/lib<name>.so + census_wasm.mem):
+    the SMTVerifier program of oracle/make_smt_wasm.py, built by `make ref_smt`."""
+
+    def __init__(self, sub="smt", libname="libsmt_wasm.so"):
+        self.dir = os.path.join(REF_DIR, sub)
+        self.path = os.path.join(self.dir, libname)
+        self._lib = None
+
+    def available(self):
+        return os.path.exists(self.path) and os.path.exists(os.path.join(self.dir, "census_wasm.mem"))
+
+    def lib(self):
+        if self._lib is None:
+            L = ctypes.CDLL(self.path)
+            L.wc_load.argtypes = [ctypes.c_char_p]
+            L.wc_witness.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+            rc = L.wc_load(os.path.join(self.dir, "census_wasm.mem").encode())
+            if rc != 0:
+                raise RuntimeError(f"wc_load failed: {rc}")
+            self._lib = L
+        return self._lib
+
+    def witness(self, inputs: dict, sanity=True):
+        L = self.lib()
+        flat = flatten_inputs(inputs)
+        n = len(flat)
+        hashes = np.array([f[0] for f in flat], dtype=np.uint64)
+        idx = np.array([f[1] for f in flat], dtype=np.uint32)
+        vals = np.frombuffer(b"".join(f[2].to_bytes(32, "little") for f in flat), dtype=np.uint32).copy()
+        nw = L.wc_witness_size()
+        out = np.zeros((nw, 32), dtype=np.uint8)
+        code = L.wc_witness(n, hashes.ctypes.data, idx.ctypes.data, vals.ctypes.data, out.ctypes.data, 1 if sanity else 0)
+        return code, out
+
+
 if __name__ == "__main__":
     import hashlib
     import sys

@@ -310,3 +310,50 @@ def test_pair_tree_prover_path_matches_oracle(files, monkeypatch):
             assert proofs[i].tobytes() == H.zkey_ref().prove(w, H.R_FIXED, H.S_FIXED), f"voter {i}"
     finally:
         c.close()
+
+
+def test_second_circuit_proves_end_to_end():
+    """A wasm that is NOT census.circom (zk_census_test.go:27-34 takes other circuit names): the
+    SMTVerifier(160) program of oracle/make_smt_wasm.py with its own dev key, in the reference's on-disk layout
+    (artifacts/smtVerifier/dev/160).  zkb_load_circuit picks the generic witness path by itself; the witness equals the
+    wasm run natively (committed KAT + oracle/_ref/smt), the proof equals the CPU oracle's and verifies under the key
+    zkb_export_vkey writes; a wrong root is exception 4."""
+    import make_smt_wasm as SW
+    import ref_witness as RW
+    from zk_franchise_proof_circuit_b200 import prover
+    from zk_franchise_proof_circuit_b200.prover import NativeError
+    d = os.path.join(H.ROOT, "artifacts", "smtVerifier", "dev", "160")
+    if not os.path.exists(d + "/proving_key.zkey"):
+        pytest.skip("artifacts/smtVerifier not generated (run __graft_entry__.build())")
+    zkey, wasm = open(d + "/proving_key.zkey", "rb").read(), open(d + "/circuit.wasm", "rb").read()
+    c = prover.load(zkey, wasm)                       # no flag: the wasm is simply not the census program
+    try:
+        assert (c.n_vars, c.n_public, c.n_inputs) == (82754, 2, 169)
+        kat = json.load(open(H.GOLDEN + "/smt_verifier_kat.json"))
+        voters = [H.fixture_inputs()] + list(H.voters(2)) + [H.deep_voters()[0]]
+        docs = [json.dumps(SW.smt_inputs(v)) for v in voters]
+        for i, doc in enumerate(docs):
+            w = H.wtns_payload(c.witness(doc), c.n_vars)
+            assert H.sha(w.tobytes()) == kat["witness_sha256"][i], f"case {i}"
+        c.set_blinding(H.R_FIXED, H.S_FIXED)
+        proofs, pubs, status = c.fullprove_batch(docs)
+        c.set_blinding(None, None)
+        assert status == [0] * 4
+        vkey = prover.export_vkey(zkey)
+        assert vkey == open(d + "/verification_key.json", "rb").read()
+        assert prover.verify_batch(vkey, pubs, proofs) == [1] * 4
+        assert json.loads(pubs[0]) == ["1", voters[0]["censusRoot"]]
+        ref = RW.RefWasm()
+        if ref.available():
+            zk = O.ZKeyRef(zkey)
+            for i in (0, 3):
+                rc, w = ref.witness(SW.smt_inputs(voters[i]))
+                assert rc == 0 and O.proof_bin(json.loads(proofs[i])) == zk.prove(w, H.R_FIXED, H.S_FIXED), f"proof {i}"
+        bad = SW.smt_inputs(voters[0])
+        bad["root"] = "7"
+        with pytest.raises(NativeError) as ei:
+            c.fullprove(json.dumps(bad))
+        assert ei.value.code == 4
+    finally:
+        c.close()
+        prover._circuits.clear()

@@ -98,3 +98,59 @@ def test_generic_witness_asserts_match_wasm(tape):
         assert code == 4, patch
         if RW.available():
             assert RW.witness(bad)[0] == 4
+
+
+# ---- a second circom program: SMTVerifier(160) as the main component (oracle/make_smt_wasm.py) -----------------------
+
+@pytest.fixture(scope="module")
+def smt_tape(art_dir, tmp_path_factory):
+    import make_smt_wasm as SW
+    src = os.path.join(H.ROOT, "tests", "host_emul", "tape_host.cc")
+    so = str(tmp_path_factory.mktemp("tape_smt") / "libtape_host.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
+    L = ctypes.CDLL(so)
+    L.tape_host_build.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+    L.tape_host_input.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+    L.tape_host_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    wasm = SW.patch(open(art_dir + "/circuit.wasm", "rb").read())
+    buf = (ctypes.c_char * len(wasm)).from_buffer_copy(wasm)
+    info = np.zeros(8, dtype=np.uint32)
+    err = ctypes.create_string_buffer(512)
+    assert L.tape_host_build(ctypes.addressof(buf), len(wasm), info.ctypes.data, err, 512) == 0, err.value
+    return L, info, wasm
+
+
+def test_second_program_is_a_different_circuit(smt_tape):
+    L, info, wasm = smt_tape
+    n_inputs, n_wires, n_slots, n_ops, n_levels, n_consts, n_asserts, n_selects = (int(x) for x in info)
+    assert (n_inputs, n_wires) == (169, 82754)
+    assert 150_000 < n_ops < 250_000 and n_selects == 326 and n_asserts > 500
+    kat = json.load(open(H.GOLDEN + "/smt_verifier_kat.json"))
+    assert H.sha(wasm) == kat["wasm_sha256"]
+    size = ctypes.c_uint32(0)
+    assert L.tape_host_input(b"siblings", ctypes.byref(size)) == 2 and size.value == 161
+    assert L.tape_host_input(b"censusSiblings", ctypes.byref(size)) == -1
+
+
+def test_second_program_witness_matches_native_run_and_kat(smt_tape):
+    """The SMTVerifier program through the generic path == the same wasm transpiled to C and run natively
+    (oracle/_ref/smt, `make ref_smt`) == the committed known answers; a wrong root raises exception 4 in both."""
+    import make_smt_wasm as SW
+    import ref_witness as RW
+    L, info, _ = smt_tape
+    kat = json.load(open(H.GOLDEN + "/smt_verifier_kat.json"))
+    ref = RW.RefWasm()
+    voters = [H.fixture_inputs()] + list(H.voters(2)) + [H.deep_voters()[0]]
+    for i, v in enumerate(voters):
+        inp = SW.smt_inputs(v)
+        code, w = _eval(L, info, inp)
+        assert code == 0
+        assert H.sha(w.tobytes()) == kat["witness_sha256"][i], f"case {i}"
+        if ref.available():
+            rc, rw = ref.witness(inp)
+            assert rc == 0 and np.array_equal(rw, w)
+    bad = SW.smt_inputs(voters[0])
+    bad["root"] = "7"
+    assert _eval(L, info, bad)[0] == 4
+    if ref.available():
+        assert ref.witness(bad)[0] == 4
