@@ -624,7 +624,8 @@ def run_ours(args, rank, world, local_rank):
         generic = {"proofs_per_s": rate_generic, "load_s": round(t_gen, 2), "status_ok": int(sum(1 for x in sg if x == 0)),
                    "verified": int(sum(prover.verify_batch(vkey, qg, pg))), "proofs": nd,
                    "what": "ZKB_LOAD_GENERIC_WITNESS: witness by the straight-line program extracted from circuit.wasm at load "
-                           "time (one warp per proof), no template shortcut; zkb_fullprove_batch end to end"}
+                           "time (one warp per proof, whole group in one launch); witness MSMs over the difference to the "
+                           "program's all-zero-input witness (16-bit windows); zkb_fullprove_batch end to end"}
         cg.close()
         prover._circuits.clear()
         shortcut = {"what": "SURVEY 8a W7: ~91 % of the wires are identical in every proof below the leaf's level; the four "

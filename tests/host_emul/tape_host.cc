@@ -61,3 +61,68 @@ int tape_host_eval(const uint8_t *inputs, uint8_t *witness) {
 }
 
 }  // extern "C"
+
+// ---- the reference wasm's OWN field runtime as the oracle of tape_ops.cuh ------------------------------------------
+// The census program only uses part of the operation set.  Every operation of tape_ops.cuh is therefore also compared
+// with the wasm's Fr_* function of the same name, executed concretely by the interpreter of wasm_symexec.cc on the
+// same operands (the mechanism the extractor uses for constant sub-expressions).
+static Machine *g_rt = nullptr;
+static std::vector<uint8_t> g_rt_wasm;
+
+extern "C" {
+
+int tape_host_rt_load(const uint8_t *wasm, size_t len) {
+  delete g_rt;
+  g_rt_wasm.assign(wasm, wasm + len);
+  g_rt = new Machine();
+  g_rt->bin = g_rt_wasm.data();
+  g_rt->bin_len = g_rt_wasm.size();
+  std::string err;
+  if (!g_rt->parse(err)) { delete g_rt; g_rt = nullptr; return 1; }
+  return 0;
+}
+
+// out = Fr_<name>(a, b) as the wasm computes it; a, b, out canonical 32-byte little-endian.  unary: b ignored.
+int tape_host_rt_op(const char *name, int unary, const uint8_t *a32, const uint8_t *b32, uint8_t *out32) {
+  if (!g_rt) return 1;
+  Machine &m = *g_rt;
+  uint32_t fi = ~0u;
+  for (auto &kv : m.names) if (kv.second == name) fi = kv.first;
+  if (fi == ~0u) return 2;
+  const uint32_t base = (uint32_t)m.mem.size() - 4096, pa = base, pb = base + 64, pd = base + 128;
+  auto put = [&](uint32_t addr, const uint8_t *v) {
+    uint32_t hdr[2] = {0, 0x80000000u};              // long form, not Montgomery
+    memcpy(m.mem.data() + addr, hdr, 8);
+    memcpy(m.mem.data() + addr + 8, v, 32);
+  };
+  put(pa, a32);
+  put(pb, b32);
+  memset(m.mem.data() + pd, 0, 40);
+  try {
+    std::vector<Val> args;
+    args.push_back(Val{pd, 0});
+    args.push_back(Val{pa, 0});
+    if (!unary) args.push_back(Val{pb, 0});
+    Val res{0, 0};
+    m.depth = 0;
+    m.call(fi, args, res);
+    uint32_t v[8];
+    m.record_value(pd, v);
+    memcpy(out32, v, 32);
+  } catch (Unsupported &) {
+    return 3;
+  }
+  return 0;
+}
+
+// the same operation through tape_ops.cuh (operands converted to Montgomery form and back, as the evaluators do)
+int tape_host_apply(int op, const uint8_t *a32, const uint8_t *b32, const uint8_t *c32, uint8_t *out32) {
+  Fr a, b, c;
+  memcpy(a.v, a32, 32); memcpy(b.v, b32, 32); memcpy(c.v, c32, 32);
+  bool failed = false;
+  Fr r = tape_apply((uint8_t)op, a.to_mont(), b.to_mont(), c.to_mont(), &failed).from_mont();
+  memcpy(out32, r.v, 32);
+  return failed ? 4 : 0;
+}
+
+}  // extern "C"

@@ -154,3 +154,37 @@ def test_second_program_witness_matches_native_run_and_kat(smt_tape):
     assert _eval(L, info, bad)[0] == 4
     if ref.available():
         assert ref.witness(bad)[0] == 4
+
+
+def test_every_tape_operation_matches_the_wasm_runtime(tape, art_dir):
+    """tape_ops.cuh (what the GPU lanes execute) against the reference wasm's own Fr_* functions run by the interpreter,
+    for every operation the extractor can emit - including those the census program never uses - on random and edge
+    operands (0, 1, r-1, the sign boundary (r-1)/2, shift amounts around 254 and negative ones)."""
+    L, _ = tape
+    wasm = open(art_dir + "/circuit.wasm", "rb").read()
+    buf = (ctypes.c_char * len(wasm)).from_buffer_copy(wasm)
+    L.tape_host_rt_load.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    L.tape_host_rt_op.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.tape_host_apply.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    assert L.tape_host_rt_load(ctypes.addressof(buf), len(wasm)) == 0
+    P = H.census_gen.P
+    ops = [("Fr_add", 0, 0), ("Fr_sub", 1, 0), ("Fr_mul", 2, 0), ("Fr_neg", 3, 1), ("Fr_div", 4, 0), ("Fr_inv", 5, 1),
+           ("Fr_eq", 6, 0), ("Fr_neq", 7, 0), ("Fr_lt", 8, 0), ("Fr_gt", 9, 0), ("Fr_leq", 10, 0), ("Fr_geq", 11, 0),
+           ("Fr_land", 12, 0), ("Fr_lor", 13, 0), ("Fr_lnot", 14, 1), ("Fr_shr", 15, 0), ("Fr_shl", 16, 0),
+           ("Fr_band", 17, 0), ("Fr_bor", 18, 0), ("Fr_bxor", 19, 0), ("Fr_bnot", 20, 1)]
+    import random
+    rnd = random.Random(7)
+    edge = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, 1 << 253, (1 << 253) - 1, 12345]
+    shifts = [0, 1, 31, 32, 63, 64, 200, 253, 254, 255, 300, P - 1, P - 5, P - 253, P - 254, P - 255]
+    le = lambda x: (ctypes.c_uint8 * 32).from_buffer_copy(int(x).to_bytes(32, "little"))
+    for name, op, unary in ops:
+        pairs = [(a, b) for a in edge for b in edge] + [(rnd.randrange(P), rnd.randrange(P)) for _ in range(40)]
+        if name in ("Fr_shr", "Fr_shl"):
+            pairs = [(a, s) for a in edge + [rnd.randrange(P) for _ in range(6)] for s in shifts]
+        if name in ("Fr_div", "Fr_inv"):
+            pairs = [(a, b) for a, b in pairs[:60]]
+        for a, b in pairs:
+            want, got = (ctypes.c_uint8 * 32)(), (ctypes.c_uint8 * 32)()
+            assert L.tape_host_rt_op(name.encode(), unary, le(a), le(b), want) == 0, name
+            L.tape_host_apply(op, le(a), le(b), le(0), got)
+            assert bytes(got) == bytes(want), (name, a, b, int.from_bytes(bytes(got), "little"), int.from_bytes(bytes(want), "little"))

@@ -895,6 +895,23 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
     c->gen_first_signal = prog.first_input_signal;
     c->L.n_inputs = prog.n_inputs;
     c->L.n_wires = prog.n_wires;
+    // The template trick of SURVEY 8a W7 needs nothing census-specific: sum_i w_i P_i = sum_i t_i P_i + sum_i (w_i - t_i) P_i
+    // holds for ANY vector t.  t = the program's witness on all-zero inputs (its asserts may fail; the values are still
+    // defined); wires a proof shares with it drop out of the four witness MSMs.  Single-range keys only: a sparse
+    // difference cannot be assumed for an arbitrary circuit, and a large dense one needs the point-range split.
+    if (!c->dense && z.n_vars <= (1u << 18)) {
+      Fr *zin = nullptr, *zslots = nullptr;
+      int *zst = nullptr;
+      CKR(cudaMalloc(&c->tmpl, (size_t)c->n_vars * 32), "alloc template");
+      CKR(cudaMalloc(&zin, (size_t)prog.n_inputs * 32), "alloc");
+      CKR(cudaMalloc(&zslots, (size_t)prog.n_slots * 32), "alloc");
+      CKR(cudaMalloc(&zst, 4), "alloc");
+      CKR(cudaMemsetAsync(zin, 0, (size_t)prog.n_inputs * 32, st), "memset");
+      CKR(cudaMemsetAsync(zst, 0, 4, st), "memset");
+      CKR(tape_eval(c->tape, zin, zslots, c->tmpl, zst, 1, st), "template witness (tape)");
+      CKR(cudaStreamSynchronize(st), "template witness");
+      cudaFree(zin); cudaFree(zslots); cudaFree(zst);
+    }
   }
 
   // coefficient matrices (CSR by row)
@@ -936,7 +953,9 @@ static int load_circuit(Ctx *ctx, const uint8_t *zkey, size_t zkey_len, const ui
     Affine<Fq> *d1 = nullptr;
     Affine<Fq2> *d2 = nullptr;
     const bool use_tmpl = c->tmpl && !c->dense;
-    c->cfgW = msm_cfg((int)env_u32("ZKB_C_WITNESS", use_tmpl ? 13 : 16));
+    // census: a few thousand differing wires -> 13-bit windows (4,096 buckets); a generic program's difference may be
+    // dense -> 16-bit windows whatever the template saves
+    c->cfgW = msm_cfg((int)env_u32("ZKB_C_WITNESS", use_tmpl && !c->generic ? 13 : 16));
     c->cfgH = msm_cfg((int)env_u32("ZKB_C_H", 16));
     // point ranges (see Circuit::subW): 2^17 points each once a key has more than 2^18; the last range is padded
     // with points at infinity
