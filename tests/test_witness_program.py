@@ -188,3 +188,27 @@ def test_every_tape_operation_matches_the_wasm_runtime(tape, art_dir):
             assert L.tape_host_rt_op(name.encode(), unary, le(a), le(b), want) == 0, name
             L.tape_host_apply(op, le(a), le(b), le(0), got)
             assert bytes(got) == bytes(want), (name, a, b, int.from_bytes(bytes(got), "little"), int.from_bytes(bytes(want), "little"))
+
+
+def test_extractor_rejects_what_it_cannot_run(tape, art_dir):
+    """not-a-wasm, a truncated wasm and a wasm without its name section are reported with a message (the product turns
+    that into ZKB_UNSUPPORTED_CIRCUIT), never a crash or a silent fallback"""
+    L, _ = tape
+    wasm = open(art_dir + "/circuit.wasm", "rb").read()
+
+    def build(b):
+        buf = (ctypes.c_char * len(b)).from_buffer_copy(b)
+        info = np.zeros(8, dtype=np.uint32)
+        err = ctypes.create_string_buffer(512)
+        return L.tape_host_build(ctypes.addressof(buf), len(b), info.ctypes.data, err, 512), err.value.decode()
+    rc, msg = build(b"\0asm\x01\0\0\0" + bytes(32))
+    assert rc == 1 and msg
+    rc, msg = build(wasm[:len(wasm) // 2])
+    assert rc == 1 and msg
+    cut = wasm.rfind(b"\x04name")                 # the custom "name" section is the last one circom emits
+    assert cut > 0
+    rc, msg = build(wasm[:cut - 4])               # section header = id 0x00 + 3-byte size before the name string
+    assert rc == 1 and "name" in msg
+    # the harness still works afterwards
+    rc, msg = build(wasm)
+    assert rc == 0

@@ -1512,7 +1512,6 @@ extern "C" int zkb_census_tree(zkb_circuit *h, int n_keys, const void *keys32, c
     if (memcmp(K + (size_t)ord[i] * 32, K + (size_t)ord[i - 1] * 32, 32) == 0) { set_error("census_tree: duplicate key"); return ZKB_ERROR; }
   struct Node { uint32_t lo, hi; int depth; int left, right; };          // children: node index, -1 = empty
   std::vector<Node> nodes;
-  std::vector<std::pair<int, int>> stack;                                 // iterative build (node index, unused)
   nodes.push_back({0, n, 0, -1, -1});
   int max_depth = 0;
   for (size_t q = 0; q < nodes.size(); q++) {

@@ -61,10 +61,10 @@ __global__ void __launch_bounds__(128) k_tape_eval(TapeDev T, const Fr *__restri
   // The operations of level l + 1 (and the level table two ahead) are fetched while level l computes: a level is a
   // chain tape entry -> operands -> product -> store, and the first link does not depend on the previous level.
   uint32_t beg = T.level_start[0], end = T.level_start[1];
-  TapeOp cur = T.tape[min(beg + lane, T.n_ops - 1)];
+  TapeOp cur = T.tape[beg + lane];                       // (the tape is padded by 64 entries: no clamping needed)
   for (uint32_t l = 0; l < T.n_levels; l++) {
     const uint32_t nend = T.level_start[min(l + 2, T.n_levels)];
-    const TapeOp nxt = T.tape[min(end + lane, T.n_ops - 1)];
+    const TapeOp nxt = T.tape[end + lane];
     if (beg + lane < end) exec(cur);
     for (uint32_t i = beg + lane + 32; i < end; i += 32) exec(T.tape[i]);     // levels wider than a warp (rare)
     __syncwarp();
@@ -89,7 +89,8 @@ cudaError_t TapeDev::upload(const WitnessProgram &p, cudaStream_t st) {
   n_slots = p.n_slots; n_inputs = p.n_inputs; n_wires = p.n_wires;
   n_ops = (uint32_t)p.tape.size();
   n_consts = (uint32_t)(p.consts.size() / 8);
-  CK(cudaMalloc(&tape, (p.tape.size() + 1) * sizeof(TapeOp)));
+  CK(cudaMalloc(&tape, (p.tape.size() + 64) * sizeof(TapeOp)));          // the evaluator prefetches up to a warp ahead
+  CK(cudaMemsetAsync(tape, 0, (p.tape.size() + 64) * sizeof(TapeOp), st));
   CK(cudaMalloc(&level_start, p.level_start.size() * 4));
   CK(cudaMalloc(&consts, (p.consts.size() + 8) * 4));
   CK(cudaMalloc(&wire_ref, p.wire_ref.size() * 4));

@@ -104,6 +104,10 @@ struct Journal {
 static const uint32_t RMOD[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
                                  0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
 
+// census.circom at 160 levels takes 2.7e8 interpreted instructions; a program that needs 100x that is not a witness
+// calculator this extractor can serve (and a hostile wasm must not hang zkb_load_circuit)
+static const uint64_t kMaxSteps = 30000000000ull;
+
 struct Machine {
   const uint8_t *bin = nullptr;
   size_t bin_len = 0;
@@ -578,7 +582,7 @@ struct Machine {
     };
     while (pc < end) {
       const Ins &in = f.code[pc];
-      steps++;
+      if (++steps > kMaxSteps) throw Unsupported{"the program did not finish within the interpreter's step budget"};
       switch (in.op) {
         case 0x00: throw Unsupported{"unreachable executed"};
         case 0x01: pc++; break;
