@@ -98,8 +98,9 @@ def main():
             "domain_log2": domain.bit_length() - 1, "n_gpus": world, "proof_wall_ms_p50": walls[len(walls) // 2],
             "proof_resident_wall_ms_p50": res_ms,
             "split": "MSMs by point range over the ranks, partial sums pushed to rank 0 over NVLink (CUDA IPC), H scalars "
-                     "computed on every rank" if world > 1 else "none",
-            "what": "zkb_prove_wtns: .wtns in host memory -> proof.json (H2D of the 134 MB witness included)",
+                     "computed on every rank; every rank uploads 1 / N of the witness and gathers the rest from its peers "
+                     "(P2P loads)" if world > 1 else "none",
+            "what": "zkb_prove_wtns: .wtns in host memory -> proof.json (upload of the 134 MB witness included)",
             "device_stage_ms": {k: round(float(v), 2) for k, v in zip(names, st)},
             "device_total_ms": round(float(sum(st)), 2), "verified": True,
             "zkey_mib": round(len(zkey) / 2**20, 1), "host_setup_s": round(t_setup, 1), "key_load_s": round(t_load, 1)}
