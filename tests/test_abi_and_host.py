@@ -206,3 +206,24 @@ def test_census_of_chosen_depth_passes_the_reference_wasm(art_dir):
         v = CT.gen_census_depth(Hasher(), 1, depth, seed=3)[0]
         assert CT.tree_depth(v) == depth
         assert RW.witness(v)[0] == 0
+
+
+def test_reference_arm_under_torchrun_two_ranks(art_dir):
+    """`bench.py --impl reference --gpus 2` launched like the driver launches it: rank 0 alone times the CPU
+    implementation and prints ONE JSON line with the contract's keys, rank 1 exits 0 without work."""
+    import ref_witness as RW
+    if not RW.available():
+        pytest.skip("oracle/_ref not built")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29741", ZKB_REF_SAMPLE="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29741", os.path.join(H.ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["unit"] == "proofs/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("census.circom") and "tree_depth" in d["config"]
