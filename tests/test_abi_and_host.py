@@ -227,3 +227,39 @@ def test_reference_arm_under_torchrun_two_ranks(art_dir):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("census.circom") and "tree_depth" in d["config"]
+
+
+def test_zkey_parser_survives_damaged_keys(art_dir):
+    """truncations and bit flips in the section table / header of a proving key are rejected (or accepted) without
+    reading outside the buffer: zkb_export_vkey and groth16_public_size_for_zkey_buf parse on the host, no GPU needed"""
+    import random
+    L = ctypes.CDLL(LIB)
+    L.groth16_public_size_for_zkey_buf.argtypes = [ctypes.c_void_p, ctypes.c_ulong, ctypes.POINTER(ctypes.c_ulong),
+                                                  ctypes.c_void_p, ctypes.c_ulong]
+    L.zkb_export_vkey.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
+    zkey = open(os.path.join(H.ROOT, "artifacts", "smtVerifier", "dev", "160", "proving_key.zkey"), "rb").read() \
+        if os.path.exists(os.path.join(H.ROOT, "artifacts", "smtVerifier", "dev", "160", "proving_key.zkey")) \
+        else open(art_dir + "/proving_key.zkey", "rb").read()
+    rnd = random.Random(11)
+    err = ctypes.create_string_buffer(256)
+    n = ctypes.c_ulong(0)
+    ok = bad = 0
+    for trial in range(150):
+        z = bytearray(zkey)
+        if trial % 3 == 0:
+            z = z[:rnd.randrange(0, min(len(z), 4096))]                    # truncated inside the header sections
+        elif trial % 3 == 1:
+            z = z[:rnd.randrange(len(z) // 2, len(z))]                      # truncated inside a point section
+        else:
+            for _ in range(4):
+                z[rnd.randrange(0, 2048)] ^= 1 << rnd.randrange(8)         # section ids, lengths, nVars, domain size
+        buf = (ctypes.c_char * max(len(z), 1)).from_buffer_copy(bytes(z) or b"\0")
+        rc = L.groth16_public_size_for_zkey_buf(ctypes.addressof(buf), len(z), ctypes.byref(n), err, 256)
+        assert rc in (0, 1)
+        out = ctypes.create_string_buffer(1 << 16)
+        m = ctypes.c_size_t(1 << 16)
+        rc2 = L.zkb_export_vkey(ctypes.addressof(buf), len(z), out, ctypes.byref(m))
+        assert rc2 in (0, 1, 2)
+        ok += rc == 0
+        bad += rc == 1
+    assert bad > 50 and ok + bad == 150
