@@ -62,6 +62,45 @@ int tape_host_eval(const uint8_t *inputs, uint8_t *witness) {
 
 }  // extern "C"
 
+// ---- the wasm run CONCRETELY by the interpreter (no symbols): an oracle for programs that have no native build ------
+// Drives the circom_runtime protocol (init, writeSharedRWMemory + setInputSignal per input element, getWitness +
+// readSharedRWMemory per wire) on the program tape_host_build was last given.  Every Fr_* call executes the wasm's own
+// code.  returns 0, 4 when the program raised exception 4 (assert / constraint check), 3 for any other trap.
+extern "C" int tape_host_wasm_witness(const uint8_t *wasm, size_t len, const uint8_t *inputs, uint8_t *witness) {
+  if (!g_have) return 1;
+  Machine m;
+  m.bin = wasm;
+  m.bin_len = len;
+  std::string err;
+  if (!m.parse(err)) return 2;
+  m.inputs_marked = true;                               // nothing becomes a symbol
+  try {
+    m.call_export("init", {0});
+    uint32_t flat = 0;
+    for (auto &in : g_prog.inputs)
+      for (uint32_t k = 0; k < in.size; k++, flat++) {
+        for (int j = 0; j < 8; j++) {
+          uint32_t w;
+          memcpy(&w, inputs + 32 * flat + 4 * j, 4);
+          m.call_export("writeSharedRWMemory", {(uint64_t)j, w});
+        }
+        m.call_export("setInputSignal", {in.hash >> 32, in.hash & 0xffffffffu, k});
+      }
+    for (uint32_t w = 0; w < g_prog.n_wires; w++) {
+      m.call_export("getWitness", {w});
+      for (int j = 0; j < 8; j++) {
+        uint64_t v = 0;
+        m.call_export("readSharedRWMemory", {(uint64_t)j}, &v);
+        const uint32_t v32 = (uint32_t)v;
+        memcpy(witness + 32 * w + 4 * j, &v32, 4);
+      }
+    }
+  } catch (Unsupported &u) {
+    return u.why.find("exception 4") != std::string::npos ? 4 : 3;
+  }
+  return 0;
+}
+
 // ---- the reference wasm's OWN field runtime as the oracle of tape_ops.cuh ------------------------------------------
 // The census program only uses part of the operation set.  Every operation of tape_ops.cuh is therefore also compared
 // with the wasm's Fr_* function of the same name, executed concretely by the interpreter of wasm_symexec.cc on the

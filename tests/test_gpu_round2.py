@@ -357,3 +357,47 @@ def test_second_circuit_proves_end_to_end():
     finally:
         c.close()
         prover._circuits.clear()
+
+
+@pytest.mark.gpu
+def test_third_circuit_every_runtime_operation_on_the_gpu():
+    """A SMALL non-census circuit (30 wires, artifacts/opsTest/dev/1, oracle/make_ops_wasm.py): integer division,
+    remainder, power, all comparisons / shifts / bit operations, nested and one-armed conditionals and an assert run
+    as an extracted program on the GPU.  Witness == the committed Python-model KAT (which the wasm, run concretely,
+    also gives: tests/test_witness_program.py); proofs == CPU oracle, verify; a tampered public output does not;
+    a failed assert and a zero divisor are status 4."""
+    from zk_franchise_proof_circuit_b200 import prover
+    d = os.path.join(H.ROOT, "artifacts", "opsTest", "dev", "1")
+    if not os.path.exists(d + "/proving_key.zkey"):
+        pytest.skip("artifacts/opsTest not generated (run __graft_entry__.build())")
+    zkey, wasm = open(d + "/proving_key.zkey", "rb").read(), open(d + "/circuit.wasm", "rb").read()
+    kat = json.load(open(H.GOLDEN + "/ops_program_kat.json"))
+    assert H.sha(wasm) == kat["wasm_sha256"]
+    c = prover.load(zkey, wasm)
+    try:
+        assert (c.n_vars, c.n_public, c.n_inputs) == (30, 26, 3)
+        good = [k for k in kat["cases"] if k["status"] == 0]
+        bad = [k for k in kat["cases"] if k["status"] != 0]
+        docs = [json.dumps({"x": k["x"]}) for k in good]
+        for k, doc in zip(good, docs):
+            w = H.wtns_payload(c.witness(doc), c.n_vars)
+            got = [int.from_bytes(w[i].tobytes(), "little") for i in range(c.n_vars)]
+            assert got == [int(v) for v in k["witness"]], k["x"]
+        c.set_blinding(H.R_FIXED, H.S_FIXED)
+        proofs, pubs, status = c.fullprove_batch(docs + [json.dumps({"x": k["x"]}) for k in bad])
+        c.set_blinding(None, None)
+        assert status == [0] * len(good) + [4] * len(bad)
+        vkey = open(d + "/verification_key.json", "rb").read()
+        assert prover.export_vkey(zkey) == vkey
+        assert prover.verify_batch(vkey, pubs[:len(good)], proofs[:len(good)]) == [1] * len(good)
+        zk = O.ZKeyRef(zkey)
+        for i in (0, 5, len(good) - 1):
+            assert json.loads(pubs[i]) == good[i]["witness"][1:27]
+            w = np.stack([np.frombuffer(int(v).to_bytes(32, "little"), dtype=np.uint8) for v in good[i]["witness"]])
+            assert O.proof_bin(json.loads(proofs[i])) == zk.prove(w, H.R_FIXED, H.S_FIXED), f"proof {i}"
+        tampered = json.loads(pubs[0])
+        tampered[25] = str(int(tampered[25]) + 1)
+        assert prover.verify_batch(vkey, [json.dumps(tampered)], proofs[:1]) == [0]
+    finally:
+        c.close()
+        prover._circuits.clear()

@@ -171,7 +171,8 @@ def test_every_tape_operation_matches_the_wasm_runtime(tape, art_dir):
     ops = [("Fr_add", 0, 0), ("Fr_sub", 1, 0), ("Fr_mul", 2, 0), ("Fr_neg", 3, 1), ("Fr_div", 4, 0), ("Fr_inv", 5, 1),
            ("Fr_eq", 6, 0), ("Fr_neq", 7, 0), ("Fr_lt", 8, 0), ("Fr_gt", 9, 0), ("Fr_leq", 10, 0), ("Fr_geq", 11, 0),
            ("Fr_land", 12, 0), ("Fr_lor", 13, 0), ("Fr_lnot", 14, 1), ("Fr_shr", 15, 0), ("Fr_shl", 16, 0),
-           ("Fr_band", 17, 0), ("Fr_bor", 18, 0), ("Fr_bxor", 19, 0), ("Fr_bnot", 20, 1)]
+           ("Fr_band", 17, 0), ("Fr_bor", 18, 0), ("Fr_bxor", 19, 0), ("Fr_bnot", 20, 1),
+           ("Fr_idiv", 26, 0), ("Fr_mod", 27, 0), ("Fr_pow", 28, 0)]
     import random
     rnd = random.Random(7)
     edge = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, 1 << 253, (1 << 253) - 1, 12345]
@@ -181,12 +182,25 @@ def test_every_tape_operation_matches_the_wasm_runtime(tape, art_dir):
         pairs = [(a, b) for a in edge for b in edge] + [(rnd.randrange(P), rnd.randrange(P)) for _ in range(40)]
         if name in ("Fr_shr", "Fr_shl"):
             pairs = [(a, s) for a in edge + [rnd.randrange(P) for _ in range(6)] for s in shifts]
-        if name in ("Fr_div", "Fr_inv"):
+        if name in ("Fr_div", "Fr_inv", "Fr_pow"):
             pairs = [(a, b) for a, b in pairs[:60]]
+        if name in ("Fr_idiv", "Fr_mod"):
+            pairs += [(rnd.randrange(P), rnd.randrange(1, 1 << k)) for k in (1, 8, 32, 33, 64, 128, 200, 253)]
         for a, b in pairs:
             want, got = (ctypes.c_uint8 * 32)(), (ctypes.c_uint8 * 32)()
+            if name in ("Fr_idiv", "Fr_mod") and b == 0:
+                # the wasm traps on a zero divisor; the tape reports the proof as failed (status 4) instead
+                assert L.tape_host_rt_op(name.encode(), unary, le(a), le(b), want) == 3
+                assert L.tape_host_apply(op, le(a), le(b), le(0), got) == 4
+                continue
             assert L.tape_host_rt_op(name.encode(), unary, le(a), le(b), want) == 0, name
-            L.tape_host_apply(op, le(a), le(b), le(0), got)
+            assert L.tape_host_apply(op, le(a), le(b), le(0), got) == 0
+            if name == "Fr_idiv":
+                assert int.from_bytes(bytes(want), "little") == a // b
+            if name == "Fr_mod":
+                assert int.from_bytes(bytes(want), "little") == a % b
+            if name == "Fr_pow":
+                assert int.from_bytes(bytes(want), "little") == pow(a, b, P)
             assert bytes(got) == bytes(want), (name, a, b, int.from_bytes(bytes(got), "little"), int.from_bytes(bytes(want), "little"))
 
 
@@ -212,3 +226,81 @@ def test_extractor_rejects_what_it_cannot_run(tape, art_dir):
     # the harness still works afterwards
     rc, msg = build(wasm)
     assert rc == 0
+
+
+# ---- third program: every runtime operation, nested conditionals, an assert (oracle/make_ops_wasm.py) ----------------
+
+@pytest.fixture(scope="module")
+def ops_tape(art_dir, tmp_path_factory):
+    import make_ops_wasm as OW
+    src = os.path.join(H.ROOT, "tests", "host_emul", "tape_host.cc")
+    so = str(tmp_path_factory.mktemp("tape_ops") / "libtape_host.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
+    L = ctypes.CDLL(so)
+    L.tape_host_build.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+    L.tape_host_input.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+    L.tape_host_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.tape_host_wasm_witness.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    wasm = OW.build(open(art_dir + "/circuit.wasm", "rb").read())
+    buf = (ctypes.c_char * len(wasm)).from_buffer_copy(wasm)
+    info = np.zeros(8, dtype=np.uint32)
+    err = ctypes.create_string_buffer(512)
+    assert L.tape_host_build(ctypes.addressof(buf), len(wasm), info.ctypes.data, err, 512) == 0, err.value
+    return L, info, wasm, buf
+
+
+def test_third_program_shape(ops_tape):
+    L, info, wasm, _ = ops_tape
+    n_inputs, n_wires, n_slots, n_ops, n_levels, n_consts, n_asserts, n_selects = (int(x) for x in info)
+    assert (n_inputs, n_wires, n_asserts) == (3, 30, 1)
+    assert n_selects >= 3                         # the nested pair + the one-armed conditional
+    assert 30 <= n_ops <= 60 and n_levels <= 6
+    kat = json.load(open(H.GOLDEN + "/ops_program_kat.json"))
+    assert H.sha(wasm) == kat["wasm_sha256"]
+    size = ctypes.c_uint32(0)
+    assert L.tape_host_input(b"x", ctypes.byref(size)) == 0 and size.value == 3
+
+
+def test_third_program_all_operations_match_model_and_wasm(ops_tape):
+    """OpsTest three ways: (1) the Python model of the circom operators (the committed KAT), (2) the wasm itself run
+    concretely by the interpreter - every Fr_* call executes the reference runtime's own code, (3) the extracted
+    straight-line program with tape_ops.cuh semantics (what the GPU runs).  Integer division, remainder, power, every
+    comparison / shift / bit operation, nested and one-armed conditionals, an assert."""
+    L, info, wasm, buf = ops_tape
+    kat = json.load(open(H.GOLDEN + "/ops_program_kat.json"))
+    n_valid = 0
+    for case in kat["cases"]:
+        x = [int(v) for v in case["x"]]
+        inp = np.zeros((3, 32), dtype=np.uint8)
+        for i, v in enumerate(x):
+            inp[i] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8)
+        wt, ww = np.zeros((30, 32), dtype=np.uint8), np.zeros((30, 32), dtype=np.uint8)
+        rc_tape = L.tape_host_eval(inp.ctypes.data, wt.ctypes.data)
+        rc_wasm = L.tape_host_wasm_witness(ctypes.addressof(buf), len(wasm), inp.ctypes.data, ww.ctypes.data)
+        assert rc_tape == case["status"], case["x"]
+        if x[1] == 0:
+            assert rc_wasm == 3                   # the wasm traps inside Fr_idiv; the tape reports a failed proof
+            continue
+        assert rc_wasm == case["status"], case["x"]
+        if case["status"] == 0:
+            want = np.stack([np.frombuffer(int(v).to_bytes(32, "little"), dtype=np.uint8) for v in case["witness"]])
+            bad = [k for k in range(30) if not np.array_equal(ww[k], want[k])]
+            assert not bad, ("wasm vs model", case["x"], bad)
+            bad = [k for k in range(30) if not np.array_equal(wt[k], want[k])]
+            assert not bad, ("tape vs model", case["x"], bad)
+            n_valid += 1
+    assert n_valid >= 20
+
+
+def test_census_program_run_concretely_matches_the_fixture(tape, art_dir):
+    """the interpreter itself, with no symbols: the reference wasm on the reference's inputs_example.json gives the
+    committed witness (same sha256 as the native build of the wasm and the GPU kernels)"""
+    L, info = tape
+    L.tape_host_wasm_witness.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    wasm = open(art_dir + "/circuit.wasm", "rb").read()
+    buf = (ctypes.c_char * len(wasm)).from_buffer_copy(wasm)
+    packed = _pack(L, H.fixture_inputs(), int(info[0]))
+    w = np.zeros((int(info[1]), 32), dtype=np.uint8)
+    assert L.tape_host_wasm_witness(ctypes.addressof(buf), len(wasm), packed.ctypes.data, w.ctypes.data) == 0
+    code, wt = _eval(L, info, H.fixture_inputs())
+    assert code == 0 and np.array_equal(w, wt)

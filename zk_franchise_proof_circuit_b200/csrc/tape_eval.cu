@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) k_tape_eval(TapeDev T, const Fr *__restri
   auto exec = [&](const TapeOp &o) {
     const Fr a = (o.a & 1u) ? tape_ld(T.consts + (o.a >> 1)) : tape_ld(slots + (o.a >> 1));
     Fr b = a, c = a;
-    if (o.op <= T_BXOR && o.op != T_NEG && o.op != T_INV && o.op != T_LNOT)
+    if ((o.op <= T_BXOR && o.op != T_NEG && o.op != T_INV && o.op != T_LNOT) || o.op >= T_IDIV)
       b = (o.b & 1u) ? tape_ld(T.consts + (o.b >> 1)) : tape_ld(slots + (o.b >> 1));
     if (o.op == T_SELECT) {
       b = (o.b & 1u) ? tape_ld(T.consts + (o.b >> 1)) : tape_ld(slots + (o.b >> 1));

@@ -3,7 +3,8 @@
 // Each case restates the circom field runtime function it stands for (the wasm's Fr_* functions, circom 2.1.5):
 //   comparisons treat values above (r - 1) / 2 as negative; bit operations work on the canonical value, mask the
 //   result to 254 bits and reduce it once (Fr_adjustBinResult); shifts by a "negative" amount shift the other way,
-//   shifts by 254 or more give 0; logical operations and Fr_isTrue test for non-zero; 0 has inverse 0.
+//   shifts by 254 or more give 0; logical operations and Fr_isTrue test for non-zero; 0 has inverse 0; integer
+//   division, remainder and the exponent of a power read their operands as canonical values in [0, r).
 #pragma once
 #include "fp.cuh"
 #include "wasm_symexec.h"
@@ -105,6 +106,31 @@ ZKB_HD Fr fr_shift(const Fr &a, const Fr &b, bool right) {
 }
 ZKB_HD Fr fr_bool(bool x) { return x ? Fr::one() : Fr::zero(); }
 
+// quotient and remainder of canonical values, b != 0: restoring division, one bit per step from the top set bit of a
+// (r < b < 2^254, so r << 1 stays inside 256 bits).  Rare in witness programs (range reductions of `<--` hints).
+ZKB_HD void u256_divmod(const U256 &a, const U256 &b, U256 &q, U256 &r) {
+  for (int i = 0; i < 8; i++) q.w[i] = r.w[i] = 0;
+  int top = 255;
+  while (top >= 0 && !((a.w[top >> 5] >> (top & 31)) & 1u)) top--;
+  for (int i = top; i >= 0; i--) {
+    uint32_t carry = (a.w[i >> 5] >> (i & 31)) & 1u;
+    for (int k = 0; k < 8; k++) {
+      const uint32_t nc = r.w[k] >> 31;
+      r.w[k] = (r.w[k] << 1) | carry;
+      carry = nc;
+    }
+    if (u256_cmp(r, b) >= 0) {
+      uint64_t br = 0;
+      for (int k = 0; k < 8; k++) {
+        const uint64_t d = (uint64_t)r.w[k] - b.w[k] - br;
+        r.w[k] = (uint32_t)d;
+        br = (d >> 32) & 1;
+      }
+      q.w[i >> 5] |= 1u << (i & 31);
+    }
+  }
+}
+
 // result of `op`; asserts report through *failed
 ZKB_HD Fr tape_apply(uint8_t op, const Fr &a, const Fr &b, const Fr &c, bool *failed) {
   switch (op) {
@@ -135,6 +161,16 @@ ZKB_HD Fr tape_apply(uint8_t op, const Fr &a, const Fr &b, const Fr &c, bool *fa
       U256 x = fr_canon(a);
       for (int i = 0; i < 8; i++) x.w[i] = ~x.w[i];
       return fr_from_canon(fr_adjust_bin(x));
+    }
+    case T_IDIV: case T_MOD: {
+      if (b.is_zero()) { *failed = true; return Fr::zero(); }
+      U256 q, r;
+      u256_divmod(fr_canon(a), fr_canon(b), q, r);
+      return fr_from_canon(op == T_IDIV ? q : r);
+    }
+    case T_POW: {
+      const U256 e = fr_canon(b);
+      return a.pow(e.w);
     }
     case T_ISTRUE: return fr_bool(!a.is_zero());
     case T_SELECT: return c.is_zero() ? b : a;

@@ -251,7 +251,7 @@ struct Machine {
         {"Fr_eq", RT_BIN, T_EQ}, {"Fr_neq", RT_BIN, T_NEQ}, {"Fr_lt", RT_BIN, T_LT}, {"Fr_gt", RT_BIN, T_GT},
         {"Fr_leq", RT_BIN, T_LEQ}, {"Fr_geq", RT_BIN, T_GEQ}, {"Fr_land", RT_BIN, T_LAND}, {"Fr_lor", RT_BIN, T_LOR},
         {"Fr_shr", RT_BIN, T_SHR}, {"Fr_shl", RT_BIN, T_SHL}, {"Fr_band", RT_BIN, T_BAND}, {"Fr_bor", RT_BIN, T_BOR},
-        {"Fr_bxor", RT_BIN, T_BXOR}, {"Fr_idiv", RT_BIN, T_NOPS}, {"Fr_mod", RT_BIN, T_NOPS}, {"Fr_pow", RT_BIN, T_NOPS},
+        {"Fr_bxor", RT_BIN, T_BXOR}, {"Fr_idiv", RT_BIN, T_IDIV}, {"Fr_mod", RT_BIN, T_MOD}, {"Fr_pow", RT_BIN, T_POW},
         {"Fr_neg", RT_UN, T_NEG}, {"Fr_inv", RT_UN, T_INV}, {"Fr_lnot", RT_UN, T_LNOT}, {"Fr_bnot", RT_UN, T_BNOT},
         {"Fr_copy", RT_COPY, 0}, {"Fr_copyn", RT_COPYN, 0}, {"Fr_isTrue", RT_ISTRUE, 0}, {"Fr_toInt", RT_TOINT, 0}};
     rt.assign(n_imports + funcs.size(), RtInfo());
@@ -453,7 +453,6 @@ struct Machine {
       case RT_BIN: {
         uint32_t dst = (uint32_t)args[0].v, a = (uint32_t)args[1].v, b = (uint32_t)args[2].v;
         if (!is_sym(a) && !is_sym(b)) { clear_sym(dst); return false; }
-        if (info.op == T_NOPS) throw Unsupported{"integer division / modulo / power of a signal-dependent value (" + names[fi] + ")"};
         uint32_t ra = operand_ref(a), rb = operand_ref(b);
         set_sym(dst, emit(info.op, ra, rb));
         return true;

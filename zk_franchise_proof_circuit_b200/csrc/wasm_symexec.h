@@ -17,6 +17,9 @@ enum TapeOpcode : uint8_t {
   T_ASSERT_TRUE,   // status 4 unless a != 0   (the wasm's exceptionHandler(4) path)
   T_ASSERT_FALSE,  // status 4 unless a == 0
   T_COPY,          // dst = a (only used to materialise a wire)
+  T_IDIV,          // dst = floor(a / b) on the canonical values (circom's integer division); status 4 when b == 0
+  T_MOD,           // dst = a mod b on the canonical values (circom's `%`); status 4 when b == 0
+  T_POW,           // dst = a ^ b, b read as its canonical value (circom's `**`)
   T_NOPS
 };
 struct TapeOp {
