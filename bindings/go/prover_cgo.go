@@ -78,8 +78,14 @@ func Prove(zkey, wasm, inputs []byte) (*Proof, error) {
 	if err != nil {
 		return nil, err
 	}
+	var info [8]C.uint32_t
+	C.zkb_circuit_info(c, &info[0])
+	pubCap := 96*int(info[1]) + 64 // public.json: up to 77 digits, quotes and a separator per public signal
+	if pubCap < 2048 {
+		pubCap = 2048
+	}
 	proofBuf := make([]byte, 1024)
-	pubBuf := make([]byte, 2048)
+	pubBuf := make([]byte, pubCap)
 	errBuf := make([]byte, 256)
 	pn, qn := C.size_t(len(proofBuf)), C.size_t(len(pubBuf))
 	rc := C.zkb_fullprove(c, (*C.char)(unsafe.Pointer(&inputs[0])), C.size_t(len(inputs)),

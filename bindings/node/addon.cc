@@ -6,6 +6,7 @@
 // build: node-gyp with include_dirs = [<!(node -p "require('node-addon-api').include"), ../../include],
 //        libraries = [-lzkcensus_b200, -lcudart]
 #include <napi.h>
+#include <algorithm>
 #include <fstream>
 #include <map>
 #include <mutex>
@@ -46,7 +47,10 @@ class ProveWorker : public Napi::AsyncWorker {
     std::string e;
     zkb_circuit *c = circuit_for(zkey_, wasm_, e);
     if (!c) return SetError(e);
-    proof_.resize(1024); pub_.resize(2048);
+    uint32_t info[8] = {0};
+    zkb_circuit_info(c, info);
+    proof_.resize(1024);
+    pub_.resize(std::max<size_t>(2048, 96 * (size_t)info[1] + 64));   // public.json: <= 96 bytes per public signal
     size_t pn = proof_.size(), qn = pub_.size();
     char err[256] = {0};
     int rc = zkb_fullprove(c, inputs_.data(), inputs_.size(), &proof_[0], &pn, &pub_[0], &qn, err, sizeof err);

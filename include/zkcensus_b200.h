@@ -81,7 +81,8 @@ int zkb_fullprove(zkb_circuit *c, const char *inputs_json, size_t inputs_len, ch
                   char *public_buf, size_t *public_size, char *err, size_t errmax);
 
 /* n independent proofs in one call.  Outputs are NUL-terminated strings at proofs + i*proof_stride and
- * publics + i*public_stride (1024 bytes each suffice); status[i] per proof, the batch continues past failures. */
+ * publics + i*public_stride (1024 bytes hold a proof.json; public.json needs up to 96 bytes per public signal + 64:
+ * a short stride gives status ZKB_SHORT_BUFFER for that proof); status[i] per proof, the batch continues past failures. */
 int zkb_fullprove_batch(zkb_circuit *c, int n, const char *const *inputs_json, const size_t *inputs_len, char *proofs,
                         size_t proof_stride, char *publics, size_t public_stride, int *status);
 

@@ -34,6 +34,9 @@ def test_field_ops(field, p):
     # edge cases
     a[:6] = [0, 1, p - 1, p - 1, 0, p - 2]
     b[:6] = [0, p - 1, p - 1, 1, p - 1, p - 2]
+    # carry patterns of the dedicated squaring (fp_sqr.inc): saturated limbs, single limbs, the sign boundary
+    a[6:16] = [(1 << 224) - 1, (1 << 253) - 1, p // 2, (1 << 32) - 1, (1 << 64) - 1, ((1 << 128) - 1) << 64,
+               0xFFFFFFFF << 192, (1 << 253) + (1 << 32) - 1, ((1 << 253) - 1) ^ (0xFFFFFFFF << 96), p - (1 << 200)]
     rinv = pow(1 << 256, -1, p)
     A, B = to_limbs(a), to_limbs(b)
     assert from_limbs(raw.field_op(field, "mul", A, B)) == [x * y * rinv % p for x, y in zip(a, b)]

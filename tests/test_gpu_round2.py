@@ -395,6 +395,8 @@ def test_third_circuit_every_runtime_operation_on_the_gpu():
             assert json.loads(pubs[i]) == good[i]["witness"][1:27]
             w = np.stack([np.frombuffer(int(v).to_bytes(32, "little"), dtype=np.uint8) for v in good[i]["witness"]])
             assert O.proof_bin(json.loads(proofs[i])) == zk.prove(w, H.R_FIXED, H.S_FIXED), f"proof {i}"
+        pj, sj = c.fullprove(docs[1])                      # 26 public signals: public.json is > 2 KB
+        assert json.loads(sj) == good[1]["witness"][1:27] and prover.verify_batch(vkey, [sj], [pj]) == [1]
         tampered = json.loads(pubs[0])
         tampered[25] = str(int(tampered[25]) + 1)
         assert prover.verify_batch(vkey, [json.dumps(tampered)], proofs[:1]) == [0]

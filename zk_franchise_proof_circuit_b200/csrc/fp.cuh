@@ -76,6 +76,7 @@ template <class P> struct Fp;
 // inlining ~190 SASS instructions per product: a bucket-accumulation loop body then fits the instruction cache
 // (inlined it was ~57 KB and the kernel ran instruction-fetch bound, 8x below the IMAD rate).
 template <class P> __device__ __noinline__ Fp<P> fp_mul_call(Fp<P> a, Fp<P> b);
+template <class P> __device__ __noinline__ Fp<P> fp_sqr_call(Fp<P> a);
 #endif
 
 template <class P>
@@ -359,7 +360,71 @@ struct alignas(16) Fp {
 #endif
     return res;
   }
-  ZKB_HD Fp sqr() const { return *this * *this; }
+#if defined(__CUDA_ARCH__)
+  // Montgomery square: the 512-bit square from 36 limb products (fp_sqr.inc, generated and checked by
+  // tools/gen_sqr.py), then the reduction rows of operator* without their a * b_i products - 100 IMAD.WIDE instead of
+  // 128.  (T_lo + m p) / R + T_hi < p + 1 + p^2 / R < 2 p for both BN254 fields: one final subtraction.
+  ZKB_D Fp sqr_dev() const {
+    const uint32_t *a = v;
+    uint32_t E[16], O[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) E[i] = O[i] = 0;
+#include "fp_sqr.inc"
+    uint32_t ev[8], od[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) ev[i] = O[i];
+    {
+      const uint32_t m = ev[0] * P::INV;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        od[j] = P::mod(j + 1) * m;
+        od[j + 1] = __umulhi(P::mod(j + 1), m);
+      }
+      cmad_row(ev, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m, od[7]);
+    }
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+      uint32_t *X = (i & 1) ? od : ev;
+      uint32_t *Y = (i & 1) ? ev : od;
+      const uint32_t m = (X[0] + Y[1]) * P::INV;
+      shift_mad_row(X[0], Y, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+      cmad_row(X, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m, Y[7]);
+    }
+    // (od >> 32) + ev + T_hi
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, 0;\n\t"
+        : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7])
+        : "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;\n\t"
+        : "+r"(ev[0]), "+r"(ev[1]), "+r"(ev[2]), "+r"(ev[3]), "+r"(ev[4]), "+r"(ev[5]), "+r"(ev[6]), "+r"(ev[7])
+        : "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]), "r"(O[15]));
+    Fp res;
+#pragma unroll
+    for (int i = 0; i < 8; i++) res.v[i] = ev[i];
+    final_sub(res.v);
+    return res;
+  }
+#endif
+  ZKB_HD Fp sqr() const {
+#if defined(__CUDA_ARCH__) && !defined(ZKB_NO_FAST_SQR)
+    return sqr_dev();
+#else
+    return *this * *this;
+#endif
+  }
   // call-based variants (see fp_mul_call)
   ZKB_HD Fp mulc(const Fp &o) const {
 #if defined(__CUDA_ARCH__)
@@ -368,7 +433,13 @@ struct alignas(16) Fp {
     return *this * o;
 #endif
   }
-  ZKB_HD Fp sqrc() const { return mulc(*this); }
+  ZKB_HD Fp sqrc() const {
+#if defined(__CUDA_ARCH__)
+    return fp_sqr_call<P>(*this);
+#else
+    return *this * *this;
+#endif
+  }
 
   // normal form <-> Montgomery form
   ZKB_HD Fp to_mont() const { return *this * r2(); }
@@ -402,6 +473,7 @@ struct alignas(16) Fp {
 
 #if defined(__CUDACC__)
 template <class P> __device__ __noinline__ Fp<P> fp_mul_call(Fp<P> a, Fp<P> b) { return a * b; }
+template <class P> __device__ __noinline__ Fp<P> fp_sqr_call(Fp<P> a) { return a.sqr(); }
 #endif
 
 typedef Fp<FqParams> Fq;

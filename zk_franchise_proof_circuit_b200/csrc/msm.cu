@@ -313,9 +313,9 @@ struct TablePtrs { const Affine<F> *tab[4]; };
 template <bool INL, class F> __device__ __forceinline__ F mulx(const F &a, const F &b) {
   if constexpr (INL) return a * b; else return a.mulc(b);
 }
-// squares: Fq2 has a 2-product complex squaring (3 for a general product); Fq squares are plain products
+// squares: Fq2 has a 2-product complex squaring (3 for a general product); Fq has a 36-limb-product square (fp.cuh)
 template <bool INL, class F> __device__ __forceinline__ F sqrx(const F &a) {
-  if constexpr (INL) return a * a; else return a.sqrc();
+  if constexpr (INL) return a.sqr(); else return a.sqrc();
 }
 
 template <class F, int THREADS, int MINB, bool INL>

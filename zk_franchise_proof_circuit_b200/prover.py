@@ -153,6 +153,10 @@ class Circuit:
             sb = (ctypes.c_uint8 * 32).from_buffer_copy(int(s).to_bytes(32, "little"))
             _native.check(_lib().zkb_set_blinding(self.h, rb, sb))
 
+    def _public_cap(self):
+        # public.json: one decimal string of up to 77 digits per public signal, quotes, separators
+        return max(2048, 96 * self.n_public + 64)
+
     # ---- reference-shaped calls (JSON in, JSON out; host<->device copies inside) --------------
     def fullprove_batch(self, inputs_json):
         """inputs_json: list of bytes/str documents.  Returns (proofs, publics, status) lists."""
@@ -160,7 +164,7 @@ class Circuit:
         docs = [d if isinstance(d, bytes) else d.encode() for d in inputs_json]
         arr = (ctypes.c_char_p * n)(*docs)
         lens = (ctypes.c_size_t * n)(*[len(d) for d in docs])
-        ps, qs = 1024, 1024
+        ps, qs = 1024, self._public_cap()
         pbuf = ctypes.create_string_buffer(ps * n)
         qbuf = ctypes.create_string_buffer(qs * n)
         status = (ctypes.c_int * n)()
@@ -172,8 +176,9 @@ class Circuit:
 
     def fullprove(self, inputs_json):
         doc = inputs_json if isinstance(inputs_json, bytes) else inputs_json.encode()
-        pbuf, qbuf, ebuf = ctypes.create_string_buffer(1024), ctypes.create_string_buffer(2048), ctypes.create_string_buffer(256)
-        pn, qn = ctypes.c_size_t(1024), ctypes.c_size_t(2048)
+        qcap = self._public_cap()
+        pbuf, qbuf, ebuf = ctypes.create_string_buffer(1024), ctypes.create_string_buffer(qcap), ctypes.create_string_buffer(256)
+        pn, qn = ctypes.c_size_t(1024), ctypes.c_size_t(qcap)
         rc = _lib().zkb_fullprove(self.h, doc, len(doc), pbuf, ctypes.byref(pn), qbuf, ctypes.byref(qn), ebuf, 256)
         if rc:
             raise NativeError(rc, ebuf.value.decode(errors="replace"))
@@ -191,8 +196,9 @@ class Circuit:
     def prove_wtns(self, wtns: bytes, stages=False):
         """Groth16 from a .wtns (go-rapidsnark Groth16ProverRaw).  stages=True also returns the 8 device stage times.
         wtns=None proves again from the witness already resident on the device."""
-        pbuf, qbuf = ctypes.create_string_buffer(1024), ctypes.create_string_buffer(2048)
-        pn, qn = ctypes.c_size_t(1024), ctypes.c_size_t(2048)
+        qcap = self._public_cap()
+        pbuf, qbuf = ctypes.create_string_buffer(1024), ctypes.create_string_buffer(qcap)
+        pn, qn = ctypes.c_size_t(1024), ctypes.c_size_t(qcap)
         # the bytes object is handed over as it is (no copy: round 1 copied the 134 MB witness of the 2^22-constraint
         # circuit into a fresh ctypes array on every call, ~60 ms of the measured wall time)
         wb = ctypes.cast(ctypes.c_char_p(wtns), _vp) if wtns is not None else None
