@@ -310,15 +310,17 @@ struct TablePtrs { const Affine<F> *tab[4]; };
 // version returned early from the add for empty accumulators / infinity bases; with independent thread scheduling
 // the lanes then ran their lists one after another - ncu showed 2.4 of 32 threads active per instruction.)
 // The P == +-acc cases are handled in a rare slow path taken only when some lane of the warp needs it.
-template <bool INL, class F> __device__ __forceinline__ F mulx(const F &a, const F &b) {
-  if constexpr (INL) return a * b; else return a.mulc(b);
+// INL: 0 = products through the out-of-line calls, 1 = all inlined, 2 = all inlined with squares as plain products,
+// 3 = products inlined, squares through the out-of-line 36-product squaring (smaller loop body; the default)
+template <int INL, class F> __device__ __forceinline__ F mulx(const F &a, const F &b) {
+  if constexpr (INL != 0) return a * b; else return a.mulc(b);
 }
 // squares: Fq2 has a 2-product complex squaring (3 for a general product); Fq has a 36-limb-product square (fp.cuh)
-template <bool INL, class F> __device__ __forceinline__ F sqrx(const F &a) {
-  if constexpr (INL) return a.sqr(); else return a.sqrc();
+template <int INL, class F> __device__ __forceinline__ F sqrx(const F &a) {
+  if constexpr (INL == 2) return a * a; else if constexpr (INL == 1) return a.sqr(); else return a.sqrc();
 }
 
-template <class F, int THREADS, int MINB, bool INL>
+template <class F, int THREADS, int MINB, int INL>
 __global__ void __launch_bounds__(THREADS, MINB) k_accumulate(TablePtrs<F> tabs, int ntab, uint32_t n, int windows,
                                                         uint32_t nbuckets, const uint32_t *__restrict__ offsets,
                                                         const uint32_t *__restrict__ entries,
@@ -392,7 +394,7 @@ __device__ __forceinline__ Fq2 pair_xchg(const Fq2 &v, uint32_t mask = 0xfffffff
   return r;
 }
 
-template <int THREADS, int MINB, bool INL, bool SMB>
+template <int THREADS, int MINB, int INL, bool SMB>
 __global__ void __launch_bounds__(THREADS, MINB) k_accumulate_g2pair(TablePtrs<Fq2> tabs, int ntab, uint32_t n, int windows,
                                                                    uint32_t nbuckets, const uint32_t *__restrict__ offsets,
                                                                    const uint32_t *__restrict__ entries,
@@ -1050,7 +1052,11 @@ cudaError_t msm_accumulate(const MsmSort &sort, const MsmTable<F> *tables, int n
       case 2: ZKB_ACC(5, false); break;
       case 3: ZKB_ACC(3, true); break;
       case 4: ZKB_ACC(5, true); break;
-      default: ZKB_ACC(4, true); break;     // measured best on B200: inlined products, 128 registers
+      case 5: ZKB_ACC(4, 2); break;          // everything inlined, squares as plain products (the default until the squaring existed)
+      case 6: ZKB_ACC(4, 3); break;          // inlined products, squares through the out-of-line call
+      case 7: ZKB_ACC(4, 1); break;          // everything inlined, squares by Fp::sqr_dev
+      default: ZKB_ACC(4, 3); break;         // measured best on B200: inlined products, the two squares through the
+                                             // out-of-line 36-product squaring (128 registers, no stack)
     }
   } else {
     static const int variant2 = getenv("ZKB_ACC_VARIANT_G2") ? atoi(getenv("ZKB_ACC_VARIANT_G2")) : 0;
