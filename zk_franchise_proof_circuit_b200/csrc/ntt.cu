@@ -10,12 +10,12 @@
 // Roots are snarkjs' / ptau's: omega_{2^28} = 5^((r-1)/2^28), omega_{2^k} by repeated squaring.
 #include "ntt.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 namespace zkb {
 
 static constexpr int TILE_LOG = 11;
 static constexpr int TILE = 1 << TILE_LOG;      // elements per CTA tile
-static constexpr int NTT_THREADS = 256;
 
 // omega_{2^28} in Montgomery form
 __device__ __constant__ uint32_t OMEGA28[8] = {0x80d13d9cu, 0x636e7355u, 0x2445ffd6u, 0xa22bf374u,
@@ -90,8 +90,8 @@ __device__ __forceinline__ void stg_fr(Fr *p, const Fr &x) {
 // elements apart.  DIF=true: stages hi-1 .. lo with (u,v) -> (u+v, (u-v)w).  DIF=false (DIT):
 // stages lo .. hi-1 with (u,v) -> (u+vw, u-vw).  tw[e] = omega_N^e (or its inverse), e < N/2.
 // `scale` (optional) multiplies the element stored at position p by scale[p].
-template <bool DIF>
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr *data, size_t vec_stride, int logn, int lo, int hi,
+template <bool DIF, int UNR, int THREADS>
+__global__ void __launch_bounds__(THREADS, UNR ? 3 : 1) k_ntt_pass(Fr *data, size_t vec_stride, int logn, int lo, int hi,
                                                            const Fr *__restrict__ tw, const Fr *__restrict__ scale) {
   extern __shared__ uint32_t sm[];
   const int rows_log = hi - lo, rows = 1 << rows_log;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr *data, size_t vec_s
     base = (size_t)tile * TILE;
   }
   // ---- load -----------------------------------------------------------------------------
-  for (int i = threadIdx.x; i < TILE; i += NTT_THREADS) {
+  for (int i = threadIdx.x; i < TILE; i += THREADS) {
     int k, g;
     size_t addr;
     int sidx;
@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr *data, size_t vec_s
     const int sb = DIF ? (rows_log - 1 - st) : st;    // bit (within the tile rows) of this stage
     const int s = lo + sb;                            // global stage: half distance 2^s
     const int d = 1 << sb;
-    for (int b = threadIdx.x; b < TILE / 2; b += NTT_THREADS) {
+#pragma unroll (UNR ? UNR : 1)
+    for (int b = threadIdx.x; b < TILE / 2; b += THREADS) {
       int kk, g;
       if (col) { g = b & g_mask; kk = b >> g_log; } else { kk = b & (rows_mask >> 1); g = b >> (rows_log - 1); }
       int k = ((kk >> sb) << (sb + 1)) | (kk & (d - 1));
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(Fr *data, size_t vec_s
     __syncthreads();
   }
   // ---- store ----------------------------------------------------------------------------
-  for (int i = threadIdx.x; i < TILE; i += NTT_THREADS) {
+  for (int i = threadIdx.x; i < TILE; i += THREADS) {
     int k, g;
     size_t addr;
     int sidx;
@@ -210,8 +211,11 @@ cudaError_t NttPlan::init(int logn_, cudaStream_t st) {
   CK(cudaStreamSynchronize(st));
   CK(cudaFree(pw));
   CK(cudaFree(ninv));
-  CK(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 32));
-  CK(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 32));
+#define ZKB_NTT_ATTR(U, T)                                                                                          \
+  CK((cudaFuncSetAttribute(k_ntt_pass<true, U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 32)));      \
+  CK((cudaFuncSetAttribute(k_ntt_pass<false, U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 32)));
+  ZKB_NTT_ATTR(0, 256) ZKB_NTT_ATTR(4, 256) ZKB_NTT_ATTR(8, 128) ZKB_NTT_ATTR(4, 128) ZKB_NTT_ATTR(2, 512)
+#undef ZKB_NTT_ATTR
   return cudaGetLastError();
 }
 
@@ -237,6 +241,30 @@ static int split_passes(int logn, int lo[4], int hi[4]) {
   return np + 1;
 }
 
+// butterflies of one thread and stage the compiler may interleave (independent products hide each other's carry-chain
+// latency; three 64 KB tiles per SM leave 85 registers per thread).  ZKB_NTT_UNROLL overrides the default.
+// Threads per 2048-element tile and butterflies of one thread the compiler may interleave (independent products hide
+// each other's carry-chain latency; three 64 KB tiles per SM leave 85 registers per thread).  Measured on B200, ntt_join
+// per 512 proofs (profiles/r02_ntt_variant_sweep.log): 256 threads, loop not unrolled 68.7 ms; 256 x 4 interleaved
+// 65.9 ms (default); 128 x 8 69.6; 128 x 4 71.2; 512 x 2 70.9.  ZKB_NTT_VARIANT selects another one.
+static int ntt_variant() {
+  static const int v = getenv("ZKB_NTT_VARIANT") ? atoi(getenv("ZKB_NTT_VARIANT")) : 0;
+  return v;
+}
+template <bool DIF>
+static void launch_pass(dim3 grid, cudaStream_t st, Fr *data, size_t vec_stride, int logn, int lo, int hi, const Fr *tw,
+                        const Fr *scale) {
+#define ZKB_NTT_GO(U, T) k_ntt_pass<DIF, U, T><<<grid, T, TILE * 32, st>>>(data, vec_stride, logn, lo, hi, tw, scale)
+  switch (ntt_variant()) {
+    case 1: ZKB_NTT_GO(0, 256); break;
+    case 2: ZKB_NTT_GO(8, 128); break;
+    case 3: ZKB_NTT_GO(4, 128); break;
+    case 4: ZKB_NTT_GO(2, 512); break;
+    default: ZKB_NTT_GO(4, 256); break;
+  }
+#undef ZKB_NTT_GO
+}
+
 // DIF passes: natural in -> bit-reversed out.  inverse selects the twiddle table; with_coset_scale
 // multiplies by n^-1 * inc^bitrev(p) in the last pass.
 cudaError_t NttPlan::dif(Fr *data, int nvec, size_t vec_stride, bool inverse, bool with_coset_scale,
@@ -247,8 +275,7 @@ cudaError_t NttPlan::dif(Fr *data, int nvec, size_t vec_stride, bool inverse, bo
   dim3 grid((unsigned)(n / TILE), nvec);
   for (int p = 0; p < np; p++) {
     const Fr *sc = (with_coset_scale && p == np - 1) ? coset_scale : nullptr;
-    k_ntt_pass<true><<<grid, NTT_THREADS, TILE * 32, st>>>(data, vec_stride, logn, lo[p], hi[p],
-                                                           inverse ? tw_inv : tw_fwd, sc);
+    launch_pass<true>(grid, st, data, vec_stride, logn, lo[p], hi[p], inverse ? tw_inv : tw_fwd, sc);
   }
   return cudaGetLastError();
 }
@@ -260,8 +287,7 @@ cudaError_t NttPlan::dit(Fr *data, int nvec, size_t vec_stride, bool inverse, cu
   size_t n = (size_t)1 << logn;
   dim3 grid((unsigned)(n / TILE), nvec);
   for (int p = np - 1; p >= 0; p--)
-    k_ntt_pass<false><<<grid, NTT_THREADS, TILE * 32, st>>>(data, vec_stride, logn, lo[p], hi[p],
-                                                            inverse ? tw_inv : tw_fwd, nullptr);
+    launch_pass<false>(grid, st, data, vec_stride, logn, lo[p], hi[p], inverse ? tw_inv : tw_fwd, nullptr);
   return cudaGetLastError();
 }
 
