@@ -349,11 +349,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_accumulate(TablePtrs<F> tabs,
     // madd-2008-s, unconditionally
     F U2 = mulx<INL>(p.x, acc.ZZ), S2 = mulx<INL>(p.y, acc.ZZZ);
     F P = U2 - acc.X, R = S2 - acc.Y;
-    const bool special = use && !acc_inf && P.is_zero();
     F PP = sqrx<INL>(P), PPP = mulx<INL>(P, PP), Q = mulx<INL>(acc.X, PP);
     F X3 = sqrx<INL>(R) - PPP - Q.dbl();
     F Y3 = mulx<INL>(R, Q - X3) - mulx<INL>(acc.Y, PPP);
     F ZZ3 = mulx<INL>(acc.ZZ, PP), ZZZ3 = mulx<INL>(acc.ZZZ, PPP);
+    const bool special = use && !acc_inf && P.is_zero();
     const bool normal = use && !acc_inf && !special, first = use && acc_inf;
     acc.X = F::select(normal, X3, F::select(first, p.x, acc.X));
     acc.Y = F::select(normal, Y3, F::select(first, p.y, acc.Y));
