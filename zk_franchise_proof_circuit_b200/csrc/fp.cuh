@@ -9,7 +9,11 @@
 // aligned limb pair and each row is ONE carry chain; ptxas turns each lo/hi pair into a single
 // IMAD.WIDE.U32 with carry-in/out.  The one-limb right shift of the reduction is absorbed by
 // swapping the roles of the two accumulators every row.  Integer pipe only - there is no dense
-// contraction here for tensor cores to do.
+// contraction here for tensor cores to do.  SASS per product: 121 IMAD.WIDE + 16 IMAD / IMAD.HI = 137
+// multiplier instructions ("modmul" in the roofline bookkeeping).
+//
+// Device square (sqr_dev): the 512-bit square from 36 instead of 64 limb products (fp_sqr.inc, generated and
+// checked by tools/gen_sqr.py), then the reduction rows of the product alone: 117 multiplier instructions.
 //
 // Inline-asm rule used throughout: an asm block holds a whole carry chain (the CC flag never crosses
 // statements) and every pure output that is written before the last input is read is early-clobber
