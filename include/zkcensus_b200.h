@@ -228,7 +228,7 @@ int zkb_msm_session_run(zkb_msm_session *s, float *ms);
 int zkb_msm_session_combine(zkb_msm_session *s, int nslots, void *out64, float *ms);
 int zkb_msm_session_madds(zkb_msm_session *s, uint64_t *madds);
 int zkb_msm_session_read(zkb_msm_session *s, void *bases_out, void *scalars_out);
-/* 4-step NTT of 2^logn (>= 2^24) values over nranks GPUs, one session per rank: rank g owns N2/G columns of the
+/* 4-step NTT of 2^logn (>= 2^22) values over nranks GPUs, one session per rank: rank g owns N2/G columns of the
  * N1 x N2 input, runs the length-N1 column transforms, then READS its N1/G positions of every rank's columns through
  * CUDA IPC mappings (the all-to-all transpose and the omega_N^(n2 k1) twiddles are fused into that load), then runs
  * the length-N2 row transforms.  Output rows, concatenated over ranks, are the transform in bit-reversed order

@@ -52,7 +52,7 @@ def test_field_ops(field, p):
     assert got == exp
 
 
-@pytest.mark.parametrize("logn", [12, 13, 17, 19])
+@pytest.mark.parametrize("logn", [11, 12, 13, 17, 19])
 def test_ntt_matches_oracle(logn):
     from zk_franchise_proof_circuit_b200 import raw
     rng = np.random.default_rng(logn)

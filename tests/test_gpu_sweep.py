@@ -132,11 +132,12 @@ def _ntt_dist_group(logn, nranks, devices):
     return x, out, times
 
 
-@pytest.mark.parametrize("nranks", [1, 4])
-def test_ntt_dist_matches_single_gpu_plan(nranks):
-    """2^24 values, ranks as streams of one GPU: concatenated output rows == the single-GPU DIF transform."""
+@pytest.mark.parametrize("logn,nranks", [(24, 1), (24, 4), (22, 2), (23, 4)])
+def test_ntt_dist_matches_single_gpu_plan(logn, nranks):
+    """2^22 (the smallest: 2^11 x 2^11, one tile per column), 2^23 (odd split) and 2^24 values, ranks as streams of one
+    GPU: concatenated output rows == the single-GPU DIF transform."""
     from zk_franchise_proof_circuit_b200 import raw
-    x, out, _ = _ntt_dist_group(24, nranks, [0])
+    x, out, _ = _ntt_dist_group(logn, nranks, [0])
     assert np.array_equal(out, raw.ntt_dif_forward(x))
 
 

@@ -27,7 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--msm", default="16,18,20,22,24")
     ap.add_argument("--ntt", default="16,18,20,22,24")
-    ap.add_argument("--ntt-dist", default="", help="sizes (log2, >= 24) for the 4-step NTT split over all ranks")
+    ap.add_argument("--ntt-dist", default="", help="sizes (log2, >= 22) for the 4-step NTT split over all ranks")
     ap.add_argument("--nccl-compare", action="store_true",
                     help="also time the NCCL collectives the P2P exchanges replace (all_gather of one 128-byte partial "
                          "sum; all_to_all of the NTT columns), same GPUs, CUDA events")

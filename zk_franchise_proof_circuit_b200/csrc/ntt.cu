@@ -191,7 +191,7 @@ __global__ void k_from_mont(Fr *x, size_t n) {
 
 cudaError_t NttPlan::init(int logn_, cudaStream_t st) {
   logn = logn_;
-  if (logn < TILE_LOG + 1 || logn > 27) return cudaErrorInvalidValue;
+  if (logn < TILE_LOG || logn > 27) return cudaErrorInvalidValue;    // 2^11 = one tile, one pass over stages [0, 11)
   size_t n = (size_t)1 << logn;
   CK(cudaMalloc(&tw_fwd, (n / 2) * sizeof(Fr)));
   CK(cudaMalloc(&tw_inv, (n / 2) * sizeof(Fr)));

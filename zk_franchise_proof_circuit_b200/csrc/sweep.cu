@@ -532,8 +532,8 @@ int zkb_ntt_bench(int device, int logn, int nvec, int iters, float *dif_ms, floa
 struct zkb_ntt_dist;
 int zkb_ntt_dist_create(int device, int logn, int rank, int nranks, uint64_t seed, zkb_ntt_dist **out) {
   if (require_device()) return ZKB_ERROR;
-  if (logn < 24 || logn > 30 || nranks < 1 || nranks > MAX_RANKS || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) {
-    set_error("ntt dist: logn in [24,30], nranks a power of two <= 16");
+  if (logn < 22 || logn > 30 || nranks < 1 || nranks > MAX_RANKS || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) {
+    set_error("ntt dist: logn in [22,30], nranks a power of two <= 16");
     return ZKB_ERROR;
   }
   CKR(cudaSetDevice(device), "set device");
