@@ -167,6 +167,126 @@ __global__ void __launch_bounds__(THREADS, UNR ? 3 : 1) k_ntt_pass(Fr *data, siz
   }
 }
 
+// The same pass with TWO stages per barrier (radix 4): a thread takes the four elements that differ in two adjacent
+// stage bits from shared memory, runs both butterfly stages on them in registers and stores them back - half the
+// shared-memory traffic, barriers and index arithmetic of k_ntt_pass; an odd stage count ends with one radix-2 stage.
+// Twiddles are the ones the two radix-2 stages would load: two for the stage of the upper bit (its two butterflies sit
+// at rows k and k + d0), one for the stage of the lower bit (both of its butterflies have the same row bits below it).
+template <bool DIF>
+__global__ void __launch_bounds__(256, 3) k_ntt_pass4(Fr *data, size_t vec_stride, int logn, int lo, int hi,
+                                                      const Fr *__restrict__ tw, const Fr *__restrict__ scale) {
+  constexpr int THREADS = 256;
+  extern __shared__ uint32_t sm[];
+  const int rows_log = hi - lo, rows = 1 << rows_log;
+  const int g_log = TILE_LOG - rows_log, G = 1 << g_log;
+  const int rows_mask = rows - 1, g_mask = G - 1;
+  const bool col = lo > 0;
+  Fr *vec = data + (size_t)blockIdx.y * vec_stride;
+  const int tile = blockIdx.x;
+  size_t base;
+  int low0 = 0;
+  if (col) {
+    int lg_log = lo - g_log;
+    int hi_idx = tile >> lg_log, low_grp = tile & ((1 << lg_log) - 1);
+    low0 = low_grp * G;
+    base = ((size_t)hi_idx << hi) + low0;
+  } else {
+    base = (size_t)tile * TILE;
+  }
+  for (int i = threadIdx.x; i < TILE; i += THREADS) {
+    size_t addr;
+    if (col) { int g = i & g_mask, k = i >> g_log; addr = base + ((size_t)k << lo) + g; }
+    else addr = base + i;
+    sts_fr(sm, i, ldg_fr(vec + addr));
+  }
+  __syncthreads();
+  const int stride = col ? G : 1;
+  // twiddle of the butterfly whose lower row is `krow` in the stage of row bit `sb` (column g)
+  auto twd = [&](int krow, int sb, int g) -> Fr {
+    const size_t j = ((size_t)(krow & ((1 << sb) - 1)) << lo) + (col ? (low0 + g) : 0);
+    return ldg_fr(tw + (j << (logn - 1 - (lo + sb))));
+  };
+  int st = 0;
+  for (; st + 1 < rows_log; st += 2) {
+    const int sb0 = DIF ? rows_log - 2 - st : st, sb1 = sb0 + 1;     // the two row bits of this double stage
+    const int d0 = 1 << sb0;
+    const bool unit0 = lo + sb0 == 0;                                 // global stage 0: every twiddle is 1
+#pragma unroll 2
+    for (int q = threadIdx.x; q < TILE / 4; q += THREADS) {
+      int kk, g;
+      if (col) { g = q & g_mask; kk = q >> g_log; } else { kk = q & (rows_mask >> 2); g = q >> (rows_log - 2); }
+      const int k = ((kk >> sb0) << (sb0 + 2)) | (kk & (d0 - 1));    // row with bits sb0, sb1 clear
+      const int i00 = col ? ((k << g_log) + g) : ((g << rows_log) + k);
+      const int i01 = i00 + d0 * stride, i10 = i00 + 2 * d0 * stride, i11 = i10 + d0 * stride;
+      const Fr x00 = lds_fr(sm, i00), x01 = lds_fr(sm, i01), x10 = lds_fr(sm, i10), x11 = lds_fr(sm, i11);
+      if (DIF) {
+        const Fr a0 = x00 + x10, a2 = (x00 - x10) * twd(k, sb1, g);
+        const Fr a1 = x01 + x11, a3 = (x01 - x11) * twd(k + d0, sb1, g);
+        sts_fr(sm, i00, a0 + a1);
+        sts_fr(sm, i10, a2 + a3);
+        if (unit0) {
+          sts_fr(sm, i01, a0 - a1);
+          sts_fr(sm, i11, a2 - a3);
+        } else {
+          const Fr w0 = twd(k, sb0, g);
+          sts_fr(sm, i01, (a0 - a1) * w0);
+          sts_fr(sm, i11, (a2 - a3) * w0);
+        }
+      } else {
+        Fr t0 = x01, t1 = x11;
+        if (!unit0) {
+          const Fr w0 = twd(k, sb0, g);
+          t0 = t0 * w0;
+          t1 = t1 * w0;
+        }
+        const Fr b0 = x00 + t0, b1 = x00 - t0, b2 = x10 + t1, b3 = x10 - t1;
+        const Fr u0 = b2 * twd(k, sb1, g), u1 = b3 * twd(k + d0, sb1, g);
+        sts_fr(sm, i00, b0 + u0);
+        sts_fr(sm, i10, b0 - u0);
+        sts_fr(sm, i01, b1 + u1);
+        sts_fr(sm, i11, b1 - u1);
+      }
+    }
+    __syncthreads();
+  }
+  if (st < rows_log) {                                                // odd count: the last stage alone
+    const int sb = DIF ? (rows_log - 1 - st) : st;
+    const int s = lo + sb, d = 1 << sb;
+#pragma unroll 4
+    for (int b = threadIdx.x; b < TILE / 2; b += THREADS) {
+      int kk, g;
+      if (col) { g = b & g_mask; kk = b >> g_log; } else { kk = b & (rows_mask >> 1); g = b >> (rows_log - 1); }
+      const int k = ((kk >> sb) << (sb + 1)) | (kk & (d - 1));
+      const int i0 = col ? ((k << g_log) + g) : ((g << rows_log) + k);
+      const int i1 = i0 + d * stride;
+      const Fr u = lds_fr(sm, i0), v = lds_fr(sm, i1);
+      if (s == 0) {
+        sts_fr(sm, i0, u + v);
+        sts_fr(sm, i1, u - v);
+        continue;
+      }
+      const Fr w = twd(k, sb, g);
+      if (DIF) {
+        sts_fr(sm, i0, u + v);
+        sts_fr(sm, i1, (u - v) * w);
+      } else {
+        const Fr t = v * w;
+        sts_fr(sm, i0, u + t);
+        sts_fr(sm, i1, u - t);
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < TILE; i += THREADS) {
+    size_t addr;
+    if (col) { int g = i & g_mask, k = i >> g_log; addr = base + ((size_t)k << lo) + g; }
+    else addr = base + i;
+    Fr x = lds_fr(sm, i);
+    if (scale) x = x * ldg_fr(scale + addr);
+    stg_fr(vec + addr, x);
+  }
+}
+
 // out[bitrev(i)] = in[i]
 __global__ void k_bitrev(Fr *out, const Fr *in, int logn, size_t vec_stride) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -216,6 +336,8 @@ cudaError_t NttPlan::init(int logn_, cudaStream_t st) {
   CK((cudaFuncSetAttribute(k_ntt_pass<false, U, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 32)));
   ZKB_NTT_ATTR(0, 256) ZKB_NTT_ATTR(4, 256) ZKB_NTT_ATTR(8, 128) ZKB_NTT_ATTR(4, 128) ZKB_NTT_ATTR(2, 512)
 #undef ZKB_NTT_ATTR
+  CK((cudaFuncSetAttribute(k_ntt_pass4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 32)));
+  CK((cudaFuncSetAttribute(k_ntt_pass4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 32)));
   return cudaGetLastError();
 }
 
@@ -245,8 +367,9 @@ static int split_passes(int logn, int lo[4], int hi[4]) {
 // latency; three 64 KB tiles per SM leave 85 registers per thread).  ZKB_NTT_UNROLL overrides the default.
 // Threads per 2048-element tile and butterflies of one thread the compiler may interleave (independent products hide
 // each other's carry-chain latency; three 64 KB tiles per SM leave 85 registers per thread).  Measured on B200, ntt_join
-// per 512 proofs (profiles/r02_ntt_variant_sweep.log): 256 threads, loop not unrolled 68.7 ms; 256 x 4 interleaved
-// 65.9 ms (default); 128 x 8 69.6; 128 x 4 71.2; 512 x 2 70.9.  ZKB_NTT_VARIANT selects another one.
+// per 512 proofs (profiles/r02_ntt_variant_sweep.log, r02_ntt_radix4_sweep.log): 256 threads, loop not unrolled 68.7 ms;
+// 256 x 4 interleaved 65.9 ms; 128 x 8 69.6; 128 x 4 71.2; 512 x 2 70.9; radix 4 (k_ntt_pass4, two stages per barrier)
+// 63.7 - 65.4 ms (default).  ZKB_NTT_VARIANT selects another one.
 static int ntt_variant() {
   static const int v = getenv("ZKB_NTT_VARIANT") ? atoi(getenv("ZKB_NTT_VARIANT")) : 0;
   return v;
@@ -260,7 +383,8 @@ static void launch_pass(dim3 grid, cudaStream_t st, Fr *data, size_t vec_stride,
     case 2: ZKB_NTT_GO(8, 128); break;
     case 3: ZKB_NTT_GO(4, 128); break;
     case 4: ZKB_NTT_GO(2, 512); break;
-    default: ZKB_NTT_GO(4, 256); break;
+    case 5: ZKB_NTT_GO(4, 256); break;     // radix 2, four butterflies interleaved
+    default: k_ntt_pass4<DIF><<<grid, 256, TILE * 32, st>>>(data, vec_stride, logn, lo, hi, tw, scale); break;   // radix 4
   }
 #undef ZKB_NTT_GO
 }
