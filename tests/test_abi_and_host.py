@@ -284,3 +284,25 @@ def test_generated_squaring_is_current_and_exact():
     vals += [M ^ (0xFFFFFFFF << (32 * i)) for i in range(8)] + [rnd.getrandbits(256) for _ in range(500)]
     for v in vals:
         assert G.emulate(blocks, v) == v * v
+
+
+def test_ntt_pass_model_radix4_equals_radix2_and_the_dft():
+    """tools/ntt_pass_model.py restates the index / twiddle logic of csrc/ntt.cu's passes (k_ntt_pass, k_ntt_pass4) over
+    a small prime: the radix-4 pass == the radix-2 pass for every pass shape of 2^11..2^13 (DIF and DIT), and the DIF
+    passes of a 2^11 vector are the DFT in bit-reversed order."""
+    import importlib.util
+    import random
+    spec = importlib.util.spec_from_file_location("ntt_pass_model", os.path.join(H.ROOT, "tools", "ntt_pass_model.py"))
+    M = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(M)
+    M.main((11, 12, 13))
+    logn, n, P = 11, 1 << 11, M.P
+    w = pow(M.GEN, (P - 1) // n, P)
+    tw = [pow(w, e, P) for e in range(n // 2)]
+    rnd = random.Random(2)
+    x = [rnd.randrange(P) for _ in range(n)]
+    got = M.run(logn, 0, 11, True, True, x, tw)
+    pw = [pow(w, e, P) for e in range(n)]
+    for k in rnd.sample(range(n), 64):
+        want = sum(x[j] * pw[(j * k) % n] for j in range(n)) % P
+        assert got[int(format(k, "011b")[::-1], 2)] == want
