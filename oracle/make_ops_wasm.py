@@ -171,6 +171,20 @@ def ops_body(fn, zero_addr, one_addr):
     return bytes(a.b)
 
 
+def toint_body(fn):
+    """a template that uses a signal as an integer (`var n = x[0]; for (i < n) ...`): circom calls Fr_toInt on it.  The
+    generic extractor cannot turn that into a straight-line program and must say so."""
+    a = Asm(fn)
+    a.const(0); a.load(); a.set(6)
+    a.get(6); a.const(0); a.add(); a.set(7)
+    a.const(40 * 4); a.call("reserveStackFr"); a.set(1)
+    a.get(0); a.const(4); a.add(); a.load(); a.set(2)
+    a.sig(N_OUT); a.call("Fr_toInt"); a.set(3)            # local 3 = x[0] as an integer
+    a.const(0); a.get(1); a.store()
+    a.const(0); a.end()
+    return bytes(a.b)
+
+
 def replace_body(wasm: bytes, code_index: int, instrs: bytes) -> bytes:
     """new module in which the code_index-th body of the code section keeps its locals and gets `instrs`"""
     p = 8
@@ -197,7 +211,7 @@ def replace_body(wasm: bytes, code_index: int, instrs: bytes) -> bytes:
     raise ValueError("no code section")
 
 
-def build(wasm: bytes) -> bytes:
+def build(wasm: bytes, body: str = "ops") -> bytes:
     mod = W.Module(wasm)
     b = bytearray(wasm)
     by_name = {f.name: f for f in mod.funcs}
@@ -249,7 +263,8 @@ def build(wasm: bytes) -> bytes:
         elif len(data) == 4 * n_wires_old:                      # witness -> signal map: identity
             assert wasm.count(bytes(data)) == 1
             b[at:at + len(data)] = b"".join(struct.pack("<I", i) for i in range(n_wires_old))
-    return replace_body(bytes(b), run.idx - len(mod.imports), ops_body(fn, zero_addr, one_addr))
+    instrs = ops_body(fn, zero_addr, one_addr) if body == "ops" else toint_body(fn)
+    return replace_body(bytes(b), run.idx - len(mod.imports), instrs)
 
 
 if __name__ == "__main__":

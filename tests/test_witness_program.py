@@ -304,3 +304,16 @@ def test_census_program_run_concretely_matches_the_fixture(tape, art_dir):
     assert L.tape_host_wasm_witness(ctypes.addressof(buf), len(wasm), packed.ctypes.data, w.ctypes.data) == 0
     code, wt = _eval(L, info, H.fixture_inputs())
     assert code == 0 and np.array_equal(w, wt)
+
+
+def test_signal_used_as_integer_is_rejected_with_the_reason(ops_tape, art_dir):
+    """a program whose main component calls Fr_toInt on an input (a loop bound or array index that depends on a signal)
+    has no straight-line form: the extractor reports it, the product would return ZKB_UNSUPPORTED_CIRCUIT"""
+    import make_ops_wasm as OW
+    L = ops_tape[0]
+    wasm = OW.build(open(art_dir + "/circuit.wasm", "rb").read(), body="toint")
+    buf = (ctypes.c_char * len(wasm)).from_buffer_copy(wasm)
+    info = np.zeros(8, dtype=np.uint32)
+    err = ctypes.create_string_buffer(512)
+    assert L.tape_host_build(ctypes.addressof(buf), len(wasm), info.ctypes.data, err, 512) == 1
+    assert "used as an integer" in err.value.decode()
