@@ -317,3 +317,18 @@ def test_signal_used_as_integer_is_rejected_with_the_reason(ops_tape, art_dir):
     err = ctypes.create_string_buffer(512)
     assert L.tape_host_build(ctypes.addressof(buf), len(wasm), info.ctypes.data, err, 512) == 1
     assert "used as an integer" in err.value.decode()
+
+
+def test_damaged_wasm_through_the_extractor_under_address_sanitizer(art_dir):
+    """tools/fuzz_wasm_extractor.py, bounded: 3 child processes x 8 damaged copies of the small test program (truncated,
+    bit flips in section headers, random bytes in type / function / element / code / data / name sections) through
+    build_witness_program compiled with -fsanitize=address: a message or a program, never a memory error."""
+    import importlib.util
+    if not os.path.exists(os.path.join(H.ROOT, "artifacts", "opsTest", "dev", "1", "circuit.wasm")):
+        pytest.skip("artifacts/opsTest not generated (run __graft_entry__.build())")
+    spec = importlib.util.spec_from_file_location("fuzz_wasm_extractor", os.path.join(H.ROOT, "tools", "fuzz_wasm_extractor.py"))
+    F = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(F)
+    clean, failures = F.run(3, first_seed=132, n_mutants=8, timeout=600)
+    assert not failures, failures[0][1][-1500:]
+    assert clean == 3

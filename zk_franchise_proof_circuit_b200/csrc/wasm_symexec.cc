@@ -84,7 +84,7 @@ struct Rd {
   }
   std::string str() {
     size_t l = (size_t)leb();
-    if (p + l > end) { ok = false; return ""; }
+    if (!ok || p > end || l > end - p) { ok = false; return ""; }
     std::string s((const char *)b + p, l);
     p += l;
     return s;
@@ -148,22 +148,25 @@ struct Machine {
     std::vector<Seg> segs;
     while (r.p < bin_len && r.ok) {
       uint8_t id = r.u8();
-      size_t size = (size_t)r.leb(), end = r.p + size;
-      if (end > bin_len) { err = "truncated section"; return false; }
+      const size_t size = (size_t)r.leb();
+      if (!r.ok || size > bin_len - r.p) { err = "truncated section"; return false; }
+      const size_t end = r.p + size;
       Rd s{bin, r.p, end};
+      // every vector of a section has at least one byte per element: a count above the section size is damage
+      auto count = [&]() -> uint64_t { uint64_t n = s.leb(); if (n > size) { s.ok = false; return 0; } return n; };
       if (id == 1) {
-        uint64_t n = s.leb();
+        uint64_t n = count();
         for (uint64_t i = 0; i < n; i++) {
           if (s.u8() != 0x60) { err = "bad type section"; return false; }
           FuncType t;
-          uint64_t np = s.leb();
+          uint64_t np = count();
           for (uint64_t k = 0; k < np; k++) t.params.push_back(s.u8());
-          uint64_t nr = s.leb();
+          uint64_t nr = count();
           for (uint64_t k = 0; k < nr; k++) t.results.push_back(s.u8());
           types.push_back(t);
         }
       } else if (id == 2) {
-        uint64_t n = s.leb();
+        uint64_t n = count();
         for (uint64_t i = 0; i < n; i++) {
           s.str();
           std::string nm = s.str();
@@ -173,7 +176,7 @@ struct Machine {
         }
         n_imports = (uint32_t)n;
       } else if (id == 3) {
-        uint64_t n = s.leb();
+        uint64_t n = count();
         for (uint64_t i = 0; i < n; i++) ftypes.push_back((uint32_t)s.leb());
       } else if (id == 5) {
         uint64_t n = s.leb();
@@ -182,7 +185,7 @@ struct Machine {
         mem_pages = (uint32_t)s.leb();
         if (fl & 1) s.leb();
       } else if (id == 7) {
-        uint64_t n = s.leb();
+        uint64_t n = count();
         for (uint64_t i = 0; i < n; i++) {
           std::string nm = s.str();
           uint8_t kind = s.u8();
@@ -190,20 +193,22 @@ struct Machine {
           if (kind == 0) exports[nm] = idx;
         }
       } else if (id == 9) {
-        uint64_t n = s.leb();
+        uint64_t n = count();
         for (uint64_t i = 0; i < n; i++) {
           if (s.leb() != 0 || s.u8() != 0x41) { err = "unsupported element segment"; return false; }
           int64_t off = s.sleb();
           if (s.u8() != 0x0b) { err = "unsupported element segment"; return false; }
-          uint64_t cnt = s.leb();
+          uint64_t cnt = count();
+          if (!s.ok || off < 0 || off > (1 << 20) || cnt > (1u << 20)) { err = "implausible element segment"; return false; }
           if (table.size() < (size_t)off + cnt) table.resize((size_t)off + cnt, ~0u);
           for (uint64_t k = 0; k < cnt; k++) table[(size_t)off + k] = (uint32_t)s.leb();
         }
       } else if (id == 10) {
-        uint64_t n = s.leb();
+        uint64_t n = count();
         if (n != ftypes.size()) { err = "function / code section mismatch"; return false; }
         for (uint64_t i = 0; i < n; i++) {
           size_t bs = (size_t)s.leb();
+          if (!s.ok || bs > end - s.p) { err = "function body outside the code section"; return false; }
           Func f;
           f.type = ftypes[i];
           f.start = s.p;
@@ -212,13 +217,13 @@ struct Machine {
           s.p += bs;
         }
       } else if (id == 11) {
-        uint64_t n = s.leb();
+        uint64_t n = count();
         for (uint64_t i = 0; i < n; i++) {
           if (s.leb() != 0 || s.u8() != 0x41) { err = "unsupported data segment"; return false; }
           int64_t off = s.sleb();
           if (s.u8() != 0x0b) { err = "unsupported data segment"; return false; }
           size_t l = (size_t)s.leb();
-          if (s.p + l > end) { err = "truncated data segment"; return false; }
+          if (!s.ok || l > end - s.p) { err = "truncated data segment"; return false; }
           segs.push_back({(uint32_t)off, bin + s.p, l});
           s.p += l;
         }
@@ -227,9 +232,10 @@ struct Machine {
           while (s.p < end && s.ok) {
             uint8_t sub = s.u8();
             size_t ssz = (size_t)s.leb(), send = s.p + ssz;
+            if (ssz > end - s.p) { s.ok = false; break; }
             if (sub == 1) {
-              uint64_t n = s.leb();
-              for (uint64_t i = 0; i < n; i++) { uint32_t fi = (uint32_t)s.leb(); names[fi] = s.str(); }
+              uint64_t n = count();
+              for (uint64_t i = 0; i < n && s.ok; i++) { uint32_t fi = (uint32_t)s.leb(); names[fi] = s.str(); }
             }
             s.p = send;
           }
@@ -238,6 +244,8 @@ struct Machine {
       if (!s.ok) { err = "malformed section"; return false; }
       r.p = end;
     }
+    for (uint32_t t : import_types) if (t >= types.size()) { err = "import with an undefined type"; return false; }
+    for (auto &f : funcs) if (f.type >= types.size()) { err = "function with an undefined type"; return false; }
     if (!mem_pages || mem_pages > 16384) { err = "memory size"; return false; }
     mem.assign((size_t)mem_pages << 16, 0);
     symbits.assign(mem.size() / 64 + 8, 0);
@@ -449,6 +457,8 @@ struct Machine {
     has_result = false;
     for (auto &a : args)
       if (a.tag) throw Unsupported{"a value derived from a signal is passed to a function as an integer"};
+    static const size_t need[] = {0, 3, 2, 2, 3, 1, 1};      // RT_NONE, RT_BIN, RT_UN, RT_COPY, RT_COPYN, RT_ISTRUE, RT_TOINT
+    if (args.size() < need[info.kind]) throw Unsupported{"a function of the field runtime has an unexpected signature: " + names[fi]};
     switch (info.kind) {
       case RT_BIN: {
         uint32_t dst = (uint32_t)args[0].v, a = (uint32_t)args[1].v, b = (uint32_t)args[2].v;
@@ -748,6 +758,7 @@ struct Machine {
             if (idx >= table.size() || table[idx] == ~0u) throw Unsupported{"call_indirect outside the table"};
             fi = table[idx];
           }
+          if (fi >= n_imports && fi - n_imports >= funcs.size()) throw Unsupported{"call of an undefined function"};
           const FuncType &t = fi < n_imports ? types[import_types[fi]] : types[funcs[fi - n_imports].type];
           std::vector<Val> args(t.params.size());
           for (size_t i = args.size(); i-- > 0;) args[i] = pop();
