@@ -306,3 +306,85 @@ def test_ntt_pass_model_radix4_equals_radix2_and_the_dft():
     for k in rnd.sample(range(n), 64):
         want = sum(x[j] * pw[(j * k) % n] for j in range(n)) % P
         assert got[int(format(k, "011b")[::-1], 2)] == want
+
+
+def test_host_parsers_on_damaged_documents_under_address_sanitizer(tmp_path):
+    """tests/host_emul/parsers_asan.cc: the JSON parsers, the census-wasm recogniser and the .zkey reader built with
+    -fsanitize=address on truncated / spliced / bit-flipped documents (held in exact-size heap buffers): they accept or
+    reject, never read outside the buffer.  (The generic extractor has its own run in test_witness_program.py.)"""
+    import random
+    exe = str(tmp_path / "parsers_asan")
+    csrc = os.path.join(H.ROOT, "zk_franchise_proof_circuit_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=address", "-std=c++17", "-o", exe,
+                           os.path.join(H.ROOT, "tests", "host_emul", "parsers_asan.cc")] +
+                          [os.path.join(csrc, n) for n in ("json_io.cc", "wasm_circuit.cc", "zkey.cc")])
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0")
+    rnd = random.Random(9)
+    m = str(tmp_path / "m.bin")
+
+    def run(kind, data):
+        open(m, "wb").write(bytes(data))
+        r = subprocess.run([exe, kind, m], capture_output=True, text=True, env=env, timeout=120)
+        assert r.returncode == 0, (kind, r.stderr[:2000])
+        return int(r.stdout.strip())
+    docs = [open(os.path.join(H.GOLDEN, n), "rb").read() for n in ("inputs_example.json", "proof.json", "verification_key.json", "signals.json")]
+    assert run("json", docs[0]) & 1 and run("json", docs[3]) & 4
+    specials = [b"", b"{", b"[", b"\"", b"{\"a\":", b"{\"a\":[", b"{\"a\":\"", b"[\"1\",", b"[" * 5000, b"{\"a\":" + b"9" * 5000 + b"}",
+                b"{\"a\":\"" + b"9" * 5000 + b"\"}", b"[-1]", b"{\"a\":1e5}", b"{\"a\":[1,2,],}", b"\xff\xfe{}"]
+    for d in specials:
+        run("json", d)
+    for t in range(120):
+        d = bytearray(rnd.choice(docs))
+        k = t % 4
+        if k == 0:
+            d = d[:rnd.randrange(0, len(d))]
+        elif k == 1:
+            for _ in range(rnd.randrange(1, 6)):
+                d[rnd.randrange(len(d))] = rnd.choice(b"{}[]\",:0123456789 \n\\-eE.x\x00\xff")
+        elif k == 2:
+            i = rnd.randrange(len(d))
+            d[i:i] = bytes(rnd.choice(b"{}[]\",:") for _ in range(rnd.randrange(1, 30)))
+        else:
+            i = rnd.randrange(len(d))
+            del d[i:min(len(d), i + rnd.randrange(1, 200))]
+        run("json", d)
+    art = os.path.join(H.ROOT, "artifacts", "zkCensus", "dev", "160")
+    if not os.path.exists(art + "/circuit.wasm"):
+        return
+    wasm = open(art + "/circuit.wasm", "rb").read()
+    assert run("wasm", wasm) == 1
+    for t in range(24):
+        d = bytearray(wasm)
+        if t % 3 == 0:
+            d = d[:rnd.randrange(8, len(d))]
+        elif t % 3 == 1:
+            for _ in range(rnd.randrange(1, 6)):
+                d[rnd.randrange(0, 4096)] ^= 1 << rnd.randrange(8)
+        else:
+            for _ in range(rnd.randrange(1, 12)):
+                d[rnd.randrange(len(d) - 600000, len(d))] = rnd.randrange(256)
+        run("wasm", d)
+    zpath = os.path.join(H.ROOT, "artifacts", "opsTest", "dev", "1", "proving_key.zkey")
+    if not os.path.exists(zpath):
+        return
+    zkey = open(zpath, "rb").read()
+    assert run("zkey", zkey) == 1
+    offs, p = [], 12
+    while p + 12 <= len(zkey):
+        offs.append(p)
+        p += 12 + int.from_bytes(zkey[p + 4:p + 12], "little")
+    for t in range(80):
+        z = bytearray(zkey)
+        if t % 4 == 0:
+            z = z[:rnd.randrange(0, len(z))]
+        elif t % 4 == 1:
+            for _ in range(rnd.randrange(1, 5)):
+                z[rnd.randrange(0, 600)] ^= 1 << rnd.randrange(8)
+        elif t % 4 == 2:
+            for _ in range(rnd.randrange(1, 5)):
+                z[rnd.randrange(0, len(z))] = rnd.randrange(256)
+        else:
+            o = rnd.choice(offs)                    # a section id / length / first count field
+            for _ in range(rnd.randrange(1, 3)):
+                z[o + rnd.randrange(0, 24)] = rnd.randrange(256)
+        run("zkey", z)
